@@ -1,0 +1,104 @@
+"""ctypes binding of libb200gs.so (the C ABI declared in include/b200gs.h).
+
+There is no CPU fallback: importing this module without the built library, or calling into it without
+a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint32,
+                    c_void_p)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200gs.so")
+
+OK = 0
+ERR_CAPACITY = -5
+TILE = 16
+
+
+class Gaussians(Structure):
+    _fields_ = [("n", c_int32), ("pos", c_void_p), ("opacity_raw", c_void_p), ("scale_raw", c_void_p),
+                ("q_raw", c_void_p), ("sigma", c_void_p), ("f_dc", c_void_p), ("f_rest", c_void_p),
+                ("color", c_void_p)]
+
+
+class Camera(Structure):
+    _fields_ = [("c2w", c_void_p), ("H", c_int32), ("W", c_int32), ("fx", c_double), ("fy", c_double),
+                ("cx", c_double), ("cy", c_double), ("near_plane", c_double), ("far_plane", c_double),
+                ("pix_guard", c_double), ("min_conis", c_double), ("chi_square_clip", c_double),
+                ("alpha_max", c_double), ("alpha_cutoff", c_double), ("tile", c_int32),
+                ("tile_row_begin", c_int32), ("tile_row_end", c_int32)]
+
+
+class Grads(Structure):
+    _fields_ = [("pos", c_void_p), ("opacity_raw", c_void_p), ("scale_raw", c_void_p), ("q_raw", c_void_p),
+                ("sigma", c_void_p), ("f_dc", c_void_p), ("f_rest", c_void_p), ("color", c_void_p)]
+
+
+class Sizes(Structure):
+    _fields_ = [("frame_bytes", c_size_t), ("isect_bytes", c_size_t)]
+
+
+class FrameStats(Structure):
+    _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
+                ("n_in_frustum", c_uint32), ("reserved", c_uint32 * 12)]
+
+
+# every symbol include/b200gs.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b200gs_abi_version": (c_int, []),
+    "b200gs_last_error": (c_char_p, []),
+    "b200gs_workspace_sizes": (c_int, [c_int32, c_int32, c_int32, c_uint32, POINTER(Sizes)]),
+    "b200gs_build_sigma": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200gs_build_sigma_backward": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200gs_evaluate_sh": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200gs_evaluate_sh_backward": (c_int, [c_int32] + [c_void_p] * 10),
+    "b200gs_render_project": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b200gs_render_rasterize": (c_int, [POINTER(Camera), c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_uint32,
+                                        c_void_p, c_void_p, c_void_p]),
+    "b200gs_render_backward": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, c_void_p, c_size_t,
+                                       c_uint32, c_void_p, POINTER(Grads), c_void_p]),
+    "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
+    "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
+    "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
+    "b200gs_exclusive_scan_u32": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200gs_scan_scratch_bytes": (c_size_t, [c_uint32]),
+    "b200gs_radix_sort_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_void_p,
+                                        c_size_t, c_void_p]),
+    "b200gs_sort_scratch_bytes": (c_size_t, [c_uint32]),
+}
+
+_lib = None
+
+
+class B200GSError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libb200gs.so and type every entry point.  Fails loudly when the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200GSError(
+            f"{LIB_PATH} is missing: build it with `python 3d-gaussian-splatting-for-novel-view-synthesis_b200/"
+            "build.py` (or __graft_entry__.build()).  b200gs has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200gs_abi_version() != 1:
+        raise B200GSError("libb200gs.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != OK:
+        msg = load().b200gs_last_error()
+        raise B200GSError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")

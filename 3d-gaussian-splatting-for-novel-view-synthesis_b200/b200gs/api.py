@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference's render-path interface (same names, arguments and error
+behaviour), backed by the CUDA kernels of libb200gs.
+
+Reference signatures mirrored (paths relative to the reference checkout):
+  gaussian_splatting/gaussian.py:71             build_sigma_from_params(scale_raw, q_raw) -> [N,3,3]
+  gaussian_splatting/spherical_harmonics.py:70  evaluate_sh(f_dc, f_rest, points, c2w) -> [N,3]
+  gaussian_splatting/render.py:62-64            render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
+                                                       near, far, pix_guard, T, min_conis, chi_square_clip,
+                                                       alpha_max, alpha_cutoff) -> [H,W,3]
+
+Fusion across the three calls: the tensors returned by `build_sigma_from_params` / `evaluate_sh` carry
+a tag naming the leaves they were computed from.  When `render` receives tagged `sigma` / `color` whose
+sources are unchanged (and `color` was evaluated at the same points and pose), it runs the fused
+kernels straight from the raw parameters, so gradients flow to scale_raw / q_raw / f_dc / f_rest / pos
+in one preprocess-backward kernel; otherwise it consumes `sigma` / `color` as given, exactly like the
+reference.  Callers need no change (scripts/train.py:463,502,505-508 keep working verbatim).
+"""
+from __future__ import annotations
+
+import os
+import weakref
+
+import torch
+
+from . import ops
+
+_TAG = "_b200gs_src"
+
+
+def _fusion_enabled() -> bool:
+    return os.environ.get("B200GS_FUSE", "1") != "0"
+
+
+class _Source:
+    """What a derived tensor was computed from (weak references + version counters)."""
+
+    def __init__(self, *tensors):
+        self.refs = [weakref.ref(t) for t in tensors]
+        self.versions = [t._version for t in tensors]
+
+    def resolve(self):
+        out = []
+        for r, v in zip(self.refs, self.versions):
+            t = r()
+            if t is None or t._version != v:
+                return None
+            out.append(t)
+        return out
+
+
+def build_sigma_from_params(scale_raw: torch.Tensor, q_raw: torch.Tensor) -> torch.Tensor:
+    """Sigma = R S S^T R^T with s = max(exp(scale_raw), 1e-6), q normalised (gaussian.py:71-127)."""
+    ops._require_cuda(scale_raw, "scale_raw")
+    sigma = ops._BuildSigma.apply(scale_raw, q_raw)
+    setattr(sigma, _TAG, _Source(scale_raw, q_raw))
+    return sigma
+
+
+def evaluate_sh(f_dc: torch.Tensor, f_rest: torch.Tensor, points: torch.Tensor, c2w: torch.Tensor) -> torch.Tensor:
+    """sigmoid(sum_k sh_k Y_k(dir)), degree-3 real SH with the reference's signs (spherical_harmonics.py:70-166)."""
+    ops._require_cuda(points, "points")
+    if f_rest.dim() != 2 or f_rest.shape[1] != 45:
+        raise RuntimeError(f"evaluate_sh expects f_rest of shape [N,45], got {tuple(f_rest.shape)}")
+    c2w_d = c2w.to(device=points.device)
+    color = ops._EvaluateSH.apply(f_dc, f_rest, points, c2w_d)
+    setattr(color, _TAG, _Source(f_dc, f_rest, points, c2w))
+    return color
+
+
+def render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
+           near=0.01, far=100.0, pix_guard=32, T=16, min_conis=1e-6,
+           chi_square_clip=6.25, alpha_max=0.99, alpha_cutoff=1 / 128., *, tile_rows=None):
+    """Drop-in for render.py:62-410.  Returns [H,W,3] in [0,1], same dtype/device as `pos`.
+
+    `tile_rows=(begin, end)` (keyword-only extension) renders only that band of 16-pixel tile rows; the
+    rest of the image is zero (tile-row sharding of large frames across GPUs)."""
+    ops._require_cuda(pos, "pos")
+    H, W = int(H), int(W)           # callers pass Python ints, 0-dim tensors (train.py:499) or floats
+    cfg = ops.RenderConfig(H=H, W=W, fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), near=float(near),
+                           far=float(far), pix_guard=float(pix_guard), T=int(T), min_conis=float(min_conis),
+                           chi_square_clip=float(chi_square_clip), alpha_max=float(alpha_max),
+                           alpha_cutoff=float(alpha_cutoff))
+    if tile_rows is not None:
+        cfg.tile_row_begin, cfg.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
+    c2w_d = ops._f32c(c2w.to(device=pos.device))
+    scale_raw = q_raw = f_dc = f_rest = None
+    if _fusion_enabled():
+        src = getattr(sigma, _TAG, None)
+        got = src.resolve() if src is not None else None
+        if got is not None:
+            scale_raw, q_raw = got
+        src = getattr(color, _TAG, None)
+        got = src.resolve() if src is not None else None
+        if got is not None and got[2] is pos and (got[3] is c2w or torch.equal(got[3].to(c2w_d.device), c2w_d)):
+            f_dc, f_rest = got[0], got[1]
+    strict = os.environ.get("B200GS_STRICT_OFFSCREEN", "1") != "0"
+    image = ops._Rasterize.apply(pos, opacity_raw,
+                                 scale_raw, q_raw, None if scale_raw is not None else sigma,
+                                 f_dc, f_rest, None if f_dc is not None else color,
+                                 c2w_d, cfg, strict)
+    return image if image.dtype == pos.dtype else image.to(pos.dtype)

@@ -1,0 +1,304 @@
+"""torch-side plumbing for libb200gs: device buffers, streams and the autograd bridge.
+
+PyTorch is used for memory (caching allocator), streams and autograd bookkeeping only; all
+arithmetic happens in the hand-written CUDA kernels behind the C ABI (include/b200gs.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Camera, FrameStats, Gaussians, Grads, Sizes
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.B200GSError(
+            f"b200gs: `{name}` lives on {t.device}; this rasterizer runs on CUDA (sm_100a) only and has no CPU "
+            "fallback.")
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class RenderConfig:
+    """The non-tensor arguments of render.py:62-64 plus the tile-row band of this rank."""
+    H: int
+    W: int
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    near: float = 0.01
+    far: float = 100.0
+    pix_guard: float = 32
+    T: int = 16
+    min_conis: float = 1e-6
+    chi_square_clip: float = 6.25
+    alpha_max: float = 0.99
+    alpha_cutoff: float = 1 / 128.
+    tile_row_begin: int = 0
+    tile_row_end: int = 0
+
+    def to_c(self, c2w: torch.Tensor) -> Camera:
+        if int(self.T) != _lib.TILE:
+            raise NotImplementedError(f"b200gs renders with T=16 tiles only (got T={self.T}); the reference's "
+                                      "callers never change T")
+        return Camera(c2w=c2w.data_ptr(), H=int(self.H), W=int(self.W), fx=float(self.fx), fy=float(self.fy),
+                      cx=float(self.cx), cy=float(self.cy), near_plane=float(self.near), far_plane=float(self.far),
+                      pix_guard=float(self.pix_guard), min_conis=float(self.min_conis),
+                      chi_square_clip=float(self.chi_square_clip), alpha_max=float(self.alpha_max),
+                      alpha_cutoff=float(self.alpha_cutoff), tile=int(self.T),
+                      tile_row_begin=int(self.tile_row_begin), tile_row_end=int(self.tile_row_end))
+
+
+_pinned_stats = {}
+
+
+def _stats_buffer(device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _pinned_stats.get(key)
+    if buf is None:
+        buf = torch.zeros(16, dtype=torch.int32).pin_memory()
+        _pinned_stats[key] = buf
+    return buf
+
+
+# Intersection-capacity policy.  "sync" (default): read I back between project and rasterize (one
+# stream sync per frame, exact buffers).  "speculative": size the lists from a per-device high-water mark
+# and launch everything without a mid-frame sync; the overflow flag is checked when the frame's stats
+# are read (end of frame) and the frame is re-rasterized with exact buffers if it did not fit.
+_high_water = {}
+
+
+class Frame:
+    """One rendered view: owns the workspaces the backward needs."""
+
+    def __init__(self, g: Gaussians, keep, cam_cfg: RenderConfig, c2w: torch.Tensor, device):
+        self.g, self.keep, self.cfg, self.c2w, self.device = g, keep, cam_cfg, c2w, device
+        self.cam = cam_cfg.to_c(c2w)
+        self.frame_ws = None
+        self.isect_ws = None
+        self.capacity = 0
+        self.n_isect = 0
+        self.n_visible = 0
+        self.n_in_frustum = 0
+
+    # -- forward ----------------------------------------------------------------------------------------
+    def render(self, mode: Optional[str] = None) -> torch.Tensor:
+        lib = _lib.load()
+        dev = self.device
+        n = int(self.g.n)
+        H, W = int(self.cfg.H), int(self.cfg.W)
+        mode = mode or os.environ.get("B200GS_CAPACITY_MODE", "sync")
+        sizes = Sizes()
+        _lib.check(lib.b200gs_workspace_sizes(n, H, W, 0, ctypes.byref(sizes)), "workspace_sizes")
+        self.frame_ws = torch.empty(sizes.frame_bytes, dtype=torch.uint8, device=dev)
+        stats = _stats_buffer(dev)
+        st = _stream(dev)
+        image = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+        spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
+        _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
+                                             sizes.frame_bytes, None if spec_cap else ctypes.c_void_p(stats.data_ptr()),
+                                             st), "render_project")
+        if spec_cap:
+            self._rasterize(lib, n, H, W, spec_cap, image, stats, st)
+            torch.cuda.current_stream(dev).synchronize()
+            self._read_stats(stats)
+            if self.n_isect > spec_cap:           # did not fit: redo with exact buffers
+                self._rasterize(lib, n, H, W, self._grow(self.n_isect), image, stats, st)
+                torch.cuda.current_stream(dev).synchronize()
+                self._read_stats(stats)
+        else:
+            torch.cuda.current_stream(dev).synchronize()
+            self._read_stats(stats)
+            self._rasterize(lib, n, H, W, self._grow(self.n_isect) if mode == "speculative" else max(self.n_isect, 1),
+                            image, None, st)
+        return image
+
+    def _grow(self, need: int) -> int:
+        cap = max(int(need * 1.25) + 1024, _high_water.get(self.device.index, 0))
+        _high_water[self.device.index] = cap
+        return cap
+
+    def _read_stats(self, stats: torch.Tensor):
+        s = FrameStats.from_buffer_copy(stats.numpy().tobytes())
+        self.n_isect, self.n_visible, self.n_in_frustum = int(s.n_isect), int(s.n_visible), int(s.n_in_frustum)
+
+    def _rasterize(self, lib, n, H, W, capacity, image, stats, st):
+        sizes = Sizes()
+        _lib.check(lib.b200gs_workspace_sizes(n, H, W, capacity, ctypes.byref(sizes)), "workspace_sizes")
+        self.capacity = capacity
+        self.isect_ws = torch.empty(sizes.isect_bytes, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.b200gs_render_rasterize(ctypes.byref(self.cam), n, _ptr(self.frame_ws), self.frame_ws.numel(),
+                                               _ptr(self.isect_ws), sizes.isect_bytes, capacity, _ptr(image),
+                                               None if stats is None else ctypes.c_void_p(stats.data_ptr()), st),
+                   "render_rasterize")
+
+    # -- backward ---------------------------------------------------------------------------------------
+    def backward(self, grad_image: torch.Tensor, grads: Grads):
+        lib = _lib.load()
+        _lib.check(lib.b200gs_render_backward(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
+                                              self.frame_ws.numel(), _ptr(self.isect_ws), self.isect_ws.numel(),
+                                              self.capacity, _ptr(grad_image), ctypes.byref(grads),
+                                              _stream(self.device)), "render_backward")
+
+    # -- introspection (parity tests) -------------------------------------------------------------------
+    def export(self):
+        lib = _lib.load()
+        n, dev = int(self.g.n), self.device
+        H, W = int(self.cfg.H), int(self.cfg.W)
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        i = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        out = dict(xy=f(n, 2), depth=f(n), conic=f(n, 3), opacity=f(n), color=f(n, 3), radius=i(n), rect=i(n, 4),
+                   tiles_touched=i(n), depth_order=i(n))
+        _lib.check(lib.b200gs_debug_export(n, _ptr(self.frame_ws), self.frame_ws.numel(), H, W, _ptr(out["xy"]),
+                                           _ptr(out["depth"]), _ptr(out["conic"]), _ptr(out["opacity"]),
+                                           _ptr(out["color"]), _ptr(out["radius"]), _ptr(out["rect"]),
+                                           _ptr(out["tiles_touched"]), _ptr(out["depth_order"]), _stream(dev)),
+                   "debug_export")
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        cnt = min(self.n_isect, self.capacity)
+        out.update(list_tile=i(max(cnt, 1)), list_id=i(max(cnt, 1)), ranges=i(tiles, 2))
+        _lib.check(lib.b200gs_debug_export_lists(_ptr(self.frame_ws), self.frame_ws.numel(), _ptr(self.isect_ws),
+                                                 self.isect_ws.numel(), self.capacity, n, H, W, _ptr(out["list_tile"]),
+                                                 _ptr(out["list_id"]), cnt, _ptr(out["ranges"]), _stream(dev)),
+                   "debug_export_lists")
+        out["list_tile"], out["list_id"] = out["list_tile"][:cnt], out["list_id"][:cnt]
+        torch.cuda.current_stream(dev).synchronize()
+        return {k: v.cpu() for k, v in out.items()}
+
+
+def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
+    keep = [_f32c(t) for t in (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)]
+    pos_, op_, sr_, q_, sg_, dc_, fr_, col_ = keep
+    n = pos_.shape[0]
+    if op_.numel() != n:
+        raise ValueError("opacity_raw must have one entry per Gaussian")
+    if fr_ is not None and (fr_.dim() != 2 or fr_.shape[1] != 45):
+        raise ValueError("f_rest must be [N,45] (spherical_harmonics.py:125-127)")
+    g = Gaussians(n=n, pos=pos_.data_ptr(), opacity_raw=op_.data_ptr(),
+                  scale_raw=None if sr_ is None else sr_.data_ptr(), q_raw=None if q_ is None else q_.data_ptr(),
+                  sigma=None if sg_ is None else sg_.data_ptr(), f_dc=None if dc_ is None else dc_.data_ptr(),
+                  f_rest=None if fr_ is None else fr_.data_ptr(), color=None if col_ is None else col_.data_ptr())
+    return g, keep
+
+
+class _Rasterize(torch.autograd.Function):
+    """render.py:62-410 (+ gaussian.py / spherical_harmonics.py when raw parameters are given)."""
+
+    @staticmethod
+    def forward(ctx, pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg, strict):
+        dev = pos.device
+        g, keep = _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)
+        with torch.cuda.device(dev):
+            frame = Frame(g, keep, cfg, c2w, dev)
+            image = frame.render()
+        if strict and frame.n_in_frustum > 0 and frame.n_visible == 0:
+            raise Exception("All projected points are off-screen")      # render.py:235-236
+        ctx.frame = frame
+        ctx.shapes = [None if t is None else (t.shape, t.dtype) for t in
+                      (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)]
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        frame: Frame = ctx.frame
+        dev = frame.device
+        gi = _f32c(grad_image)
+        n = int(frame.g.n)
+        names = ("pos", "opacity_raw", "scale_raw", "q_raw", "sigma", "f_dc", "f_rest", "color")
+        dims = dict(pos=(n, 3), opacity_raw=(n,), scale_raw=(n, 3), q_raw=(n, 4), sigma=(n, 3, 3), f_dc=(n, 3),
+                    f_rest=(n, 45), color=(n, 3))
+        out = {}
+        for name, src in zip(names, frame.keep):
+            out[name] = None if src is None else torch.empty(dims[name], dtype=torch.float32, device=dev)
+        grads = Grads(**{k: (None if v is None else v.data_ptr()) for k, v in out.items()})
+        with torch.cuda.device(dev):
+            frame.backward(gi, grads)
+        res = []
+        for name, meta in zip(names, ctx.shapes):
+            gten = out[name]
+            if gten is None or meta is None:
+                res.append(None)
+            else:
+                res.append(gten.reshape(meta[0]).to(meta[1]))
+        ctx.frame = None
+        return (*res, None, None, None)
+
+
+class _BuildSigma(torch.autograd.Function):
+    """gaussian.py:71-127."""
+
+    @staticmethod
+    def forward(ctx, scale_raw, q_raw):
+        lib = _lib.load()
+        sr, q = _f32c(scale_raw), _f32c(q_raw)
+        n = sr.shape[0]
+        out = torch.empty((n, 3, 3), dtype=torch.float32, device=sr.device)
+        with torch.cuda.device(sr.device):
+            _lib.check(lib.b200gs_build_sigma(n, _ptr(sr), _ptr(q), _ptr(out), _stream(sr.device)), "build_sigma")
+        ctx.save_for_backward(sr, q)
+        ctx.dtypes = (scale_raw.dtype, q_raw.dtype)
+        return out.to(scale_raw.dtype)
+
+    @staticmethod
+    def backward(ctx, g_sigma):
+        lib = _lib.load()
+        sr, q = ctx.saved_tensors
+        n = sr.shape[0]
+        gs = _f32c(g_sigma)
+        g_sr, g_q = torch.empty_like(sr), torch.empty_like(q)
+        with torch.cuda.device(sr.device):
+            _lib.check(lib.b200gs_build_sigma_backward(n, _ptr(sr), _ptr(q), _ptr(gs), _ptr(g_sr), _ptr(g_q),
+                                                       _stream(sr.device)), "build_sigma_backward")
+        return g_sr.to(ctx.dtypes[0]), g_q.to(ctx.dtypes[1])
+
+
+class _EvaluateSH(torch.autograd.Function):
+    """spherical_harmonics.py:70-166."""
+
+    @staticmethod
+    def forward(ctx, f_dc, f_rest, points, c2w):
+        lib = _lib.load()
+        dc, fr, pts, cw = _f32c(f_dc), _f32c(f_rest), _f32c(points), _f32c(c2w)
+        n = pts.shape[0]
+        out = torch.empty((n, 3), dtype=torch.float32, device=pts.device)
+        with torch.cuda.device(pts.device):
+            _lib.check(lib.b200gs_evaluate_sh(n, _ptr(dc), _ptr(fr), _ptr(pts), _ptr(cw), _ptr(out),
+                                              _stream(pts.device)), "evaluate_sh")
+        ctx.save_for_backward(dc, fr, pts, cw)
+        ctx.dtypes = (f_dc.dtype, f_rest.dtype, points.dtype)
+        return out.to(points.dtype)
+
+    @staticmethod
+    def backward(ctx, g_color):
+        lib = _lib.load()
+        dc, fr, pts, cw = ctx.saved_tensors
+        n = pts.shape[0]
+        gc = _f32c(g_color)
+        g_dc, g_fr, g_pts = torch.empty_like(dc), torch.empty_like(fr), torch.empty_like(pts)
+        with torch.cuda.device(pts.device):
+            _lib.check(lib.b200gs_evaluate_sh_backward(n, _ptr(dc), _ptr(fr), _ptr(pts), _ptr(cw), _ptr(gc), _ptr(g_dc),
+                                                       _ptr(g_fr), _ptr(g_pts), _stream(pts.device)),
+                       "evaluate_sh_backward")
+        return g_dc.to(ctx.dtypes[0]), g_fr.to(ctx.dtypes[1]), g_pts.to(ctx.dtypes[2]), None

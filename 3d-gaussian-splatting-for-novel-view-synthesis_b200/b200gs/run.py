@@ -1,0 +1,33 @@
+"""Run a reference script unchanged on the b200gs render path:
+
+    python -m b200gs.run /path/to/reference/scripts/render_trained.py --checkpoint ... [args]
+
+Equivalent to `install()` followed by executing the script as __main__.  The reference checkout must
+be importable: its root is derived from the script location (<root>/scripts/x.py) or taken from
+$B200GS_REFERENCE_ROOT.
+"""
+from __future__ import annotations
+
+import os
+import runpy
+import sys
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        print(__doc__)
+        return 2
+    script = os.path.abspath(argv[0])
+    root = os.environ.get("B200GS_REFERENCE_ROOT") or os.path.dirname(os.path.dirname(script))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from .install import install
+    install()
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

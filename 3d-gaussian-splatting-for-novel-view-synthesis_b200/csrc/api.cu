@@ -1,0 +1,404 @@
+// C ABI of libb200gs (see include/b200gs.h for the contract and the reference interfaces replaced).
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what) {
+  g_last_error = what;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+  return B200GS_ERR_CUDA;
+}
+#define CU(expr)                                         \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return fail_cuda(_e, #expr);  \
+  } while (0)
+
+int tile_bits(int n_tiles) {
+  int b = 1;
+  while ((1 << b) < n_tiles) ++b;
+  return b;
+}
+
+int make_params(const b200gs_camera* cam, gs::RenderParams& rp) {
+  if (!cam || !cam->c2w) return fail(B200GS_ERR_ARG, "camera or c2w is null");
+  if (cam->tile != B200GS_TILE) return fail(B200GS_ERR_TILE, "only T=16 is supported");
+  if (cam->H <= 0 || cam->W <= 0) return fail(B200GS_ERR_ARG, "H and W must be positive");
+  if (cam->W > 65535 * 16 || cam->H > 65535 * 16) return fail(B200GS_ERR_ARG, "image too large");
+  gs::fill_render_params(rp, cam->H, cam->W, cam->fx, cam->fy, cam->cx, cam->cy, cam->near_plane, cam->far_plane,
+                         cam->pix_guard, cam->min_conis, cam->chi_square_clip, cam->alpha_max, cam->alpha_cutoff);
+  if (cam->tile_row_end > 0 || cam->tile_row_begin > 0) {
+    rp.row_begin = cam->tile_row_begin < 0 ? 0 : cam->tile_row_begin;
+    rp.row_end = cam->tile_row_end > rp.tiles_y ? rp.tiles_y : cam->tile_row_end;
+    if (rp.row_end < rp.row_begin) rp.row_end = rp.row_begin;
+  }
+  return B200GS_OK;
+}
+
+int make_gauss(const b200gs_gaussians* g, gs::GaussIn& o) {
+  if (!g) return fail(B200GS_ERR_ARG, "gaussians is null");
+  if (g->n < 0) return fail(B200GS_ERR_ARG, "n < 0");
+  if (g->n > 0) {
+    if (!g->pos || !g->opacity_raw) return fail(B200GS_ERR_ARG, "pos / opacity_raw missing");
+    const bool raw_cov = g->scale_raw && g->q_raw;
+    if (!raw_cov && !g->sigma) return fail(B200GS_ERR_ARG, "need (scale_raw, q_raw) or sigma");
+    const bool raw_sh = g->f_dc && g->f_rest;
+    if (!raw_sh && !g->color) return fail(B200GS_ERR_ARG, "need (f_dc, f_rest) or color");
+    if (raw_cov && (reinterpret_cast<uintptr_t>(g->q_raw) & 15u))
+      return fail(B200GS_ERR_ARG, "q_raw must be 16-byte aligned");
+  }
+  o.n = g->n; o.pos = g->pos; o.opacity_raw = g->opacity_raw;
+  const bool raw_cov = g->scale_raw && g->q_raw;
+  o.scale_raw = raw_cov ? g->scale_raw : nullptr;
+  o.q_raw = raw_cov ? g->q_raw : nullptr;
+  o.sigma = raw_cov ? nullptr : g->sigma;
+  const bool raw_sh = g->f_dc && g->f_rest;
+  o.f_dc = raw_sh ? g->f_dc : nullptr;
+  o.f_rest = raw_sh ? g->f_rest : nullptr;
+  o.color = raw_sh ? nullptr : g->color;
+  return B200GS_OK;
+}
+
+// where the tile sort leaves its result: pass 0 writes the *_alt buffers, so odd pass counts end there
+struct SortedLists { const uint32_t* keys; const uint32_t* vals; };
+SortedLists sorted_lists(void* isect_ws, const gs::IsectLayout& IL, int n_tiles) {
+  const int passes = (tile_bits(n_tiles) + 7) / 8;
+  SortedLists s;
+  if (passes % 2 == 0) { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals); }
+  else { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt); }
+  return s;
+}
+
+// --- debug export kernels -------------------------------------------------------------------------
+__global__ void export_kernel(int n, const float4* rec0, const float4* rec1, const float4* rec2,
+                              const uint32_t* depth_key, const uint2* rect, const uint32_t* tiles, float* xy,
+                              float* depth, float* conic, float* opacity, float* color, int32_t* radius,
+                              int32_t* rect_out, int32_t* tiles_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool vis = depth_key[i] != gs::kCulledKey;
+  const float4 a = vis ? rec0[i] : make_float4(0, 0, 0, 0), b = vis ? rec1[i] : make_float4(0, 0, 0, 0),
+               c = vis ? rec2[i] : make_float4(0, 0, 0, 0);
+  if (xy) { xy[2 * i] = a.x; xy[2 * i + 1] = a.y; }
+  if (depth) depth[i] = vis ? __uint_as_float(depth_key[i]) : -1.f;
+  if (conic) { conic[3 * i] = a.z; conic[3 * i + 1] = a.w; conic[3 * i + 2] = b.x; }
+  if (opacity) opacity[i] = b.y;
+  if (color) { color[3 * i] = b.z; color[3 * i + 1] = b.w; color[3 * i + 2] = c.x; }
+  if (radius) radius[i] = vis ? (int32_t)c.w : 0;
+  if (rect_out) {
+    const uint2 r = vis ? rect[i] : make_uint2(0, 0);
+    rect_out[4 * i] = r.x & 0xFFFF; rect_out[4 * i + 1] = r.x >> 16;
+    rect_out[4 * i + 2] = r.y & 0xFFFF; rect_out[4 * i + 3] = r.y >> 16;
+  }
+  if (tiles_out) tiles_out[i] = vis ? (int32_t)tiles[i] : -1;
+}
+
+__global__ void copy_u32_kernel(const uint32_t* src, int32_t* dst, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int32_t)src[i];
+}
+__global__ void copy_ranges_kernel(const uint2* src, int32_t* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { dst[2 * i] = (int32_t)src[i].x; dst[2 * i + 1] = (int32_t)src[i].y; }
+}
+
+// --- host-buffer path cache ------------------------------------------------------------------------
+struct HostPathCache {
+  std::mutex mu;
+  void* bufs[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t caps[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t stream = nullptr;
+  b200gs_frame_stats* stats_pinned = nullptr;
+  cudaError_t ensure(int slot, size_t bytes) {
+    if (caps[slot] >= bytes) return cudaSuccess;
+    if (bufs[slot]) cudaFree(bufs[slot]);
+    bufs[slot] = nullptr; caps[slot] = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&bufs[slot], want);
+    if (e == cudaSuccess) caps[slot] = want;
+    return e;
+  }
+};
+HostPathCache g_host;
+
+}  // namespace
+
+extern "C" {
+
+int b200gs_abi_version(void) { return B200GS_ABI_VERSION; }
+const char* b200gs_last_error(void) { return g_last_error.c_str(); }
+
+int b200gs_workspace_sizes(int32_t n, int32_t H, int32_t W, uint32_t isect_capacity, b200gs_sizes* out) {
+  if (!out || n < 0 || H <= 0 || W <= 0) return fail(B200GS_ERR_ARG, "bad arguments to workspace_sizes");
+  out->frame_bytes = gs::frame_layout(n, H, W).total;
+  out->isect_bytes = gs::isect_layout(isect_capacity).total;
+  return B200GS_OK;
+}
+
+int b200gs_build_sigma(int32_t n, const float* scale_raw, const float* q_raw, float* sigma_out, void* stream) {
+  if (n < 0 || (n > 0 && (!scale_raw || !q_raw || !sigma_out))) return fail(B200GS_ERR_ARG, "build_sigma: null");
+  if (reinterpret_cast<uintptr_t>(q_raw) & 15u) return fail(B200GS_ERR_ARG, "q_raw must be 16-byte aligned");
+  CU(gs::launch_build_sigma(n, scale_raw, q_raw, sigma_out, (cudaStream_t)stream));
+  return B200GS_OK;
+}
+
+int b200gs_build_sigma_backward(int32_t n, const float* scale_raw, const float* q_raw, const float* grad_sigma,
+                                float* grad_scale_raw, float* grad_q_raw, void* stream) {
+  if (n < 0 || (n > 0 && (!scale_raw || !q_raw || !grad_sigma || !grad_scale_raw || !grad_q_raw)))
+    return fail(B200GS_ERR_ARG, "build_sigma_backward: null");
+  if ((reinterpret_cast<uintptr_t>(q_raw) & 15u) || (reinterpret_cast<uintptr_t>(grad_q_raw) & 15u))
+    return fail(B200GS_ERR_ARG, "q_raw / grad_q_raw must be 16-byte aligned");
+  CU(gs::launch_build_sigma_bwd(n, scale_raw, q_raw, grad_sigma, grad_scale_raw, grad_q_raw, (cudaStream_t)stream));
+  return B200GS_OK;
+}
+
+int b200gs_evaluate_sh(int32_t n, const float* f_dc, const float* f_rest, const float* points, const float* c2w,
+                       float* color_out, void* stream) {
+  if (n < 0 || (n > 0 && (!f_dc || !f_rest || !points || !c2w || !color_out)))
+    return fail(B200GS_ERR_ARG, "evaluate_sh: null");
+  CU(gs::launch_eval_sh(n, f_dc, f_rest, points, c2w, color_out, (cudaStream_t)stream));
+  return B200GS_OK;
+}
+
+int b200gs_evaluate_sh_backward(int32_t n, const float* f_dc, const float* f_rest, const float* points,
+                                const float* c2w, const float* grad_color, float* grad_f_dc, float* grad_f_rest,
+                                float* grad_points, void* stream) {
+  if (n < 0 || (n > 0 && (!f_dc || !f_rest || !points || !c2w || !grad_color || !grad_f_dc || !grad_f_rest ||
+                          !grad_points)))
+    return fail(B200GS_ERR_ARG, "evaluate_sh_backward: null");
+  CU(gs::launch_eval_sh_bwd(n, f_dc, f_rest, points, c2w, grad_color, grad_f_dc, grad_f_rest, grad_points,
+                            (cudaStream_t)stream));
+  return B200GS_OK;
+}
+
+int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws, size_t frame_bytes,
+                          b200gs_frame_stats* stats_host, void* stream) {
+  gs::RenderParams rp;
+  gs::GaussIn gi;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  rc = make_gauss(g, gi);
+  if (rc) return rc;
+  if (!frame_ws) return fail(B200GS_ERR_ARG, "frame_ws is null");
+  const gs::FrameLayout L = gs::frame_layout(gi.n, rp.H, rp.W);
+  if (frame_bytes < L.total) return fail(B200GS_ERR_WORKSPACE, "frame workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
+  CU(cudaMemsetAsync(stats, 0, sizeof(b200gs_frame_stats), s));
+  if (gi.n > 0) {
+    CU(gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s));
+    // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
+    int in_a = 0;
+    CU(gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
+                             gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2), gs::ws_ptr<uint32_t>(frame_ws, L.order),
+                             gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
+                             (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
+                             &in_a, s));
+    if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
+    CU(gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
+                                 gs::ws_ptr<uint32_t>(frame_ws, L.offsets), (uint32_t)gi.n, &stats->n_isect,
+                                 gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
+  }
+  if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
+  return B200GS_OK;
+}
+
+int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
+                            size_t isect_bytes, uint32_t isect_capacity, float* image_out,
+                            b200gs_frame_stats* stats_host, void* stream) {
+  gs::RenderParams rp;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  if (!frame_ws || !image_out || n < 0) return fail(B200GS_ERR_ARG, "rasterize: null argument");
+  const gs::FrameLayout L = gs::frame_layout(n, rp.H, rp.W);
+  const gs::IsectLayout IL = gs::isect_layout(isect_capacity);
+  if (frame_bytes < L.total) return fail(B200GS_ERR_WORKSPACE, "frame workspace too small");
+  if (!isect_ws || isect_bytes < IL.total) return fail(B200GS_ERR_WORKSPACE, "isect workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
+  const int n_tiles = rp.tiles_x * rp.tiles_y;
+  uint32_t* keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys);
+  uint32_t* vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals);
+  CU(gs::launch_emit_pairs(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
+                           gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint2>(frame_ws, L.rect),
+                           rp.tiles_x, isect_capacity, keys, vals, stats, s));
+  int in_a = 0;
+  CU(gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
+                           gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_isect, 0,
+                           tile_bits(n_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s));
+  const SortedLists sl = sorted_lists(isect_ws, IL, n_tiles);
+  CU(gs::launch_tile_ranges(sl.keys, isect_capacity, stats, gs::ws_ptr<uint2>(frame_ws, L.ranges), n_tiles, s));
+  // pixels of tiles outside this rank's band are not touched; the whole image is zeroed first so that
+  // "pixels in empty tiles stay 0" (render.py:318) also holds for bands
+  if (rp.row_begin == 0 && rp.row_end == rp.tiles_y) {
+    // every pixel is written by the blend kernel
+  } else {
+    CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
+  }
+  CU(gs::launch_blend_fwd(rp, frame_ws, L, sl.vals, image_out, s));
+  if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
+  return B200GS_OK;
+}
+
+int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws, size_t frame_bytes,
+                           void* isect_ws, size_t isect_bytes, uint32_t isect_capacity, const float* grad_image,
+                           const b200gs_grads* grads, void* stream) {
+  gs::RenderParams rp;
+  gs::GaussIn gi;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  rc = make_gauss(g, gi);
+  if (rc) return rc;
+  if (!frame_ws || !isect_ws || !grad_image || !grads) return fail(B200GS_ERR_ARG, "backward: null argument");
+  const gs::FrameLayout L = gs::frame_layout(gi.n, rp.H, rp.W);
+  const gs::IsectLayout IL = gs::isect_layout(isect_capacity);
+  if (frame_bytes < L.total) return fail(B200GS_ERR_WORKSPACE, "frame workspace too small");
+  if (isect_bytes < IL.total) return fail(B200GS_ERR_WORKSPACE, "isect workspace too small");
+  gs::GaussGrad gg;
+  gg.pos = grads->pos; gg.opacity_raw = grads->opacity_raw; gg.scale_raw = grads->scale_raw; gg.q_raw = grads->q_raw;
+  gg.sigma = grads->sigma; gg.f_dc = grads->f_dc; gg.f_rest = grads->f_rest; gg.color = grads->color;
+  if (gi.n > 0) {
+    if (!gg.pos || !gg.opacity_raw) return fail(B200GS_ERR_ARG, "backward: grads.pos / opacity_raw missing");
+    if (gi.scale_raw ? (!gg.scale_raw || !gg.q_raw) : !gg.sigma) return fail(B200GS_ERR_ARG, "backward: covariance grads missing");
+    if (gi.f_dc ? (!gg.f_dc || !gg.f_rest) : !gg.color) return fail(B200GS_ERR_ARG, "backward: colour grads missing");
+    if (gi.scale_raw && (reinterpret_cast<uintptr_t>(gg.q_raw) & 15u))
+      return fail(B200GS_ERR_ARG, "grads.q_raw must be 16-byte aligned");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const SortedLists sl = sorted_lists(isect_ws, IL, rp.tiles_x * rp.tiles_y);
+  CU(gs::launch_blend_bwd(rp, frame_ws, L, sl.vals, grad_image, gi.n, s));
+  CU(gs::launch_preprocess_bwd(gi, gg, cam->c2w, rp, frame_ws, L, s));
+  return B200GS_OK;
+}
+
+int b200gs_render_host(const b200gs_gaussians* gh, const b200gs_camera* cam, const float* c2w_host, float* image_host,
+                       b200gs_frame_stats* stats_out) {
+  if (!gh || !cam || !c2w_host || !image_host) return fail(B200GS_ERR_ARG, "render_host: null argument");
+  std::lock_guard<std::mutex> lock(g_host.mu);
+  if (!g_host.stream) CU(cudaStreamCreateWithFlags(&g_host.stream, cudaStreamNonBlocking));
+  if (!g_host.stats_pinned) CU(cudaMallocHost(&g_host.stats_pinned, sizeof(b200gs_frame_stats)));
+  cudaStream_t s = g_host.stream;
+  const size_t n = (size_t)(gh->n > 0 ? gh->n : 0);
+  b200gs_gaussians gd;
+  memset(&gd, 0, sizeof(gd));
+  gd.n = gh->n;
+  struct Up { const float* src; const float** dst; size_t floats; int slot; };
+  const Up ups[] = {
+      {gh->pos, &gd.pos, n * 3, 0},         {gh->opacity_raw, &gd.opacity_raw, n, 1},
+      {gh->scale_raw, &gd.scale_raw, n * 3, 2}, {gh->q_raw, &gd.q_raw, n * 4, 3},
+      {gh->sigma, &gd.sigma, n * 9, 4},     {gh->f_dc, &gd.f_dc, n * 3, 5},
+      {gh->f_rest, &gd.f_rest, n * 45, 6},  {gh->color, &gd.color, n * 3, 7},
+  };
+  for (const Up& u : ups) {
+    if (!u.src || u.floats == 0) continue;
+    CU(g_host.ensure(u.slot, u.floats * 4));
+    CU(cudaMemcpyAsync(g_host.bufs[u.slot], u.src, u.floats * 4, cudaMemcpyHostToDevice, s));
+    *u.dst = reinterpret_cast<const float*>(g_host.bufs[u.slot]);
+  }
+  CU(g_host.ensure(8, 64));
+  CU(cudaMemcpyAsync(g_host.bufs[8], c2w_host, 64, cudaMemcpyHostToDevice, s));
+  b200gs_camera cd = *cam;
+  cd.c2w = reinterpret_cast<const float*>(g_host.bufs[8]);
+  b200gs_sizes sz;
+  int rc = b200gs_workspace_sizes(gd.n, cd.H, cd.W, 0, &sz);
+  if (rc) return rc;
+  CU(g_host.ensure(9, sz.frame_bytes));
+  rc = b200gs_render_project(&gd, &cd, g_host.bufs[9], g_host.caps[9], g_host.stats_pinned, s);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s));
+  const uint32_t isect = g_host.stats_pinned->n_isect;
+  rc = b200gs_workspace_sizes(gd.n, cd.H, cd.W, isect, &sz);
+  if (rc) return rc;
+  CU(g_host.ensure(10, sz.isect_bytes));
+  const size_t img_bytes = (size_t)cd.H * cd.W * 3 * sizeof(float);
+  CU(g_host.ensure(11, img_bytes));
+  rc = b200gs_render_rasterize(&cd, gd.n, g_host.bufs[9], g_host.caps[9], g_host.bufs[10], g_host.caps[10], isect,
+                               reinterpret_cast<float*>(g_host.bufs[11]), g_host.stats_pinned, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(image_host, g_host.bufs[11], img_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (stats_out) *stats_out = *g_host.stats_pinned;
+  if (g_host.stats_pinned->overflow) return fail(B200GS_ERR_CAPACITY, "intersection list overflow");
+  return B200GS_OK;
+}
+
+int b200gs_debug_export(int32_t n, const void* frame_ws, size_t frame_bytes, int32_t H, int32_t W, float* xy,
+                        float* depth, float* conic, float* opacity, float* color, int32_t* radius, int32_t* rect,
+                        int32_t* tiles_touched, int32_t* depth_order, void* stream) {
+  if (!frame_ws || n < 0) return fail(B200GS_ERR_ARG, "debug_export: null");
+  const gs::FrameLayout L = gs::frame_layout(n, H, W);
+  if (frame_bytes < L.total) return fail(B200GS_ERR_WORKSPACE, "frame workspace too small");
+  if (n == 0) return B200GS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  export_kernel<<<gs::ceil_div(n, 256), 256, 0, s>>>(
+      n, gs::ws_ptr<float4>(frame_ws, L.rec0), gs::ws_ptr<float4>(frame_ws, L.rec1), gs::ws_ptr<float4>(frame_ws, L.rec2),
+      gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), gs::ws_ptr<uint2>(frame_ws, L.rect),
+      gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), xy, depth, conic, opacity, color, radius, rect, tiles_touched);
+  CU(cudaGetLastError());
+  if (depth_order) {
+    copy_u32_kernel<<<gs::ceil_div(n, 256), 256, 0, s>>>(gs::ws_ptr<uint32_t>(frame_ws, L.order), depth_order, (uint32_t)n);
+    CU(cudaGetLastError());
+  }
+  return B200GS_OK;
+}
+
+int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const void* isect_ws, size_t isect_bytes,
+                              uint32_t isect_capacity, int32_t n, int32_t H, int32_t W, int32_t* list_tile,
+                              int32_t* list_id, uint32_t count, int32_t* ranges, void* stream) {
+  if (!frame_ws || !isect_ws) return fail(B200GS_ERR_ARG, "debug_export_lists: null");
+  const gs::FrameLayout L = gs::frame_layout(n, H, W);
+  const gs::IsectLayout IL = gs::isect_layout(isect_capacity);
+  if (frame_bytes < L.total || isect_bytes < IL.total) return fail(B200GS_ERR_WORKSPACE, "workspace too small");
+  if (count > isect_capacity) return fail(B200GS_ERR_ARG, "count > capacity");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_tiles = gs::ceil_div(W, gs::kTile) * gs::ceil_div(H, gs::kTile);
+  const SortedLists sl = sorted_lists(const_cast<void*>(isect_ws), IL, n_tiles);
+  if (count) {
+    if (list_tile) copy_u32_kernel<<<(count + 255) / 256, 256, 0, s>>>(sl.keys, list_tile, count);
+    if (list_id) copy_u32_kernel<<<(count + 255) / 256, 256, 0, s>>>(sl.vals, list_id, count);
+  }
+  if (ranges) copy_ranges_kernel<<<gs::ceil_div(n_tiles, 256), 256, 0, s>>>(gs::ws_ptr<uint2>(frame_ws, L.ranges), ranges, n_tiles);
+  CU(cudaGetLastError());
+  return B200GS_OK;
+}
+
+size_t b200gs_scan_scratch_bytes(uint32_t n) { return gs::scan_scratch_bytes(n); }
+size_t b200gs_sort_scratch_bytes(uint32_t n) { return gs::sort_scratch_bytes(n); }
+
+int b200gs_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out, void* scratch,
+                              size_t scratch_bytes, void* stream) {
+  if (n > 0 && (!in || !out || !scratch)) return fail(B200GS_ERR_ARG, "scan: null");
+  if (scratch_bytes < gs::scan_scratch_bytes(n)) return fail(B200GS_ERR_WORKSPACE, "scan scratch too small");
+  CU(gs::launch_exclusive_scan(in, nullptr, out, n, total_out, scratch, scratch_bytes, (cudaStream_t)stream));
+  return B200GS_OK;
+}
+
+int b200gs_radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, uint32_t n,
+                            int begin_bit, int end_bit, void* scratch, size_t scratch_bytes, void* stream) {
+  if (n > 0 && (!keys_in || !vals_in || !keys_out || !vals_out || !scratch)) return fail(B200GS_ERR_ARG, "sort: null");
+  if (end_bit <= begin_bit || end_bit > 32 || begin_bit < 0) return fail(B200GS_ERR_ARG, "sort: bad bit range");
+  if (scratch_bytes < gs::sort_scratch_bytes(n)) return fail(B200GS_ERR_WORKSPACE, "sort scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int in_a = 0;
+  // ping-pong a = *_in, b = *_out: odd pass counts end in *_out, even ones in *_in (then copy over)
+  CU(gs::launch_radix_sort(keys_in, vals_in, keys_in, vals_in, keys_out, vals_out, n, nullptr, begin_bit, end_bit,
+                           scratch, scratch_bytes, &in_a, s));
+  if (in_a && n) {
+    CU(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return B200GS_OK;
+}
+
+}  // extern "C"

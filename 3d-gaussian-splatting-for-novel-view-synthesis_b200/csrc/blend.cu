@@ -1,0 +1,243 @@
+// Per-tile front-to-back alpha blend (forward) and its replay-in-reverse backward.
+//
+// Replaces (reference): render.py:317-410 (S16-S17, the Python loop over tiles) and its autograd.
+// One 256-thread CTA per 16x16 tile; each warp owns an 8x4 pixel block.  Splat records of the tile's
+// depth-sorted list are staged 256 at a time into shared memory (3 x float4 per splat, read back as
+// warp-wide broadcasts), every pixel walks the batch front to back, and the CTA stops as soon as every
+// pixel's transmittance is <= 5e-5 (render.py:387: a splat contributes iff T *before* it is > 5e-5).
+//
+// Roofline: FP32 issue + MUFU.EX2; HBM traffic is the 36-B record gather per
+// intersection plus 12 B/pixel of output.
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int kBlendThreads = 256;
+constexpr uint32_t kCountMask = 0x1FFFFFFFu;
+
+struct PixelCoord { int px, py; bool inside; };
+
+__device__ __forceinline__ PixelCoord pixel_of_thread(const RenderParams& rp, int tile_x, int tile_y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PixelCoord p;
+  p.px = tile_x * kTile + ((warp & 1) << 3) + (lane & 7);
+  p.py = tile_y * kTile + ((warp >> 1) << 2) + (lane >> 3);
+  p.inside = (p.px < rp.W) && (p.py < rp.H);
+  return p;
+}
+
+// alpha of one splat at one pixel; identical instruction sequence in forward and backward.
+// Returns 0 when the splat does not contribute (render.py:362-374).
+__device__ __forceinline__ float splat_alpha(const float4& r0, const float4& r1, float pxf, float pyf,
+                                             const RenderParams& rp, float& du, float& dv, float& gval,
+                                             float& araw) {
+  du = pxf - r0.x;
+  dv = pyf - r0.y;
+  const float q = fmaf(r1.x * dv, dv, fmaf((2.f * r0.w) * du, dv, (r0.z * du) * du));
+  if (!(q <= rp.chi2)) return 0.f;
+  gval = __expf(-0.5f * q);
+  araw = r1.y * gval;
+  const float a = fminf(araw, rp.alpha_max);
+  return (a >= rp.alpha_cutoff) ? a : 0.f;
+}
+
+__global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams rp, const uint2* __restrict__ ranges,
+                                                                  const uint32_t* __restrict__ vals,
+                                                                  const float4* __restrict__ rec0,
+                                                                  const float4* __restrict__ rec1,
+                                                                  const float4* __restrict__ rec2,
+                                                                  float* __restrict__ image,
+                                                                  float* __restrict__ final_T,
+                                                                  uint32_t* __restrict__ n_contrib) {
+  __shared__ float4 s0[kBlendThreads], s1[kBlendThreads], s2[kBlendThreads];
+  const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
+  const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
+  const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
+  const float pxf = (float)pc.px, pyf = (float)pc.py;
+  float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  uint32_t last = 0;
+  bool done = !pc.inside;
+  for (uint32_t base = range.x; base < range.y; base += kBlendThreads) {
+    if (__syncthreads_count(done) == kBlendThreads) break;
+    const uint32_t idx = base + threadIdx.x;
+    if (idx < range.y) {
+      const uint32_t id = vals[idx];
+      s0[threadIdx.x] = rec0[id];
+      s1[threadIdx.x] = rec1[id];
+      s2[threadIdx.x] = rec2[id];
+    }
+    __syncthreads();
+    const int cnt = (int)min((uint32_t)kBlendThreads, range.y - base);
+    if (!done) {
+      for (int j = 0; j < cnt; ++j) {
+        if (!(T > 5e-5f)) { done = true; break; }
+        const float4 r0 = s0[j], r1 = s1[j];
+        float du, dv, gval, araw;
+        const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
+        if (a > 0.f) {
+          const float w = a * T;
+          C0 = fmaf(w, r1.z, C0);
+          C1 = fmaf(w, r1.w, C1);
+          C2 = fmaf(w, s2[j].x, C2);
+          T *= (1.f - a);
+          last = (base - range.x) + (uint32_t)j + 1u;
+        }
+      }
+    }
+  }
+  if (pc.inside) {
+    const size_t pix = (size_t)pc.py * rp.W + pc.px;
+    uint32_t flags = last;
+    if (C0 > 1.f) flags |= 1u << 29;
+    if (C1 > 1.f) flags |= 1u << 30;
+    if (C2 > 1.f) flags |= 1u << 31;
+    image[3 * pix + 0] = fminf(fmaxf(C0, 0.f), 1.f);
+    image[3 * pix + 1] = fminf(fmaxf(C1, 0.f), 1.f);
+    image[3 * pix + 2] = fminf(fmaxf(C2, 0.f), 1.f);
+    final_T[pix] = T;
+    n_contrib[pix] = flags;
+  }
+}
+
+cudaError_t launch_blend_fwd(const RenderParams& rp, const void* ws, const FrameLayout& L, const uint32_t* vals,
+                             float* image, cudaStream_t s) {
+  const int rows = rp.row_end - rp.row_begin;
+  if (rows <= 0 || rp.tiles_x <= 0) return cudaSuccess;
+  dim3 grid(rp.tiles_x, rows);
+  blend_fwd_kernel<<<grid, kBlendThreads, 0, s>>>(
+      rp, ws_ptr<uint2>(ws, L.ranges), vals, ws_ptr<float4>(ws, L.rec0), ws_ptr<float4>(ws, L.rec1),
+      ws_ptr<float4>(ws, L.rec2), image, const_cast<float*>(ws_ptr<float>(ws, L.final_T)),
+      const_cast<uint32_t*>(ws_ptr<uint32_t>(ws, L.n_contrib)));
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  Walks each tile's list back to front from the last contributor, recomputing alpha and
+// recovering T_i = T_{i+1} / (1 - alpha_i).  Per-splat gradients (u, v, A11, A12, A22, opacity, r, g, b)
+// are reduced over the warp's 32 pixels with shuffles, accumulated per batch in shared memory, and
+// flushed with one global atomic per splat and component per tile.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams rp, const uint2* __restrict__ ranges,
+                                                                  const uint32_t* __restrict__ vals,
+                                                                  const float4* __restrict__ rec0,
+                                                                  const float4* __restrict__ rec1,
+                                                                  const float4* __restrict__ rec2,
+                                                                  const float* __restrict__ image_grad,
+                                                                  const float* __restrict__ final_T,
+                                                                  const uint32_t* __restrict__ n_contrib,
+                                                                  float* __restrict__ grad_acc) {
+  __shared__ float4 s0[kBlendThreads], s1[kBlendThreads];
+  __shared__ float s_cb[kBlendThreads];
+  __shared__ uint32_t s_id[kBlendThreads];
+  __shared__ float s_grad[kBlendThreads][9];
+  __shared__ uint32_t s_max;
+  const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
+  const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
+  const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
+  const float pxf = (float)pc.px, pyf = (float)pc.py;
+  const int lane = threadIdx.x & 31;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, T = 1.f;
+  uint32_t last = 0;
+  if (pc.inside) {
+    const size_t pix = (size_t)pc.py * rp.W + pc.px;
+    const uint32_t flags = n_contrib[pix];
+    last = flags & kCountMask;
+    // final clamp(0,1): gradient passes where 0 <= C <= 1 (C >= 0 always)
+    g0 = (flags & (1u << 29)) ? 0.f : image_grad[3 * pix + 0];
+    g1 = (flags & (1u << 30)) ? 0.f : image_grad[3 * pix + 1];
+    g2 = (flags & (1u << 31)) ? 0.f : image_grad[3 * pix + 2];
+    T = final_T[pix];
+  }
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
+  if (lane == 0 && wmax) atomicMax(&s_max, wmax);
+  __syncthreads();
+  const uint32_t max_last = s_max;
+  if (max_last == 0) return;
+  float rc0 = 0.f, rc1 = 0.f, rc2 = 0.f;   // colour accumulated behind the current splat, normalised by T_{i+1}
+  const int nb = (int)((max_last + kBlendThreads - 1) / kBlendThreads);
+  for (int b = nb - 1; b >= 0; --b) {
+    const uint32_t boff = (uint32_t)b * kBlendThreads;
+    const int cnt = (int)min((uint32_t)kBlendThreads, max_last - boff);
+    if ((int)threadIdx.x < cnt) {
+      const uint32_t id = vals[range.x + boff + threadIdx.x];
+      s_id[threadIdx.x] = id;
+      s0[threadIdx.x] = rec0[id];
+      s1[threadIdx.x] = rec1[id];
+      s_cb[threadIdx.x] = rec2[id].x;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_grad[threadIdx.x][k] = 0.f;
+    __syncthreads();
+    for (int j = cnt - 1; j >= 0; --j) {
+      const bool active = (boff + (uint32_t)j) < last;
+      float a = 0.f, du = 0.f, dv = 0.f, gval = 0.f, araw = 0.f;
+      const float4 r0 = s0[j], r1 = s1[j];
+      if (active) a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
+      const bool hit = a > 0.f;
+      if (!__any_sync(0xffffffffu, hit)) continue;
+      float v_u = 0.f, v_v = 0.f, v_a11 = 0.f, v_a12 = 0.f, v_a22 = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+      if (hit) {
+        const float cb = s_cb[j];
+        const float Ti = T / (1.f - a);
+        T = Ti;
+        const float w = a * Ti;
+        v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
+        const float dalpha = Ti * (g0 * (r1.z - rc0) + g1 * (r1.w - rc1) + g2 * (cb - rc2));
+        rc0 = fmaf(a, r1.z - rc0, rc0);
+        rc1 = fmaf(a, r1.w - rc1, rc1);
+        rc2 = fmaf(a, cb - rc2, rc2);
+        const float draw = (araw <= rp.alpha_max) ? dalpha : 0.f;   // clamp_max passes on <=
+        v_op = draw * gval;
+        const float dq = -0.5f * araw * draw;                       // d/dq of op*exp(-q/2)
+        const float B2 = 2.f * r0.w;
+        v_u = -dq * (2.f * r0.z * du + B2 * dv);
+        v_v = -dq * (2.f * r1.x * dv + B2 * du);
+        v_a11 = dq * du * du;
+        v_a12 = dq * 2.f * du * dv;
+        v_a22 = dq * dv * dv;
+      }
+      v_u = warp_sum(v_u); v_v = warp_sum(v_v); v_a11 = warp_sum(v_a11); v_a12 = warp_sum(v_a12);
+      v_a22 = warp_sum(v_a22); v_op = warp_sum(v_op); v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
+      if (lane == 0) {
+        float* sg = s_grad[j];
+        atomicAdd(sg + 0, v_u); atomicAdd(sg + 1, v_v); atomicAdd(sg + 2, v_a11); atomicAdd(sg + 3, v_a12);
+        atomicAdd(sg + 4, v_a22); atomicAdd(sg + 5, v_op); atomicAdd(sg + 6, v_r); atomicAdd(sg + 7, v_g);
+        atomicAdd(sg + 8, v_b);
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+      float* dst = grad_acc + (size_t)s_id[threadIdx.x] * 12;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float v = s_grad[threadIdx.x][k];
+        if (v != 0.f) atomicAdd(dst + k, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_blend_bwd(const RenderParams& rp, void* ws, const FrameLayout& L, const uint32_t* vals,
+                             const float* image_grad, int n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(ws_ptr<float>(ws, L.grad_acc), 0, (size_t)(n > 0 ? n : 1) * 12 * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  const int rows = rp.row_end - rp.row_begin;
+  if (rows <= 0 || rp.tiles_x <= 0) return cudaSuccess;
+  dim3 grid(rp.tiles_x, rows);
+  blend_bwd_kernel<<<grid, kBlendThreads, 0, s>>>(
+      rp, ws_ptr<uint2>(ws, L.ranges), vals, ws_ptr<float4>(ws, L.rec0), ws_ptr<float4>(ws, L.rec1),
+      ws_ptr<float4>(ws, L.rec2), image_grad, ws_ptr<float>(ws, L.final_T), ws_ptr<uint32_t>(ws, L.n_contrib),
+      ws_ptr<float>(ws, L.grad_acc));
+  return cudaGetLastError();
+}
+
+}  // namespace gs

@@ -1,0 +1,158 @@
+// Shared device helpers + the workspace layout used by every stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "gs_math.cuh"
+#include "../../include/b200gs.h"
+
+namespace gs {
+
+constexpr int kTile = 16;
+constexpr uint32_t kCulledKey = 0xFFFFFFFFu;
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- streaming loads / stores (read-once data must not pollute L1) ---------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream_f(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// ---- workspace layouts -----------------------------------------------------------------------------
+// Frame workspace: header | per-Gaussian | per-tile | per-pixel.   Everything 256-byte aligned.
+struct FrameLayout {
+  size_t header;          // b200gs_frame_stats (64 B) + scan/sort bookkeeping
+  size_t rec0, rec1, rec2;  // float4[n] each: (u,v,A11,A12) (A22,op,r,g) (b,ext_u,ext_v,radius)
+  size_t depth_key;       // u32[n]  float bits of z, 0xFFFFFFFF when culled
+  size_t rect;            // uint2[n] packed u16 tile rect: x = tu0 | tu1<<16, y = tv0 | tv1<<16
+  size_t tiles_touched;   // u32[n]
+  size_t sort_key_alt;    // u32[n]  depth-sort ping-pong buffers (depth_key itself stays intact)
+  size_t sort_key_alt2;   // u32[n]
+  size_t order;           // u32[n]  Gaussian ids in depth order (sorted values)
+  size_t order_alt;       // u32[n]
+  size_t offsets;         // u32[n]  exclusive scan of tiles_touched in depth order
+  size_t grad_acc;        // float[n*12] blend-backward accumulators (u,v,A11,A12,A22,op,r,g,b,+pad)
+  size_t ranges;          // uint2[tiles] (start,end) per tile
+  size_t final_T;         // float[P]
+  size_t n_contrib;       // u32[P]  (#list entries consumed) | channel-overflow bits 29..31
+  size_t scratch;         // scan + sort scratch (sized for max(n, isect) users at call time)
+  size_t scratch_bytes;
+  size_t total;
+};
+
+struct IsectLayout {
+  size_t keys, keys_alt;  // u32[cap] tile ids
+  size_t vals, vals_alt;  // u32[cap] Gaussian ids
+  size_t scratch;         // sort scratch for cap entries
+  size_t scratch_bytes;
+  size_t total;
+};
+
+// device-visible header (first bytes of the frame workspace)
+struct FrameHeader {
+  b200gs_frame_stats stats;   // 64 bytes
+};
+
+size_t scan_scratch_bytes(uint32_t n);
+size_t sort_scratch_bytes(uint32_t n);
+
+inline FrameLayout frame_layout(int n, int H, int W) {
+  FrameLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  const size_t tiles = (size_t)ceil_div(W, kTile) * ceil_div(H, kTile);
+  const size_t P = (size_t)H * W;
+  L.header = take(256);
+  L.rec0 = take(N * 16); L.rec1 = take(N * 16); L.rec2 = take(N * 16);
+  L.depth_key = take(N * 4);
+  L.rect = take(N * 8);
+  L.tiles_touched = take(N * 4);
+  L.sort_key_alt = take(N * 4);
+  L.sort_key_alt2 = take(N * 4);
+  L.order = take(N * 4);
+  L.order_alt = take(N * 4);
+  L.offsets = take(N * 4);
+  L.grad_acc = take(N * 12 * 4);
+  L.ranges = take(tiles * 8);
+  L.final_T = take(P * 4);
+  L.n_contrib = take(P * 4);
+  const size_t a = scan_scratch_bytes((uint32_t)N), b = sort_scratch_bytes((uint32_t)N);
+  L.scratch_bytes = a > b ? a : b;
+  L.scratch = take(L.scratch_bytes);
+  L.total = off;
+  return L;
+}
+
+inline IsectLayout isect_layout(uint32_t cap) {
+  IsectLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t C = cap > 0 ? cap : 1;
+  L.keys = take(C * 4); L.keys_alt = take(C * 4);
+  L.vals = take(C * 4); L.vals_alt = take(C * 4);
+  L.scratch_bytes = sort_scratch_bytes((uint32_t)C);
+  L.scratch = take(L.scratch_bytes);
+  L.total = off;
+  return L;
+}
+
+template <typename T>
+__host__ __device__ inline T* ws_ptr(void* base, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off);
+}
+template <typename T>
+__host__ __device__ inline const T* ws_ptr(const void* base, size_t off) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + off);
+}
+
+// ---- stage entry points (host functions implemented in the .cu files) --------------------------------
+struct GaussIn {       // device pointers, mirrors b200gs_gaussians
+  int n;
+  const float *pos, *opacity_raw, *scale_raw, *q_raw, *sigma, *f_dc, *f_rest, *color;
+};
+struct GaussGrad {
+  float *pos, *opacity_raw, *scale_raw, *q_raw, *sigma, *f_dc, *f_rest, *color;
+};
+
+cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const RenderParams& rp, void* frame_ws,
+                                  const FrameLayout& L, cudaStream_t s);
+cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const float* c2w, const RenderParams& rp,
+                                  void* frame_ws, const FrameLayout& L, cudaStream_t s);
+cudaError_t launch_build_sigma(int n, const float* scale_raw, const float* q_raw, float* sigma, cudaStream_t s);
+cudaError_t launch_build_sigma_bwd(int n, const float* scale_raw, const float* q_raw, const float* g_sigma,
+                                   float* g_scale, float* g_q, cudaStream_t s);
+cudaError_t launch_eval_sh(int n, const float* f_dc, const float* f_rest, const float* pts, const float* c2w,
+                           float* color, cudaStream_t s);
+cudaError_t launch_eval_sh_bwd(int n, const float* f_dc, const float* f_rest, const float* pts, const float* c2w,
+                               const float* g_color, float* g_dc, float* g_rest, float* g_pts, cudaStream_t s);
+
+cudaError_t launch_exclusive_scan(const uint32_t* in, const uint32_t* gather_idx, uint32_t* out, uint32_t n,
+                                  uint32_t* total_out, void* scratch, size_t scratch_bytes, cudaStream_t s);
+cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_a,
+                              uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
+                              const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
+                              size_t scratch_bytes, int* result_in_a, cudaStream_t s);
+
+cudaError_t launch_emit_pairs(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* tiles_touched,
+                              const uint2* rect, int tiles_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+                              b200gs_frame_stats* stats, cudaStream_t s);
+cudaError_t launch_tile_ranges(const uint32_t* keys, uint32_t capacity, const b200gs_frame_stats* stats,
+                               uint2* ranges, int n_tiles, cudaStream_t s);
+
+cudaError_t launch_blend_fwd(const RenderParams& rp, const void* frame_ws, const FrameLayout& L, const uint32_t* vals,
+                             float* image, cudaStream_t s);
+cudaError_t launch_blend_bwd(const RenderParams& rp, void* frame_ws, const FrameLayout& L, const uint32_t* vals,
+                             const float* image_grad, int n, cudaStream_t s);
+
+}  // namespace gs

@@ -1,0 +1,487 @@
+// Per-Gaussian kernels: fused preprocess forward / backward, stand-alone Sigma and SH kernels.
+//
+// Replaces (reference paths): gaussian_splatting/gaussian.py:71-127, spherical_harmonics.py:70-166,
+// render.py:104-258 + 305-315 (S1-S11, S15) and their autograd.
+//
+// Roofline: HBM.  Each Gaussian is read once (236 B from raw parameters, 64 B from sigma/color) and a
+// 64-B splat record is written for survivors.  Rows of the [n,3] / [n,9] / [n,45] arrays are staged
+// through shared memory with 16-byte coalesced streaming loads (row strides of 3, 9 and 45 words are
+// odd, so the per-thread reads from shared memory are bank-conflict free).
+//
+// Compiled with -fmad=false: the projection feeds floor()/ceil() decisions that must not depend on
+// the compiler's contraction choices; FMAs are written explicitly (fmaf) where wanted.
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int kPreBlock = 128;
+
+template <int K>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, float* __restrict__ dst, int n0,
+                                           int count) {
+  const float* s = src + (size_t)n0 * K;
+  const int total = count * K;
+  if ((reinterpret_cast<uintptr_t>(s) & 15u) == 0) {
+    const int nvec = total >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < nvec; i += kPreBlock) d4[i] = ld_stream_f4(s4 + i);
+    for (int i = (nvec << 2) + threadIdx.x; i < total; i += kPreBlock) dst[i] = ld_stream_f(s + i);
+  } else {
+    for (int i = threadIdx.x; i < total; i += kPreBlock) dst[i] = ld_stream_f(s + i);
+  }
+}
+
+// coalesced write-back of K floats per thread through shared memory
+template <int K>
+__device__ __forceinline__ void unstage_rows(float* __restrict__ dstg, const float* __restrict__ srcs, int n0,
+                                             int count) {
+  float* d = dstg + (size_t)n0 * K;
+  const int total = count * K;
+  if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+    const int nvec = total >> 2;
+    float4* d4 = reinterpret_cast<float4*>(d);
+    const float4* s4 = reinterpret_cast<const float4*>(srcs);
+    for (int i = threadIdx.x; i < nvec; i += kPreBlock) d4[i] = s4[i];
+    for (int i = (nvec << 2) + threadIdx.x; i < total; i += kPreBlock) d[i] = srcs[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += kPreBlock) d[i] = srcs[i];
+  }
+}
+
+struct FrameView {
+  float4 *rec0, *rec1, *rec2;
+  uint32_t* depth_key;
+  uint2* rect;
+  uint32_t* tiles_touched;
+  float* grad_acc;
+  b200gs_frame_stats* stats;
+};
+
+__device__ __forceinline__ void sh_color(const float* coef_dc, const float* coef_rest, const float Y[16],
+                                         float rgb[3], float acc_out[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = coef_dc[c] * Y[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) acc = fmaf(coef_rest[15 * c + k - 1], Y[k], acc);
+    acc_out[c] = acc;
+    rgb[c] = sigmoidf_(acc);
+  }
+}
+
+// tight half-extents of { q <= chi2 } for the per-warp culling in the blend kernels (conservative)
+__device__ __forceinline__ void conic_extent(float A11, float A12, float A22, float chi2, float& eu, float& ev) {
+  const float detc = A11 * A22 - A12 * A12;
+  if (detc > 0.f && isfinite(detc)) {
+    eu = sqrtf(chi2 * A22 / detc) * 1.001f + 0.01f;
+    ev = sqrtf(chi2 * A11 / detc) * 1.001f + 0.01f;
+    if (!isfinite(eu)) eu = 1e30f;
+    if (!isfinite(ev)) ev = 1e30f;
+  } else {
+    eu = 1e30f; ev = 1e30f;
+  }
+}
+
+template <bool RAW_COV, bool RAW_SH>
+__global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, const float* __restrict__ c2w,
+                                                                   RenderParams rp, FrameView f) {
+  __shared__ __align__(16) float s_pos[kPreBlock * 3];
+  __shared__ __align__(16) float s_cov[kPreBlock * (RAW_COV ? 3 : 9)];
+  __shared__ __align__(16) float s_col[kPreBlock * 3];
+  __shared__ __align__(16) float s_rest[RAW_SH ? kPreBlock * 45 : 4];
+  __shared__ float s_c2w[16];
+
+  const int n0 = blockIdx.x * kPreBlock;
+  const int count = min(kPreBlock, g.n - n0);
+  const int tid = threadIdx.x;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  stage_rows<3>(g.pos, s_pos, n0, count);
+  if (RAW_COV) stage_rows<3>(g.scale_raw, s_cov, n0, count); else stage_rows<9>(g.sigma, s_cov, n0, count);
+  if (RAW_SH) { stage_rows<3>(g.f_dc, s_col, n0, count); stage_rows<45>(g.f_rest, s_rest, n0, count); }
+  else stage_rows<3>(g.color, s_col, n0, count);
+  __syncthreads();
+  const int i = n0 + tid;
+  bool vis = false, past_s7 = false;
+  if (tid < count) {
+    const Pose ps = make_pose(s_c2w);
+    const float p[3] = {s_pos[3 * tid], s_pos[3 * tid + 1], s_pos[3 * tid + 2]};
+    Cov3 S;
+    if (RAW_COV) {
+      const float sr[3] = {s_cov[3 * tid], s_cov[3 * tid + 1], s_cov[3 * tid + 2]};
+      const float4 q4 = ld_stream_f4(reinterpret_cast<const float4*>(g.q_raw) + i);
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+      QuatScale qs;
+      quat_scale_forward(sr, q, qs);
+      float full[9];
+      sigma_full(qs, full);
+      S = sym_from_full(full);
+    } else {
+      S = sym_from_full(&s_cov[9 * tid]);
+    }
+    Projection o;
+    vis = project_gaussian(p, S, ld_stream_f(g.opacity_raw + i), ps, rp, o);
+    past_s7 = vis || o.offscreen;
+    if (!vis) {
+      f.depth_key[i] = kCulledKey;
+      f.tiles_touched[i] = 0;
+    } else {
+      float rgb[3];
+      if (RAW_SH) {
+        const ViewDir vd = view_dir(p, ps.cam);
+        float Y[16], acc[3];
+        sh_basis(vd.d, Y);
+        sh_color(&s_col[3 * tid], &s_rest[45 * tid], Y, rgb, acc);
+      } else {
+        rgb[0] = s_col[3 * tid]; rgb[1] = s_col[3 * tid + 1]; rgb[2] = s_col[3 * tid + 2];
+      }
+      // tile-row sharding: this rank only bins tile rows [row_begin, row_end)
+      int tv0 = max(o.tv0, rp.row_begin), tv1 = min(o.tv1, rp.row_end - 1);
+      const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
+      if (tiles == 0) { tv0 = 0; tv1 = 0; }
+      float eu, ev;
+      conic_extent(o.A11, o.A12, o.A22, rp.chi2, eu, ev);
+      f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
+      f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
+      f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
+      f.depth_key[i] = __float_as_uint(o.z);
+      f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
+      f.tiles_touched[i] = (uint32_t)tiles;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, vis);
+  const unsigned m7 = __ballot_sync(0xffffffffu, past_s7);
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicAdd(&f.stats->n_visible, (uint32_t)__popc(m));
+    if (m7) atomicAdd(&f.stats->n_in_frustum, (uint32_t)__popc(m7));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward: recompute the forward from the inputs, chain the 9 per-Gaussian gradients that the blend
+// backward accumulated (grad_acc[n][12]) down to the leaves.  Dense outputs (zeros when culled).
+// ------------------------------------------------------------------------------------------------
+template <bool RAW_COV, bool RAW_SH>
+__global__ void __launch_bounds__(kPreBlock) preprocess_bwd_kernel(GaussIn g, GaussGrad gg,
+                                                                   const float* __restrict__ c2w, RenderParams rp,
+                                                                   FrameView f) {
+  __shared__ __align__(16) float s_pos[kPreBlock * 3];
+  __shared__ __align__(16) float s_cov[kPreBlock * (RAW_COV ? 3 : 9)];   // in: scale/sigma, out: grads
+  __shared__ __align__(16) float s_col[kPreBlock * 3];
+  __shared__ __align__(16) float s_rest[RAW_SH ? kPreBlock * 45 : 4];
+  __shared__ float s_c2w[16];
+
+  const int n0 = blockIdx.x * kPreBlock;
+  const int count = min(kPreBlock, g.n - n0);
+  const int tid = threadIdx.x;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  stage_rows<3>(g.pos, s_pos, n0, count);
+  if (RAW_COV) stage_rows<3>(g.scale_raw, s_cov, n0, count); else stage_rows<9>(g.sigma, s_cov, n0, count);
+  if (RAW_SH) { stage_rows<3>(g.f_dc, s_col, n0, count); stage_rows<45>(g.f_rest, s_rest, n0, count); }
+  __syncthreads();
+  const int i = n0 + tid;
+  const bool live = tid < count;
+  float gp[3] = {0.f, 0.f, 0.f}, g_op = 0.f;
+  float g_cov[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // RAW_COV: [0..2] scale grads; else sigma grads
+  float g_q[4] = {0.f, 0.f, 0.f, 0.f};
+  float g_dc[3] = {0.f, 0.f, 0.f};
+  bool vis = false;
+  Pose ps;
+  float Y[16];
+  float g_acc[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    ps = make_pose(s_c2w);
+    const float p[3] = {s_pos[3 * tid], s_pos[3 * tid + 1], s_pos[3 * tid + 2]};
+    Cov3 S;
+    QuatScale qs;
+    float q[4] = {0.f, 0.f, 0.f, 1.f};
+    if (RAW_COV) {
+      const float sr[3] = {s_cov[3 * tid], s_cov[3 * tid + 1], s_cov[3 * tid + 2]};
+      const float4 q4 = ld_stream_f4(reinterpret_cast<const float4*>(g.q_raw) + i);
+      q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+      quat_scale_forward(sr, q, qs);
+      float full[9];
+      sigma_full(qs, full);
+      S = sym_from_full(full);
+    } else {
+      S = sym_from_full(&s_cov[9 * tid]);
+    }
+    Projection o;
+    vis = project_gaussian(p, S, ld_stream_f(g.opacity_raw + i), ps, rp, o);
+    if (vis) {
+      const float4 a0 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i];
+      const float4 a1 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i + 1];
+      const float4 a2 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i + 2];
+      SplatGrad sg;
+      sg.u = a0.x; sg.v = a0.y; sg.A11 = a0.z; sg.A12 = a0.w; sg.A22 = a1.x; sg.op = a1.y;
+      const float g_rgb[3] = {a1.z, a1.w, a2.x};
+      float G[9];
+      project_backward(p, S, ps, rp, o, sg, gp, G, g_op);
+      if (RAW_COV) {
+        quat_scale_backward(qs, q, G, g_cov, g_q);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_cov[k] = G[k];
+      }
+      if (RAW_SH) {
+        const ViewDir vd = view_dir(p, ps.cam);
+        sh_basis(vd.d, Y);
+        float rgb[3], acc[3];
+        sh_color(&s_col[3 * tid], &s_rest[45 * tid], Y, rgb, acc);
+        float gY[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gY[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          g_acc[c] = g_rgb[c] * rgb[c] * (1.f - rgb[c]);
+          g_dc[c] = g_acc[c] * Y[0];
+#pragma unroll
+          for (int k = 1; k < 16; ++k) gY[k] = fmaf(g_acc[c], s_rest[45 * tid + 15 * c + k - 1], gY[k]);
+        }
+        float gd[3], gpv[3];
+        sh_basis_backward(vd.d, gY, gd);
+        view_dir_backward(vd, gd, gpv);
+        gp[0] += gpv[0]; gp[1] += gpv[1]; gp[2] += gpv[2];
+      } else {
+        g_dc[0] = g_rgb[0]; g_dc[1] = g_rgb[1]; g_dc[2] = g_rgb[2];   // dL/dcolor
+      }
+    }
+  }
+  __syncthreads();   // everyone is done reading the staged inputs; reuse the buffers for the outputs
+  if (live) {
+    s_pos[3 * tid] = gp[0]; s_pos[3 * tid + 1] = gp[1]; s_pos[3 * tid + 2] = gp[2];
+    s_col[3 * tid] = g_dc[0]; s_col[3 * tid + 1] = g_dc[1]; s_col[3 * tid + 2] = g_dc[2];
+    if (RAW_COV) {
+      s_cov[3 * tid] = g_cov[0]; s_cov[3 * tid + 1] = g_cov[1]; s_cov[3 * tid + 2] = g_cov[2];
+      reinterpret_cast<float4*>(gg.q_raw)[i] = make_float4(g_q[0], g_q[1], g_q[2], g_q[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s_cov[9 * tid + k] = g_cov[k];
+    }
+    if (RAW_SH) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 1; k < 16; ++k) s_rest[45 * tid + 15 * c + k - 1] = vis ? g_acc[c] * Y[k] : 0.f;
+    }
+    gg.opacity_raw[i] = g_op;
+  }
+  __syncthreads();
+  unstage_rows<3>(gg.pos, s_pos, n0, count);
+  if (RAW_COV) unstage_rows<3>(gg.scale_raw, s_cov, n0, count); else unstage_rows<9>(gg.sigma, s_cov, n0, count);
+  if (RAW_SH) { unstage_rows<3>(gg.f_dc, s_col, n0, count); unstage_rows<45>(gg.f_rest, s_rest, n0, count); }
+  else unstage_rows<3>(gg.color, s_col, n0, count);
+}
+
+static FrameView make_view(void* ws, const FrameLayout& L) {
+  FrameView f;
+  f.rec0 = ws_ptr<float4>(ws, L.rec0); f.rec1 = ws_ptr<float4>(ws, L.rec1); f.rec2 = ws_ptr<float4>(ws, L.rec2);
+  f.depth_key = ws_ptr<uint32_t>(ws, L.depth_key);
+  f.rect = ws_ptr<uint2>(ws, L.rect);
+  f.tiles_touched = ws_ptr<uint32_t>(ws, L.tiles_touched);
+  f.grad_acc = ws_ptr<float>(ws, L.grad_acc);
+  f.stats = ws_ptr<b200gs_frame_stats>(ws, L.header);
+  return f;
+}
+
+cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const RenderParams& rp, void* ws,
+                                  const FrameLayout& L, cudaStream_t s) {
+  if (g.n <= 0) return cudaSuccess;
+  const FrameView f = make_view(ws, L);
+  const int grid = ceil_div(g.n, kPreBlock);
+  const bool rc = g.scale_raw != nullptr, rs = g.f_dc != nullptr;
+  if (rc && rs) preprocess_fwd_kernel<true, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
+  else if (rc && !rs) preprocess_fwd_kernel<true, false><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
+  else if (!rc && rs) preprocess_fwd_kernel<false, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
+  else preprocess_fwd_kernel<false, false><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const float* c2w, const RenderParams& rp,
+                                  void* ws, const FrameLayout& L, cudaStream_t s) {
+  if (g.n <= 0) return cudaSuccess;
+  const FrameView f = make_view(ws, L);
+  const int grid = ceil_div(g.n, kPreBlock);
+  const bool rc = g.scale_raw != nullptr, rs = g.f_dc != nullptr;
+  if (rc && rs) preprocess_bwd_kernel<true, true><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
+  else if (rc && !rs) preprocess_bwd_kernel<true, false><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
+  else if (!rc && rs) preprocess_bwd_kernel<false, true><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
+  else preprocess_bwd_kernel<false, false><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone Sigma (gaussian.py:71-127) and its backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPreBlock) build_sigma_kernel(int n, const float* __restrict__ scale_raw,
+                                                                const float* __restrict__ q_raw,
+                                                                float* __restrict__ sigma) {
+  __shared__ __align__(16) float s_in[kPreBlock * 3];
+  __shared__ __align__(16) float s_out[kPreBlock * 9];
+  const int n0 = blockIdx.x * kPreBlock, count = min(kPreBlock, n - n0), tid = threadIdx.x;
+  stage_rows<3>(scale_raw, s_in, n0, count);
+  __syncthreads();
+  if (tid < count) {
+    const float sr[3] = {s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2]};
+    const float4 q4 = ld_stream_f4(reinterpret_cast<const float4*>(q_raw) + n0 + tid);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    QuatScale qs;
+    quat_scale_forward(sr, q, qs);
+    float full[9];
+    sigma_full(qs, full);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_out[9 * tid + k] = full[k];
+  }
+  __syncthreads();
+  unstage_rows<9>(sigma, s_out, n0, count);
+}
+
+__global__ void __launch_bounds__(kPreBlock) build_sigma_bwd_kernel(int n, const float* __restrict__ scale_raw,
+                                                                    const float* __restrict__ q_raw,
+                                                                    const float* __restrict__ g_sigma,
+                                                                    float* __restrict__ g_scale,
+                                                                    float* __restrict__ g_q) {
+  __shared__ __align__(16) float s_in[kPreBlock * 3];
+  __shared__ __align__(16) float s_g[kPreBlock * 9];
+  const int n0 = blockIdx.x * kPreBlock, count = min(kPreBlock, n - n0), tid = threadIdx.x;
+  stage_rows<3>(scale_raw, s_in, n0, count);
+  stage_rows<9>(g_sigma, s_g, n0, count);
+  __syncthreads();
+  float gs[3] = {0.f, 0.f, 0.f};
+  if (tid < count) {
+    const float sr[3] = {s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2]};
+    const float4 q4 = ld_stream_f4(reinterpret_cast<const float4*>(q_raw) + n0 + tid);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    QuatScale qs;
+    quat_scale_forward(sr, q, qs);
+    // the reference's Sigma is a function of the full (not symmetrised) gradient: dL = <G, dSigma>, and
+    // dSigma is symmetric, so only the symmetric part of G matters
+    float G[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) G[3 * a + b] = 0.5f * (s_g[9 * tid + 3 * a + b] + s_g[9 * tid + 3 * b + a]);
+    float gq[4];
+    quat_scale_backward(qs, q, G, gs, gq);
+    reinterpret_cast<float4*>(g_q)[n0 + tid] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+  }
+  __syncthreads();
+  if (tid < count) { s_in[3 * tid] = gs[0]; s_in[3 * tid + 1] = gs[1]; s_in[3 * tid + 2] = gs[2]; }
+  __syncthreads();
+  unstage_rows<3>(g_scale, s_in, n0, count);
+}
+
+cudaError_t launch_build_sigma(int n, const float* scale_raw, const float* q_raw, float* sigma, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  build_sigma_kernel<<<ceil_div(n, kPreBlock), kPreBlock, 0, s>>>(n, scale_raw, q_raw, sigma);
+  return cudaGetLastError();
+}
+cudaError_t launch_build_sigma_bwd(int n, const float* scale_raw, const float* q_raw, const float* g_sigma,
+                                   float* g_scale, float* g_q, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  build_sigma_bwd_kernel<<<ceil_div(n, kPreBlock), kPreBlock, 0, s>>>(n, scale_raw, q_raw, g_sigma, g_scale, g_q);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone SH evaluation (spherical_harmonics.py:70-166) and its backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPreBlock) eval_sh_kernel(int n, const float* __restrict__ f_dc,
+                                                            const float* __restrict__ f_rest,
+                                                            const float* __restrict__ pts,
+                                                            const float* __restrict__ c2w,
+                                                            float* __restrict__ color) {
+  __shared__ __align__(16) float s_pos[kPreBlock * 3];
+  __shared__ __align__(16) float s_dc[kPreBlock * 3];
+  __shared__ __align__(16) float s_rest[kPreBlock * 45];
+  const int n0 = blockIdx.x * kPreBlock, count = min(kPreBlock, n - n0), tid = threadIdx.x;
+  stage_rows<3>(pts, s_pos, n0, count);
+  stage_rows<3>(f_dc, s_dc, n0, count);
+  stage_rows<45>(f_rest, s_rest, n0, count);
+  __syncthreads();
+  float rgb[3] = {0.f, 0.f, 0.f};
+  if (tid < count) {
+    const float cam[3] = {c2w[3], c2w[7], c2w[11]};
+    const float p[3] = {s_pos[3 * tid], s_pos[3 * tid + 1], s_pos[3 * tid + 2]};
+    const ViewDir vd = view_dir(p, cam);
+    float Y[16], acc[3];
+    sh_basis(vd.d, Y);
+    sh_color(&s_dc[3 * tid], &s_rest[45 * tid], Y, rgb, acc);
+  }
+  __syncthreads();
+  if (tid < count) { s_pos[3 * tid] = rgb[0]; s_pos[3 * tid + 1] = rgb[1]; s_pos[3 * tid + 2] = rgb[2]; }
+  __syncthreads();
+  unstage_rows<3>(color, s_pos, n0, count);
+}
+
+__global__ void __launch_bounds__(kPreBlock) eval_sh_bwd_kernel(int n, const float* __restrict__ f_dc,
+                                                                const float* __restrict__ f_rest,
+                                                                const float* __restrict__ pts,
+                                                                const float* __restrict__ c2w,
+                                                                const float* __restrict__ g_color,
+                                                                float* __restrict__ g_dc_out,
+                                                                float* __restrict__ g_rest_out,
+                                                                float* __restrict__ g_pts_out) {
+  __shared__ __align__(16) float s_pos[kPreBlock * 3];
+  __shared__ __align__(16) float s_dc[kPreBlock * 3];
+  __shared__ __align__(16) float s_gc[kPreBlock * 3];
+  __shared__ __align__(16) float s_rest[kPreBlock * 45];
+  const int n0 = blockIdx.x * kPreBlock, count = min(kPreBlock, n - n0), tid = threadIdx.x;
+  stage_rows<3>(pts, s_pos, n0, count);
+  stage_rows<3>(f_dc, s_dc, n0, count);
+  stage_rows<3>(g_color, s_gc, n0, count);
+  stage_rows<45>(f_rest, s_rest, n0, count);
+  __syncthreads();
+  float gp[3] = {0.f, 0.f, 0.f}, gdc[3] = {0.f, 0.f, 0.f}, g_acc[3] = {0.f, 0.f, 0.f};
+  float Y[16];
+  if (tid < count) {
+    const float cam[3] = {c2w[3], c2w[7], c2w[11]};
+    const float p[3] = {s_pos[3 * tid], s_pos[3 * tid + 1], s_pos[3 * tid + 2]};
+    const ViewDir vd = view_dir(p, cam);
+    float rgb[3], acc[3], gY[16];
+    sh_basis(vd.d, Y);
+    sh_color(&s_dc[3 * tid], &s_rest[45 * tid], Y, rgb, acc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) gY[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      g_acc[c] = s_gc[3 * tid + c] * rgb[c] * (1.f - rgb[c]);
+      gdc[c] = g_acc[c] * Y[0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) gY[k] = fmaf(g_acc[c], s_rest[45 * tid + 15 * c + k - 1], gY[k]);
+    }
+    float gd[3];
+    sh_basis_backward(vd.d, gY, gd);
+    view_dir_backward(vd, gd, gp);
+  }
+  __syncthreads();
+  if (tid < count) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      s_pos[3 * tid + c] = gp[c];
+      s_dc[3 * tid + c] = gdc[c];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) s_rest[45 * tid + 15 * c + k - 1] = g_acc[c] * Y[k];
+    }
+  }
+  __syncthreads();
+  unstage_rows<3>(g_pts_out, s_pos, n0, count);
+  unstage_rows<3>(g_dc_out, s_dc, n0, count);
+  unstage_rows<45>(g_rest_out, s_rest, n0, count);
+}
+
+cudaError_t launch_eval_sh(int n, const float* f_dc, const float* f_rest, const float* pts, const float* c2w,
+                           float* color, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  eval_sh_kernel<<<ceil_div(n, kPreBlock), kPreBlock, 0, s>>>(n, f_dc, f_rest, pts, c2w, color);
+  return cudaGetLastError();
+}
+cudaError_t launch_eval_sh_bwd(int n, const float* f_dc, const float* f_rest, const float* pts, const float* c2w,
+                               const float* g_color, float* g_dc, float* g_rest, float* g_pts, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  eval_sh_bwd_kernel<<<ceil_div(n, kPreBlock), kPreBlock, 0, s>>>(n, f_dc, f_rest, pts, c2w, g_color, g_dc, g_rest,
+                                                                  g_pts);
+  return cudaGetLastError();
+}
+
+}  // namespace gs

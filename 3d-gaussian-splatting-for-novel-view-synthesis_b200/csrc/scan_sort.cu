@@ -1,0 +1,354 @@
+// Integer stages of the binning pipeline: single-pass exclusive scan (decoupled look-back) and a
+// stable onesweep LSD radix sort of (u32 key, u32 value) pairs.  Hand-written; no CUB.
+//
+// Replaces (reference): torch.argsort (render.py:211), torch.sort on composite keys (render.py:292),
+// cumsum (render.py:302).  Roofline: HBM (streaming reads, scattered-but-run-coalesced writes).
+//
+// Both kernels hand out "virtual" block ids through an atomic ticket so that block v only ever waits
+// on blocks < v that are already resident: the look-back cannot deadlock whatever the hardware's
+// block scheduling order is.
+#include "common.cuh"
+
+namespace gs {
+
+// =================================================================================================
+// Exclusive scan
+// =================================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;   // 4096
+
+// status word: [63:32] flag (0 = empty, 1 = tile aggregate, 2 = inclusive prefix), [31:0] value
+__device__ __forceinline__ void st_status64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_status64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_status32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+size_t scan_scratch_bytes(uint32_t n) {
+  const size_t tiles = (n + kScanTile - 1) / kScanTile + 1;
+  return 256 + tiles * 8;
+}
+
+// out[i] = sum_{j<i} in[gather ? gather[j] : j];  *total_out = sum of everything.
+__global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t* __restrict__ in,
+                                                                      const uint32_t* __restrict__ gather,
+                                                                      uint32_t* __restrict__ out, uint32_t n,
+                                                                      uint32_t* __restrict__ total_out,
+                                                                      uint32_t* ticket,
+                                                                      unsigned long long* status) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kScanTile + tid * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint32_t idx = base + k;
+    uint32_t x = 0;
+    if (idx < n) x = gather ? in[gather[idx]] : in[idx];
+    v[k] = sum;          // exclusive within the thread
+    sum += x;
+  }
+  // warp inclusive scan of thread sums
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) warp_off += t;
+    tile_sum += t;
+  }
+  if (tid == 0) {
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      st_status64(status + tile, (2ull << 32) | tile_sum);
+    } else {
+      st_status64(status + tile, (1ull << 32) | tile_sum);
+      int j = (int)tile - 1;
+      while (true) {
+        const unsigned long long s = ld_status64(status + j);
+        const uint32_t flag = (uint32_t)(s >> 32);
+        if (flag == 0) { __nanosleep(32); continue; }
+        prefix += (uint32_t)s;
+        if (flag == 2) break;
+        --j;
+      }
+      st_status64(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
+    }
+    s_prefix = prefix;
+    if (total_out && tile == (n - 1) / kScanTile) *total_out = prefix + tile_sum;
+  }
+  __syncthreads();
+  const uint32_t off = s_prefix + warp_off + (inc - sum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint32_t idx = base + k;
+    if (idx < n) out[idx] = off + v[k];
+  }
+}
+
+cudaError_t launch_exclusive_scan(const uint32_t* in, const uint32_t* gather_idx, uint32_t* out, uint32_t n,
+                                  uint32_t* total_out, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  if (scratch_bytes < scan_scratch_bytes(n)) return cudaErrorInvalidValue;
+  if (n == 0) {
+    if (total_out) return cudaMemsetAsync(total_out, 0, 4, s);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMemsetAsync(scratch, 0, scan_scratch_bytes(n), s);
+  if (e != cudaSuccess) return e;
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(scratch);
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + 256);
+  const int grid = (int)((n + kScanTile - 1) / kScanTile);
+  exclusive_scan_kernel<<<grid, kScanThreads, 0, s>>>(in, gather_idx, out, n, total_out, ticket, status);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Onesweep radix sort (8-bit digits)
+// =================================================================================================
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per block
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 4;
+
+// scratch: [0,64): tickets u32[4] | [256, 256+4*256*4): global histograms | then per-pass status arrays
+static size_t sort_blocks(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+size_t sort_scratch_bytes(uint32_t n) {
+  return 256 + (size_t)kMaxPasses * kRadix * 4 + (size_t)kMaxPasses * (sort_blocks(n) + 1) * kRadix * 4;
+}
+
+struct SortPasses {
+  int num;
+  int shift[kMaxPasses];
+  int bits[kMaxPasses];
+};
+
+__device__ __forceinline__ uint32_t eff_count(uint32_t n_host, const uint32_t* n_dev) {
+  if (n_dev) { const uint32_t d = *n_dev; return d < n_host ? d : n_host; }
+  return n_host;
+}
+
+// One read of the keys builds the digit histograms of every pass.
+__global__ void __launch_bounds__(kSortThreads) sort_histogram_kernel(const uint32_t* __restrict__ keys,
+                                                                      uint32_t n_host,
+                                                                      const uint32_t* __restrict__ n_dev,
+                                                                      SortPasses sp, uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+  const uint32_t n = eff_count(n_host, n_dev);
+  for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kSortThreads) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * kSortThreads;
+  for (uint32_t i = blockIdx.x * kSortThreads + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = keys[i];
+#pragma unroll
+    for (int p = 0; p < kMaxPasses; ++p)
+      if (p < sp.num) atomicAdd(&s_hist[p][(k >> sp.shift[p]) & ((1u << sp.bits[p]) - 1u)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kSortThreads) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+}
+
+// exclusive scan of each pass's 256-bin histogram, in place (one block per pass)
+__global__ void __launch_bounds__(kRadix) sort_scan_hist_kernel(uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t s[kRadix];
+  uint32_t* h = ghist + blockIdx.x * kRadix;
+  const int t = threadIdx.x;
+  const uint32_t mine = h[t];
+  s[t] = mine;
+  __syncthreads();
+  for (int d = 1; d < kRadix; d <<= 1) {
+    const uint32_t add = (t >= d) ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += add;
+    __syncthreads();
+  }
+  h[t] = s[t] - mine;
+}
+
+__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int shift, int bits,
+    const uint32_t* __restrict__ gbase /*[256] exclusive*/, uint32_t* __restrict__ status, uint32_t* ticket) {
+  __shared__ uint32_t s_warp_hist[kSortWarps][kRadix + 1];
+  __shared__ uint32_t s_keys[kSortTile];
+  __shared__ uint32_t s_vals[kSortTile];
+  __shared__ uint32_t s_digit_start[kRadix];
+  __shared__ uint32_t s_delta[kRadix];
+  __shared__ uint32_t s_scan[kRadix];
+  __shared__ uint32_t s_vbid;
+
+  const uint32_t n = eff_count(n_host, n_dev);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_vbid = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kSortWarps * (kRadix + 1); i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t vbid = s_vbid;
+  const uint32_t base = vbid * (uint32_t)kSortTile;
+  if (base >= n) return;   // uniform for the whole block
+  const uint32_t mask = (1u << bits) - 1u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+
+  // ---- load (warp-striped: item i of lane l sits at warp_base + 32 i + l) and rank ---------------------
+  const uint32_t warp_base = base + warp * (32 * kSortItems);
+  uint32_t key[kSortItems];
+  uint32_t rank[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = warp_base + i * 32 + lane;
+    key[i] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = warp_base + i * 32 + lane;
+    const uint32_t d = (idx < n) ? ((key[i] >> shift) & mask) : (uint32_t)kRadix;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) {
+      old = s_warp_hist[warp][d];
+      s_warp_hist[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[i] = old + __popc(peers & lane_lt);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit (thread d): exclusive offsets across warps, block count, look-back ----------------------
+  uint32_t cnt = 0;
+  {
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t t = s_warp_hist[w][tid];
+      s_warp_hist[w][tid] = cnt;
+      cnt += t;
+    }
+    uint32_t* st = status + (size_t)vbid * kRadix + tid;
+    uint32_t excl = 0;
+    if (vbid == 0) {
+      st_status32(st, (2u << 30) | cnt);
+    } else {
+      st_status32(st, (1u << 30) | cnt);
+      int j = (int)vbid - 1;
+      while (true) {
+        const uint32_t sv = ld_status32(status + (size_t)j * kRadix + tid);
+        const uint32_t flag = sv >> 30;
+        if (flag == 0) { __nanosleep(32); continue; }
+        excl += sv & 0x3FFFFFFFu;
+        if (flag == 2) break;
+        --j;
+      }
+      st_status32(st, (2u << 30) | (excl + cnt));
+    }
+    // block-level exclusive scan of cnt over the 256 digits
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int d = 1; d < kRadix; d <<= 1) {
+      const uint32_t add = (tid >= d) ? s_scan[tid - d] : 0u;
+      __syncthreads();
+      s_scan[tid] += add;
+      __syncthreads();
+    }
+    const uint32_t dstart = s_scan[tid] - cnt;
+    s_digit_start[tid] = dstart;
+    s_delta[tid] = gbase[tid] + excl - dstart;
+  }
+  __syncthreads();
+
+  // ---- scatter into shared memory in sorted order, then stream out in digit runs -------------------------
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = warp_base + i * 32 + lane;
+    if (idx < n) {
+      const uint32_t d = (key[i] >> shift) & mask;
+      const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[i];
+      s_keys[pos] = key[i];
+      s_vals[pos] = vals_in ? vals_in[idx] : idx;
+    }
+  }
+  __syncthreads();
+  const uint32_t in_block = min((uint32_t)kSortTile, n - base);
+  for (uint32_t p = tid; p < in_block; p += kSortThreads) {
+    const uint32_t k = s_keys[p];
+    const uint32_t d = (k >> shift) & mask;
+    const uint32_t dst = s_delta[d] + p;
+    keys_out[dst] = k;
+    vals_out[dst] = s_vals[p];
+  }
+}
+
+// Sorts on key bits [begin_bit, end_bit) with ceil(bits/8) passes.  Pass 0 reads (keys_src, vals_src) and
+// writes (keys_b, vals_b); later passes ping-pong b -> a -> b ...  `*result_in_a` tells where the sorted
+// data ended up (a for an even pass count, b for an odd one).  keys_src may alias keys_a (then the
+// source is clobbered by pass 1) or be a separate read-only buffer.  vals_src == nullptr means
+// "values are 0..n-1".  n is the host-side upper bound used for grid sizing; n_dev (optional) holds the
+// real count on the device.
+cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_a,
+                              uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
+                              const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
+                              size_t scratch_bytes, int* result_in_a, cudaStream_t s) {
+  if (end_bit <= begin_bit || end_bit - begin_bit > 8 * kMaxPasses) return cudaErrorInvalidValue;
+  if (scratch_bytes < sort_scratch_bytes(n)) return cudaErrorInvalidValue;
+  SortPasses sp;
+  sp.num = (end_bit - begin_bit + 7) / 8;
+  for (int p = 0; p < kMaxPasses; ++p) { sp.shift[p] = 0; sp.bits[p] = 8; }
+  for (int p = 0; p < sp.num; ++p) {
+    sp.shift[p] = begin_bit + 8 * p;
+    sp.bits[p] = (end_bit - sp.shift[p]) < 8 ? (end_bit - sp.shift[p]) : 8;
+  }
+  if (result_in_a) *result_in_a = (sp.num % 2 == 0) ? 1 : 0;
+  if (n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), s);
+  if (e != cudaSuccess) return e;
+  uint32_t* tickets = reinterpret_cast<uint32_t*>(scratch);
+  uint32_t* ghist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 256);
+  uint32_t* status0 = ghist + kMaxPasses * kRadix;
+  const size_t nblk = sort_blocks(n);
+  int hgrid = (int)((n + kSortThreads * 8 - 1) / (kSortThreads * 8));
+  if (hgrid > 148 * 8) hgrid = 148 * 8;
+  sort_histogram_kernel<<<hgrid, kSortThreads, 0, s>>>(keys_src, n, n_dev, sp, ghist);
+  sort_scan_hist_kernel<<<sp.num, kRadix, 0, s>>>(ghist);
+  const uint32_t *ki = keys_src, *vi = vals_src;
+  uint32_t *ko = keys_b, *vo = vals_b;
+  for (int p = 0; p < sp.num; ++p) {
+    uint32_t* status = status0 + (size_t)p * (nblk + 1) * kRadix;
+    onesweep_pass_kernel<<<(int)nblk, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, n_dev, sp.shift[p], sp.bits[p],
+                                                           ghist + p * kRadix, status, tickets + p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ki = ko; vi = vo;
+    if (ko == keys_b) { ko = keys_a; vo = vals_a; } else { ko = keys_b; vo = vals_b; }
+  }
+  return cudaSuccess;
+}
+
+}  // namespace gs

@@ -1,0 +1,177 @@
+/*
+ * b200gs - C ABI of the B200-native (sm_100a) differentiable Gaussian-splat rasterizer.
+ *
+ * This is the drop-in boundary for the reference's render path.  The reference
+ * (ashu1069/3D-Gaussian-Splatting-for-Novel-View-Synthesis) has no FFI: the path sits behind three
+ * Python callables.  Each entry point below names the reference interface it replaces:
+ *
+ *   gaussian_splatting/gaussian.py:71            build_sigma_from_params(scale_raw, q_raw)
+ *   gaussian_splatting/spherical_harmonics.py:70 evaluate_sh(f_dc, f_rest, points, c2w)
+ *   gaussian_splatting/render.py:62-64           render(pos, color, opacity_raw, sigma, c2w, H, W,
+ *                                                       fx, fy, cx, cy, near, far, pix_guard, T,
+ *                                                       min_conis, chi_square_clip, alpha_max,
+ *                                                       alpha_cutoff)
+ *   (autograd of the three above)                scripts/train.py:530  total_loss.backward()
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all buffers are caller-owned (the Python host allocates them with torch's caching allocator);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream unless
+ *     stated otherwise;
+ *   - return value: 0 = OK, negative = B200GS_ERR_* (no exceptions cross this boundary);
+ *   - fp32 arithmetic throughout ("dtype": "f32"); tile size is fixed at 16x16 (the reference's
+ *     callers never pass another T).
+ */
+#ifndef B200GS_H
+#define B200GS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GS_ABI_VERSION 1
+#define B200GS_TILE 16
+
+enum {
+  B200GS_OK = 0,
+  B200GS_ERR_ARG = -1,       /* null / inconsistent argument */
+  B200GS_ERR_WORKSPACE = -2, /* workspace too small */
+  B200GS_ERR_CUDA = -3,      /* a CUDA runtime call failed; see b200gs_last_error() */
+  B200GS_ERR_TILE = -4,      /* T != 16 */
+  B200GS_ERR_CAPACITY = -5   /* intersection list did not fit isect_capacity (result invalid) */
+};
+
+/* The Gaussian set.  `pos` and `opacity_raw` are always required.  Shape/colour come either from
+ * the raw parameters (fused path: scale_raw+q_raw and/or f_dc+f_rest non-null) or precomputed
+ * (sigma / color non-null) exactly as the reference's render() receives them. */
+typedef struct b200gs_gaussians {
+  int32_t n;
+  const float* pos;         /* [n,3] */
+  const float* opacity_raw; /* [n]   */
+  const float* scale_raw;   /* [n,3]  log-scales            (or NULL -> use sigma) */
+  const float* q_raw;       /* [n,4]  quaternion (x,y,z,w)  (or NULL -> use sigma) */
+  const float* sigma;       /* [n,3,3] precomputed covariance (used when scale_raw==NULL) */
+  const float* f_dc;        /* [n,3]  SH band 0             (or NULL -> use color) */
+  const float* f_rest;      /* [n,45] SH bands 1-3, channel-major (or NULL -> use color) */
+  const float* color;       /* [n,3]  precomputed RGB (used when f_dc==NULL) */
+} b200gs_gaussians;
+
+/* Camera + the keyword arguments of render.py:62-64 (doubles, because the reference receives Python
+ * floats and casts them to fp32 only at the point of use; the library does the same). */
+typedef struct b200gs_camera {
+  const float* c2w; /* DEVICE pointer, 16 floats row-major (render.py: c2w is a device tensor) */
+  int32_t H, W;
+  double fx, fy, cx, cy;
+  double near_plane, far_plane, pix_guard;
+  double min_conis, chi_square_clip, alpha_max, alpha_cutoff;
+  int32_t tile;          /* must be 16 */
+  int32_t tile_row_begin; /* render only tile rows [begin, end) - tile-row sharding; 0,0 = all */
+  int32_t tile_row_end;
+} b200gs_camera;
+
+/* Gradients written by b200gs_render_backward.  Non-null members are OVERWRITTEN (dense, zero for
+ * culled Gaussians).  Members for the path not in use must be NULL. */
+typedef struct b200gs_grads {
+  float* pos;         /* [n,3] */
+  float* opacity_raw; /* [n]   */
+  float* scale_raw;   /* [n,3] */
+  float* q_raw;       /* [n,4] */
+  float* sigma;       /* [n,3,3] */
+  float* f_dc;        /* [n,3] */
+  float* f_rest;      /* [n,45] */
+  float* color;       /* [n,3] */
+} b200gs_grads;
+
+typedef struct b200gs_sizes {
+  size_t frame_bytes; /* per-Gaussian + per-tile + per-pixel state (must survive until backward) */
+  size_t isect_bytes; /* per-intersection lists for `isect_capacity` entries */
+} b200gs_sizes;
+
+/* Counters the device leaves in the first 64 bytes of the frame workspace. */
+typedef struct b200gs_frame_stats {
+  uint32_t n_isect;    /* I: total (tile, Gaussian) intersections */
+  uint32_t n_visible;  /* V: Gaussians that survive every cull */
+  uint32_t overflow;   /* 1 if I exceeded isect_capacity in rasterize */
+  uint32_t n_in_frustum; /* survivors of S1-S7 (before the on-screen test; render.py:235 raises when
+                            this is > 0 but n_visible == 0) */
+  uint32_t reserved[12];
+} b200gs_frame_stats;
+
+int b200gs_abi_version(void);
+const char* b200gs_last_error(void);
+
+/* Workspace sizes for n Gaussians, an HxW frame and room for isect_capacity intersections. */
+int b200gs_workspace_sizes(int32_t n, int32_t H, int32_t W, uint32_t isect_capacity, b200gs_sizes* out);
+
+/* gaussian.py:71-127.  sigma_out [n,3,3]. */
+int b200gs_build_sigma(int32_t n, const float* scale_raw, const float* q_raw, float* sigma_out, void* stream);
+/* autograd of the above: grad_sigma [n,3,3] -> grad_scale_raw [n,3], grad_q_raw [n,4] (overwritten). */
+int b200gs_build_sigma_backward(int32_t n, const float* scale_raw, const float* q_raw,
+                                const float* grad_sigma, float* grad_scale_raw, float* grad_q_raw,
+                                void* stream);
+
+/* spherical_harmonics.py:70-166.  color_out [n,3]. */
+int b200gs_evaluate_sh(int32_t n, const float* f_dc, const float* f_rest, const float* points,
+                       const float* c2w, float* color_out, void* stream);
+/* autograd of the above: grad_color [n,3] -> grad_f_dc [n,3], grad_f_rest [n,45], grad_points [n,3]. */
+int b200gs_evaluate_sh_backward(int32_t n, const float* f_dc, const float* f_rest, const float* points,
+                                const float* c2w, const float* grad_color, float* grad_f_dc,
+                                float* grad_f_rest, float* grad_points, void* stream);
+
+/* render.py:104-258 + 305-315 (S1-S11, S15) fused with Sigma/SH when given raw parameters, then the
+ * global depth sort (S8) and the prefix sum over tile counts.  Leaves I in the frame header; when
+ * `stats_host` (pinned host memory) is non-null the header is also copied there asynchronously. */
+int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws,
+                          size_t frame_bytes, b200gs_frame_stats* stats_host, void* stream);
+
+/* render.py:260-410 (S12-S17): emit (tile, id) pairs in depth order, stable radix sort by tile,
+ * tile ranges, per-tile front-to-back blend.  image_out [H,W,3], clamped to [0,1].
+ * If I > isect_capacity the overflow flag in the frame header is set and the image is invalid. */
+int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes,
+                            void* isect_ws, size_t isect_bytes, uint32_t isect_capacity,
+                            float* image_out, b200gs_frame_stats* stats_host, void* stream);
+
+/* Backward of project+rasterize (scripts/train.py:530): grad_image [H,W,3] -> b200gs_grads.
+ * Needs the frame/isect workspaces exactly as the forward left them. */
+int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws,
+                           size_t frame_bytes, void* isect_ws, size_t isect_bytes,
+                           uint32_t isect_capacity, const float* grad_image, const b200gs_grads* grads,
+                           void* stream);
+
+/* One-call forward with HOST buffers (pageable or pinned): uploads the Gaussian set and the pose,
+ * allocates its own device workspaces, renders, downloads the image.  Synchronous.  This is the call
+ * `bench.py` times as "e2e".  c2w_host: 16 floats.  image_host: [H,W,3]. */
+int b200gs_render_host(const b200gs_gaussians* g_host, const b200gs_camera* cam, const float* c2w_host,
+                       float* image_host, b200gs_frame_stats* stats_out);
+
+/* Introspection for parity tests: copies of device-side per-Gaussian results.  All optional outputs
+ * are DEVICE pointers of n elements (xy: [n,2], conic: [n,3], rect: [n,4] int32 tile rect
+ * tu0,tu1,tv0,tv1), valid after b200gs_render_project. */
+int b200gs_debug_export(int32_t n, const void* frame_ws, size_t frame_bytes, int32_t H, int32_t W,
+                        float* xy, float* depth, float* conic, float* opacity, float* color,
+                        int32_t* radius, int32_t* rect, int32_t* tiles_touched, int32_t* depth_order,
+                        void* stream);
+/* After rasterize: sorted (tile, Gaussian id) list and per-tile ranges [tiles,2]. */
+int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const void* isect_ws,
+                              size_t isect_bytes, uint32_t isect_capacity, int32_t n, int32_t H, int32_t W,
+                              int32_t* list_tile, int32_t* list_id, uint32_t count, int32_t* ranges,
+                              void* stream);
+
+/* Stand-alone primitives (exported for unit tests of the integer stages). */
+int b200gs_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out,
+                              void* scratch, size_t scratch_bytes, void* stream);
+size_t b200gs_scan_scratch_bytes(uint32_t n);
+/* Stable LSD radix sort of (key, value) pairs on key bits [begin_bit, end_bit).  Results end up in
+ * keys_out/vals_out; keys_in/vals_in are clobbered. */
+int b200gs_radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                            uint32_t n, int begin_bit, int end_bit, void* scratch, size_t scratch_bytes,
+                            void* stream);
+size_t b200gs_sort_scratch_bytes(uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GS_H */

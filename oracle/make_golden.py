@@ -115,6 +115,23 @@ def run_case(name, scene_fn, cam_kw, with_grad):
             report[f"grad_{k}_relerr"] = err
             report[f"grad_{k}_nonfinite"] = int((~fin).sum())
 
+    # --- fp64 run of the oracle: the arbiter for fp32 round-off (threshold flips, ill-conditioned
+    # covariances): a result counts as matching when it is as close to this as the fp32 reference is.
+    l3 = {k: sc[k].double().clone().requires_grad_(with_grad) for k in PARAMS}
+    c2w64 = c2w.double()
+    sig64 = O.build_sigma_from_params(l3["scale_raw"], l3["q_raw"])
+    col64 = O.evaluate_sh(l3["f_dc"], l3["f_rest"], l3["pos"], c2w64)
+    img64 = O.render(l3["pos"], col64, l3["opacity_raw"], sig64, c2w64, H, W, fx, fy, cx, cy)
+    out["image64"] = img64.detach().numpy()
+    d = (img_ref.detach().double() - img64.detach()).abs()
+    report["ref32_vs_64_image_max"] = float(d.max())
+    report["ref32_vs_64_image_n_gt_1e-4"] = int((d > 1e-4).sum())
+    if with_grad:
+        grads64 = torch.autograd.grad((img64 * wimg.double()).sum(), [l3[k] for k in PARAMS])
+        for k, g64, g32 in zip(PARAMS, grads64, grads_ref):
+            out[f"grad64_{k}"] = g64.numpy()
+            report[f"ref32_vs_64_grad_{k}"] = float((g32.double() - g64).abs().max() / g64.abs().max())
+
     # --- intermediates -----------------------------------------------------------------------------
     out.update(ids=proj.ids.numpy().astype(np.int32), u=proj.u.detach().numpy(), v=proj.v.detach().numpy(),
                z=proj.z.detach().numpy(), opacity=proj.opacity.detach().numpy(),

