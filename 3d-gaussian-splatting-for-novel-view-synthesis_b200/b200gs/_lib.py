@@ -54,7 +54,7 @@ SYMBOLS = {
     "b200gs_build_sigma": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200gs_build_sigma_backward": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200gs_evaluate_sh": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b200gs_evaluate_sh_backward": (c_int, [c_int32] + [c_void_p] * 10),
+    "b200gs_evaluate_sh_backward": (c_int, [c_int32] + [c_void_p] * 9),
     "b200gs_render_project": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200gs_render_rasterize": (c_int, [POINTER(Camera), c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_uint32,
                                         c_void_p, c_void_p, c_void_p]),
