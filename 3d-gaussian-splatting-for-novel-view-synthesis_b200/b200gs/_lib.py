@@ -64,6 +64,10 @@ SYMBOLS = {
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
     "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
+    "b200gs_profile_enable": (c_int, [c_int]),
+    "b200gs_profile_collect": (c_int, [c_void_p, c_void_p, c_int32]),
+    "b200gs_profile_region_name": (c_char_p, [c_int32]),
+    "b200gs_kernel_launch_count": (ctypes.c_ulonglong, []),
     "b200gs_exclusive_scan_u32": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200gs_scan_scratch_bytes": (c_size_t, [c_uint32]),
     "b200gs_radix_sort_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_void_p,

@@ -2,8 +2,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,6 +25,42 @@ int fail_cuda(cudaError_t e, const char* where) {
   do {                                                   \
     cudaError_t _e = (expr);                             \
     if (_e != cudaSuccess) return fail_cuda(_e, #expr);  \
+  } while (0)
+
+// --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
+enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_RANGES, R_BLEND_FWD, R_BLEND_BWD,
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_COUNT };
+const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_pairs", "tile_sort", "tile_ranges",
+                                     "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
+                                     "evaluate_sh_bwd", "build_sigma_bwd"};
+struct ProfRec { int region; cudaEvent_t a, b; };
+struct Profiler {
+  std::mutex mu;
+  bool on = false;
+  std::vector<ProfRec> recs;
+};
+Profiler g_prof;
+std::atomic<unsigned long long> g_launches{0};
+
+struct ProfScope {
+  int region; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(int region_, cudaStream_t s_, int launches) : region(region_), s(s_) {
+    g_launches.fetch_add((unsigned long long)launches, std::memory_order_relaxed);
+    if (!g_prof.on) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+    cudaEventRecord(a, s);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.recs.push_back({region, a, b});
+  }
+};
+#define PCU(region, launches, expr)             \
+  do {                                          \
+    ProfScope _scope(region, s, launches);      \
+    CU(expr);                                   \
   } while (0)
 
 int tile_bits(int n_tiles) {
@@ -149,7 +187,8 @@ int b200gs_workspace_sizes(int32_t n, int32_t H, int32_t W, uint32_t isect_capac
 int b200gs_build_sigma(int32_t n, const float* scale_raw, const float* q_raw, float* sigma_out, void* stream) {
   if (n < 0 || (n > 0 && (!scale_raw || !q_raw || !sigma_out))) return fail(B200GS_ERR_ARG, "build_sigma: null");
   if (reinterpret_cast<uintptr_t>(q_raw) & 15u) return fail(B200GS_ERR_ARG, "q_raw must be 16-byte aligned");
-  CU(gs::launch_build_sigma(n, scale_raw, q_raw, sigma_out, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_BUILD_SIGMA, 1, gs::launch_build_sigma(n, scale_raw, q_raw, sigma_out, s));
   return B200GS_OK;
 }
 
@@ -159,7 +198,8 @@ int b200gs_build_sigma_backward(int32_t n, const float* scale_raw, const float* 
     return fail(B200GS_ERR_ARG, "build_sigma_backward: null");
   if ((reinterpret_cast<uintptr_t>(q_raw) & 15u) || (reinterpret_cast<uintptr_t>(grad_q_raw) & 15u))
     return fail(B200GS_ERR_ARG, "q_raw / grad_q_raw must be 16-byte aligned");
-  CU(gs::launch_build_sigma_bwd(n, scale_raw, q_raw, grad_sigma, grad_scale_raw, grad_q_raw, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_BUILD_SIGMA_BWD, 1, gs::launch_build_sigma_bwd(n, scale_raw, q_raw, grad_sigma, grad_scale_raw, grad_q_raw, s));
   return B200GS_OK;
 }
 
@@ -167,7 +207,8 @@ int b200gs_evaluate_sh(int32_t n, const float* f_dc, const float* f_rest, const 
                        float* color_out, void* stream) {
   if (n < 0 || (n > 0 && (!f_dc || !f_rest || !points || !c2w || !color_out)))
     return fail(B200GS_ERR_ARG, "evaluate_sh: null");
-  CU(gs::launch_eval_sh(n, f_dc, f_rest, points, c2w, color_out, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_EVAL_SH, 1, gs::launch_eval_sh(n, f_dc, f_rest, points, c2w, color_out, s));
   return B200GS_OK;
 }
 
@@ -177,8 +218,8 @@ int b200gs_evaluate_sh_backward(int32_t n, const float* f_dc, const float* f_res
   if (n < 0 || (n > 0 && (!f_dc || !f_rest || !points || !c2w || !grad_color || !grad_f_dc || !grad_f_rest ||
                           !grad_points)))
     return fail(B200GS_ERR_ARG, "evaluate_sh_backward: null");
-  CU(gs::launch_eval_sh_bwd(n, f_dc, f_rest, points, c2w, grad_color, grad_f_dc, grad_f_rest, grad_points,
-                            (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_EVAL_SH_BWD, 1, gs::launch_eval_sh_bwd(n, f_dc, f_rest, points, c2w, grad_color, grad_f_dc, grad_f_rest, grad_points, s));
   return B200GS_OK;
 }
 
@@ -197,16 +238,16 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
   CU(cudaMemsetAsync(stats, 0, sizeof(b200gs_frame_stats), s));
   if (gi.n > 0) {
-    CU(gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s));
+    PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s));
     // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
     int in_a = 0;
-    CU(gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
+    PCU(R_DEPTH_SORT, 6, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
                              gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2), gs::ws_ptr<uint32_t>(frame_ws, L.order),
                              gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
                              (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
                              &in_a, s));
     if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
-    CU(gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
+    PCU(R_SCAN, 1, gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
                                  gs::ws_ptr<uint32_t>(frame_ws, L.offsets), (uint32_t)gi.n, &stats->n_isect,
                                  gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
   }
@@ -230,15 +271,15 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   const int n_tiles = rp.tiles_x * rp.tiles_y;
   uint32_t* keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys);
   uint32_t* vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals);
-  CU(gs::launch_emit_pairs(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
+  PCU(R_EMIT, 1, gs::launch_emit_pairs(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
                            gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint2>(frame_ws, L.rect),
                            rp.tiles_x, isect_capacity, keys, vals, stats, s));
   int in_a = 0;
-  CU(gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
+  PCU(R_TILE_SORT, 2 + (tile_bits(n_tiles) + 7) / 8, gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
                            gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_isect, 0,
                            tile_bits(n_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s));
   const SortedLists sl = sorted_lists(isect_ws, IL, n_tiles);
-  CU(gs::launch_tile_ranges(sl.keys, isect_capacity, stats, gs::ws_ptr<uint2>(frame_ws, L.ranges), n_tiles, s));
+  PCU(R_RANGES, 1, gs::launch_tile_ranges(sl.keys, isect_capacity, stats, gs::ws_ptr<uint2>(frame_ws, L.ranges), n_tiles, s));
   // pixels of tiles outside this rank's band are not touched; the whole image is zeroed first so that
   // "pixels in empty tiles stay 0" (render.py:318) also holds for bands
   if (rp.row_begin == 0 && rp.row_end == rp.tiles_y) {
@@ -246,7 +287,7 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   } else {
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }
-  CU(gs::launch_blend_fwd(rp, frame_ws, L, sl.vals, image_out, s));
+  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, sl.vals, image_out, s));
   if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
   return B200GS_OK;
 }
@@ -277,8 +318,8 @@ int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   const SortedLists sl = sorted_lists(isect_ws, IL, rp.tiles_x * rp.tiles_y);
-  CU(gs::launch_blend_bwd(rp, frame_ws, L, sl.vals, grad_image, gi.n, s));
-  CU(gs::launch_preprocess_bwd(gi, gg, cam->c2w, rp, frame_ws, L, s));
+  PCU(R_BLEND_BWD, 1, gs::launch_blend_bwd(rp, frame_ws, L, sl.vals, grad_image, gi.n, s));
+  PCU(R_PREPROCESS_BWD, 1, gs::launch_preprocess_bwd(gi, gg, cam->c2w, rp, frame_ws, L, s));
   return B200GS_OK;
 }
 
@@ -372,6 +413,31 @@ int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const vo
   CU(cudaGetLastError());
   return B200GS_OK;
 }
+
+int b200gs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  for (ProfRec& r : g_prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.recs.clear();
+  g_prof.on = on != 0;
+  return B200GS_OK;
+}
+
+int b200gs_profile_collect(float* ms_out, int32_t* calls_out, int32_t max_regions) {
+  if (!ms_out || !calls_out || max_regions < R_COUNT) return fail(B200GS_ERR_ARG, "profile_collect: need room for all regions");
+  CU(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  for (int i = 0; i < max_regions; ++i) { ms_out[i] = 0.f; calls_out[i] = 0; }
+  for (ProfRec& r : g_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_out[r.region] += ms; calls_out[r.region] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.recs.clear();
+  return R_COUNT;
+}
+
+const char* b200gs_profile_region_name(int32_t id) { return (id >= 0 && id < R_COUNT) ? kRegionNames[id] : ""; }
+unsigned long long b200gs_kernel_launch_count(void) { return g_launches.load(); }
 
 size_t b200gs_scan_scratch_bytes(uint32_t n) { return gs::scan_scratch_bytes(n); }
 size_t b200gs_sort_scratch_bytes(uint32_t n) { return gs::sort_scratch_bytes(n); }

@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""Benchmark of the render path: render frames/s (+ train iterations/s) on the BASELINE.json headline
+workload - 1M Gaussians, 1920x1080, SH degree 3, synthetic seeded scene.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200gs|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one view:
+  render step = evaluate_sh + render under no_grad   (the reference's own timed region,
+                scripts/render_trained.py:337-349; build_sigma is outside, as at :192)
+  train step  = build_sigma + evaluate_sh + render + weighted-sum loss + backward (+ NCCL all-reduce of the
+                six gradient tensors when N > 1)      (scripts/train.py:463-530)
+Multi-GPU: one process per GPU; render frames are sharded round-robin (no collective), training views are
+data-parallel (weak scaling: per-GPU work fixed).  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's algorithm on the host CPU cores (the oracle port, since the
+reference checkout does not exist on the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "3d-gaussian-splatting-for-novel-view-synthesis_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(name="1M Gaussians, 1920x1080, SH3, log-scale -5.5 (headline)", n=1_000_000, W=1920, H=1080,
+                log_scale=-5.5, sh_degree=3, n_views=16, seed=0)
+PARAMS = ("pos", "scale_raw", "q_raw", "opacity_raw", "f_dc", "f_rest")
+METRIC = "render FPS (+ train it/s), 1M Gaussians 1080p SH3"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_frame_sample(sc, cam, budget_s: float):
+    """One bounded sample of the headline frame on the CPU: projection + binning of ALL Gaussians, then the
+    reference's per-tile blend loop on every k-th non-empty tile, k chosen to fit the budget.  Returns the
+    estimated seconds per full frame (project + bin + blend_time * k) and a description."""
+    from oracle import gs_oracle as O
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        color = O.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], cam["c2w"])
+        proj = O.project(sc["pos"], color, sc["opacity_raw"], sc["sigma"], cam["c2w"], cam["H"], cam["W"], cam["fx"],
+                         cam["fy"], cam["cx"], cam["cy"])
+        bins = O.bin_tiles(proj)
+        t1 = time.perf_counter()
+        n_tiles = int(bins.uniq_tiles.shape[0])
+        # calibrate the per-tile cost on a handful of tiles, then pick the stride
+        probe = max(1, n_tiles // 24)
+        O.blend(proj, bins, tile_stride=probe)
+        t2 = time.perf_counter()
+        per_tile = (t2 - t1) / max(1, len(range(0, n_tiles, probe)))
+        want = max(8, int(budget_s / max(per_tile, 1e-6)))
+        stride = max(1, n_tiles // want)
+        t3 = time.perf_counter()
+        O.blend(proj, bins, tile_stride=stride)
+        t4 = time.perf_counter()
+        blended = len(range(0, n_tiles, stride))
+    est = (t1 - t0) + (t4 - t3) * (n_tiles / blended)
+    desc = (f"evaluate_sh+project+bin of all {sc['pos'].shape[0]} Gaussians ({t1 - t0:.2f} s) + reference per-tile blend "
+            f"loop on {blended} of {n_tiles} non-empty tiles ({t4 - t3:.2f} s), extrapolated linearly in tiles")
+    return est, desc, dict(V=proj.stage_counts["visible"], I=proj.stage_counts["intersections"])
+
+
+def cpu_scene():
+    from oracle import gs_oracle as O
+    wl = WORKLOAD
+    sc = O.make_scene(wl["n"], seed=wl["seed"], log_scale=wl["log_scale"], sh_degree=wl["sh_degree"])
+    sc["sigma"] = O.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+    cams = [O.make_camera(wl["W"], wl["H"], view=v, n_views=wl["n_views"]) for v in range(wl["n_views"])]
+    return sc, cams
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc, cams = cpu_scene()
+    total_steps = args.steps + args.warmup
+    budget = min(20.0, max(1.0, 150.0 / max(1, total_steps) - 4.0))
+    ests, desc, counts = [], "", {}
+    t_begin = time.perf_counter()
+    for i in range(total_steps):
+        est, desc, counts = cpu_frame_sample(sc, cams[i % len(cams)], budget)
+        if i >= args.warmup:
+            ests.append(est)
+        if time.perf_counter() - t_begin > 420 and len(ests) >= 1:      # hard stop: stay within minutes
+            break
+    sec = sum(ests) / len(ests)
+    fps = 1.0 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(ests), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "device": "host CPU", **counts},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "torch_threads": torch.get_num_threads(),
+                             "kind": "port", "sample": desc},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# b200gs arm
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, V, I, P, tiles):
+    """Compulsory HBM bytes per kernel group for one view (each stage reads its inputs once and writes its
+    outputs once; a sort counts as one read + one write of its pairs whatever the pass count) - DESIGN.md."""
+    return {
+        "preprocess_fwd": 236 * N + 64 * V + 8 * (N - V),
+        "evaluate_sh": 204 * N + 12 * N,
+        "depth_sort": 4 * N + 8 * N,
+        "scan": 4 * N + 4 * N + 4 * N,
+        "emit_pairs": 12 * N + 8 * V + 8 * I,
+        "tile_sort": 8 * I + 8 * I,
+        "tile_ranges": 4 * I + 8 * tiles,
+        "blend_fwd": 4 * I + 36 * I + 12 * P + 8 * P,
+        "blend_bwd": 4 * I + 36 * I + 36 * I + 12 * P + 8 * P,
+        "preprocess_bwd": 236 * N + 36 * V + 236 * N,
+        "build_sigma": 28 * N + 36 * N,
+    }
+
+
+def run_b200gs(args):
+    import torch.distributed as dist
+    import b200gs
+    from b200gs import _lib, ops
+    from b200gs.dist import allreduce_gradients
+    from oracle import gs_oracle as O   # scene generator + cpu_baseline leg only (never on the product path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200gs arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = b200gs.load_library()
+    os.environ.setdefault("B200GS_CAPACITY_MODE", "speculative")
+    wl = WORKLOAD
+    H, W, K, Wm = wl["H"], wl["W"], args.steps, args.warmup
+
+    sc_cpu = O.make_scene(wl["n"], seed=wl["seed"], log_scale=wl["log_scale"], sh_degree=wl["sh_degree"])
+    sc = {k: v.to(dev) for k, v in sc_cpu.items()}
+    cams = [O.make_camera(W, H, view=v, n_views=wl["n_views"]) for v in range(wl["n_views"])]
+    c2w_dev = [c["c2w"].to(dev) for c in cams]
+    c2w_pin = [c["c2w"].clone().pin_memory() for c in cams]
+    intr = cams[0]
+    view_of = lambda step: (rank + world * step) % len(cams)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def render_step(c2w):
+        colors = b200gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
+        return b200gs.render(sc["pos"], colors, sc["opacity_raw"], sigma, c2w, H, W, intr["fx"], intr["fy"],
+                             intr["cx"], intr["cy"])
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.b200gs_kernel_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), lib.b200gs_kernel_launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- render: device-resident inputs ("value") --------------------------------------------------------
+    with torch.no_grad():
+        sigma = b200gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+        ms_render, launches_render = timed(lambda i: render_step(c2w_dev[view_of(i)]), K, Wm)
+        # ---- render e2e: pose from pinned host memory in, image to pinned host memory out, every step ----
+        img_pin = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            c2w = c2w_pin[view_of(i)].to(dev, non_blocking=True)
+            img = render_step(c2w)
+            img_pin.copy_(img, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for i in range(Wm):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(Wm + i)
+        barrier()
+        s_e2e = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- train: fwd + bwd (+ all-reduce) --------------------------------------------------------------------
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in PARAMS}
+    wimg = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1234))
+    wimg_dev = (wimg / world).to(dev)
+    wimg_pin = (wimg / world).pin_memory()
+
+    def train_step(i, w=None):
+        for p in leaves.values():
+            p.grad = None
+        c2w = c2w_dev[view_of(i)]
+        sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        img = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sg, c2w, H, W, intr["fx"], intr["fy"],
+                            intr["cx"], intr["cy"])
+        loss = (img * (wimg_dev if w is None else w)).sum()
+        loss.backward()
+        allreduce_gradients(leaves.values())
+        return loss
+    ms_train, launches_train = timed(lambda i: train_step(i), K, Wm)
+
+    def train_e2e_step(i):
+        w = wimg_pin.to(dev, non_blocking=True)          # the step's target image comes from the host
+        loss = train_step(i, w)
+        return float(loss.item())                        # D2H read of the step's result
+    for i in range(min(Wm, 3)):
+        train_e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        train_e2e_step(Wm + i)
+    barrier()
+    s_train_e2e = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event times (separate pass with an event pair around every kernel group) ------------
+    lib.b200gs_profile_enable(1)
+    with torch.no_grad():
+        for i in range(K):
+            render_step(c2w_dev[view_of(i)])
+    torch.cuda.synchronize()
+    nreg = 16
+    ms_buf, call_buf = (ctypes.c_float * nreg)(), (ctypes.c_int32 * nreg)()
+    n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
+    fwd_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
+                   for r in range(n_regions) if call_buf[r]}
+    for i in range(K):
+        train_step(i)
+    torch.cuda.synchronize()
+    n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
+    train_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
+                     for r in range(n_regions) if call_buf[r]}
+    lib.b200gs_profile_enable(0)
+
+    # ---- frame statistics of view 0 (V, I) for the byte model ---------------------------------------------------
+    with torch.no_grad():
+        g, keep = ops._gaussians(sc["pos"], sc["opacity_raw"], sc["scale_raw"], sc["q_raw"], None, sc["f_dc"],
+                                 sc["f_rest"], None)
+        cfg = ops.RenderConfig(H=H, W=W, fx=intr["fx"], fy=intr["fy"], cx=intr["cx"], cy=intr["cy"])
+        fr = ops.Frame(g, keep, cfg, c2w_dev[0], dev)
+        fr.render("sync")
+    V, I, N, P = fr.n_visible, fr.n_isect, wl["n"], H * W
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+    # ---- e2e through the C ABI with HOST buffers (whole Gaussian set uploaded every call) -------------------------
+    host_fps = None
+    if rank == 0:
+        hp = {k: sc_cpu[k].contiguous().pin_memory() for k in sc_cpu}
+        gh = _lib.Gaussians(n=N, pos=hp["pos"].data_ptr(), opacity_raw=hp["opacity_raw"].data_ptr(),
+                            scale_raw=hp["scale_raw"].data_ptr(), q_raw=hp["q_raw"].data_ptr(), sigma=None,
+                            f_dc=hp["f_dc"].data_ptr(), f_rest=hp["f_rest"].data_ptr(), color=None)
+        camc = cfg.to_c(c2w_pin[0])
+        img_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+        st = _lib.FrameStats()
+        for i in range(2):
+            _lib.check(lib.b200gs_render_host(ctypes.byref(gh), ctypes.byref(camc), c2w_pin[i].data_ptr(),
+                                              img_host.data_ptr(), ctypes.byref(st)), "render_host")
+        t0 = time.perf_counter()
+        reps = max(3, min(K, 10))
+        for i in range(reps):
+            _lib.check(lib.b200gs_render_host(ctypes.byref(gh), ctypes.byref(camc), c2w_pin[i % len(c2w_pin)].data_ptr(),
+                                              img_host.data_ptr(), ctypes.byref(st)), "render_host")
+        host_fps = reps / (time.perf_counter() - t0)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sc_cpu["sigma"] = O.build_sigma_from_params(sc_cpu["scale_raw"], sc_cpu["q_raw"])
+        est, desc, _ = cpu_frame_sample(sc_cpu, cams[0], budget_s=12.0)
+        cpu_base = {"value": 1.0 / est, "unit": "frames/s", "cores": cores, "torch_threads": torch.get_num_threads(),
+                    "kind": "port", "sample": desc}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm, peak_src, sm_max = peaks()
+    bytes_model = algorithmic_bytes(N, V, I, P, tiles)
+    table = {}
+    for name, (ms, calls) in {**train_regions, **fwd_regions}.items():
+        b = bytes_model.get(name)
+        table[name] = {"ms": round(ms, 5), "calls": calls, "alg_bytes": b,
+                       "gbs": None if b is None else round(b / (ms * 1e-3) / 1e9, 1),
+                       "frac_hbm": None if b is None else round(b / (ms * 1e-3) / 1e9 / hbm, 4)}
+    step_kernels_ms = sum(v[0] for v in fwd_regions.values())
+    dom = max(fwd_regions, key=lambda k: fwd_regions[k][0])
+    dom_ms = fwd_regions[dom][0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    fps = world * K / (ms_render * 1e-3)
+    fp32_peak = 148 * 128 * sm_max * 1e6          # FP32 lane-instructions per second at the max SM clock
+    pairs = float(I) * 256.0                       # (pixel, splat) evaluations if no tile exits early
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_render / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I,
+                   "parallelism": f"frames/views sharded round-robin over {world} rank(s); Gaussians replicated",
+                   "capacity_mode": os.environ.get("B200GS_CAPACITY_MODE"),
+                   "l2_policy": "inputs larger than L2: every step streams 236 MB of parameters (L2 = 126 MB) and a different view"},
+        "train": {"value": K / (ms_train * 1e-3), "unit": "it/s", "views_per_s": world * K / (ms_train * 1e-3),
+                  "ms_per_step": ms_train / K,
+                  "step": "build_sigma + evaluate_sh + render + weighted-sum loss + backward" +
+                          (" + NCCL sum all-reduce of 6 gradient tensors (236 MB)" if world > 1 else ""),
+                  "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
+                          "d2h_bytes_per_step": 4}},
+        "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,
+                "api": "b200gs.evaluate_sh + b200gs.render (pose from pinned host memory, image to pinned host memory)"},
+        "e2e_host_buffers": {"value": host_fps, "unit": "frames/s", "h2d_bytes_per_step": 236 * N + 64,
+                             "d2h_bytes_per_step": H * W * 12,
+                             "api": "b200gs_render_host (C ABI, every parameter array uploaded from host memory each call)"},
+        "gpu_launches": int(launches_render),
+        "gpu_launches_train": int(launches_train),
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": bytes_model[dom] / (dom_ms * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": bytes_model[dom] / (dom_ms * 1e-3) / 1e9 / hbm, "traffic": traffic,
+                     "peak_source": peak_src, "alg_bytes_per_launch": bytes_model[dom], "ms_per_launch": dom_ms,
+                     "share_of_step_kernel_time": dom_ms / step_kernels_ms,
+                     "note": "blend is FP32-issue/MUFU bound, not HBM bound (SURVEY.md 8d): see roofline_fp32"},
+        "roofline_fp32": {"kernel": "blend_fwd", "pair_evals_upper": pairs,
+                          "gpairs_per_s": pairs / (fwd_regions.get("blend_fwd", (dom_ms, 0))[0] * 1e-3) / 1e9,
+                          "fp32_lane_instr_peak_per_s": fp32_peak,
+                          "lane_instr_per_pair_at_peak": fp32_peak / (pairs / (fwd_regions.get("blend_fwd", (dom_ms, 0))[0] * 1e-3))},
+        "kernels": table,
+        "clocks": clocks,
+        "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200gs", choices=["b200gs", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200gs" else args.warmup
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched directly: re-exec under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200gs(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -160,6 +160,15 @@ int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const vo
                               int32_t* list_tile, int32_t* list_id, uint32_t count, int32_t* ranges,
                               void* stream);
 
+/* Per-region CUDA-event profiling (bench.py's per-kernel table).  enable(1) starts recording an event
+ * pair around every kernel group launched through this library; collect() synchronises the device,
+ * sums the elapsed milliseconds and the number of calls per region, clears the records and returns the
+ * number of regions.  b200gs_kernel_launch_count() counts every kernel this library has launched. */
+int b200gs_profile_enable(int on);
+int b200gs_profile_collect(float* ms_out, int32_t* calls_out, int32_t max_regions);
+const char* b200gs_profile_region_name(int32_t id);
+unsigned long long b200gs_kernel_launch_count(void);
+
 /* Stand-alone primitives (exported for unit tests of the integer stages). */
 int b200gs_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out,
                               void* scratch, size_t scratch_bytes, void* stream);

@@ -310,12 +310,15 @@ def blend_tile(u, v, color, opacity, conic, px_u, px_v,
 
 
 def blend(proj: Projected, bins: Binned, T=TILE, chi_square_clip=6.25, alpha_max=0.99,
-          alpha_cutoff=1 / 128.) -> torch.Tensor:
+          alpha_cutoff=1 / 128., tile_stride: int = 1) -> torch.Tensor:
+    """`tile_stride` > 1 blends only every tile_stride-th non-empty tile (bounded CPU-baseline samples in
+    bench.py); 1 is the reference's behaviour."""
     H, W = proj.H, proj.W
     dt, dev = proj.u.dtype, proj.u.device
     image = torch.zeros((H * W, 3), device=dev, dtype=dt)
     parts, where = [], []
-    for tile, s0, s1 in zip(bins.uniq_tiles.tolist(), bins.start.tolist(), bins.end.tolist()):
+    work = list(zip(bins.uniq_tiles.tolist(), bins.start.tolist(), bins.end.tolist()))[::max(1, int(tile_stride))]
+    for tile, s0, s1 in work:
         sel = bins.ranks[s0:s1]
         tx, ty = tile % bins.tiles_x, tile // bins.tiles_x
         x0, y0 = tx * T, ty * T
