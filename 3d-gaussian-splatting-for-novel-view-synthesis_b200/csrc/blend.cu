@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
   float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t last = 0;
   bool done = !pc.inside;
+  // centre of this warp's 8x4 pixel block: a splat can only touch the block if its centre lies within
+  // (ext_u + 3.5, ext_v + 1.5) of it, where ext_* are the conservative half-extents of {q <= chi2}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
+  const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
   for (uint32_t base = range.x; base < range.y; base += kBlendThreads) {
     if (__syncthreads_count(done) == kBlendThreads) break;
     const uint32_t idx = base + threadIdx.x;
@@ -68,19 +73,32 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
     }
     __syncthreads();
     const int cnt = (int)min((uint32_t)kBlendThreads, range.y - base);
-    if (!done) {
-      for (int j = 0; j < cnt; ++j) {
-        if (!(T > 5e-5f)) { done = true; break; }
-        const float4 r0 = s0[j], r1 = s1[j];
-        float du, dv, gval, araw;
-        const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
-        if (a > 0.f) {
-          const float w = a * T;
-          C0 = fmaf(w, r1.z, C0);
-          C1 = fmaf(w, r1.w, C1);
-          C2 = fmaf(w, s2[j].x, C2);
-          T *= (1.f - a);
-          last = (base - range.x) + (uint32_t)j + 1u;
+    for (int chunk = 0; chunk < cnt; chunk += 32) {
+      if (__all_sync(0xffffffffu, done)) break;
+      // each lane tests one splat of the chunk against the warp's pixel block
+      const int jt = chunk + lane;
+      bool touch = false;
+      if (jt < cnt) {
+        const float4 t0 = s0[jt], t2 = s2[jt];
+        touch = (fabsf(t0.x - wcx) <= t2.y + 3.5f) && (fabsf(t0.y - wcy) <= t2.z + 1.5f);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, touch);
+      while (m) {
+        const int j = chunk + __ffs(m) - 1;
+        m &= m - 1;
+        if (!done) {
+          const float4 r0 = s0[j], r1 = s1[j];
+          float du, dv, gval, araw;
+          const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
+          if (a > 0.f) {
+            const float w = a * T;
+            C0 = fmaf(w, r1.z, C0);
+            C1 = fmaf(w, r1.w, C1);
+            C2 = fmaf(w, s2[j].x, C2);
+            T *= (1.f - a);
+            last = (base - range.x) + (uint32_t)j + 1u;
+            done = !(T > 5e-5f);   // render.py:387: the next splat contributes only if T is still > 5e-5
+          }
         }
       }
     }
@@ -134,6 +152,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
                                                                   float* __restrict__ grad_acc) {
   __shared__ float4 s0[kBlendThreads], s1[kBlendThreads];
   __shared__ float s_cb[kBlendThreads];
+  __shared__ float2 s_ext[kBlendThreads];
   __shared__ uint32_t s_id[kBlendThreads];
   __shared__ float s_grad[kBlendThreads][9];
   __shared__ uint32_t s_max;
@@ -141,7 +160,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
+  const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, T = 1.f;
   uint32_t last = 0;
   if (pc.inside) {
@@ -156,8 +177,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
   }
   if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
-  const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
-  if (lane == 0 && wmax) atomicMax(&s_max, wmax);
+  const uint32_t wlast = __reduce_max_sync(0xffffffffu, last);
+  if (lane == 0 && wlast) atomicMax(&s_max, wlast);
   __syncthreads();
   const uint32_t max_last = s_max;
   if (max_last == 0) return;
@@ -171,46 +192,62 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
       s_id[threadIdx.x] = id;
       s0[threadIdx.x] = rec0[id];
       s1[threadIdx.x] = rec1[id];
-      s_cb[threadIdx.x] = rec2[id].x;
+      const float4 t2 = rec2[id];
+      s_cb[threadIdx.x] = t2.x;
+      s_ext[threadIdx.x] = make_float2(t2.y, t2.z);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) s_grad[threadIdx.x][k] = 0.f;
     __syncthreads();
-    for (int j = cnt - 1; j >= 0; --j) {
-      const bool active = (boff + (uint32_t)j) < last;
-      float a = 0.f, du = 0.f, dv = 0.f, gval = 0.f, araw = 0.f;
-      const float4 r0 = s0[j], r1 = s1[j];
-      if (active) a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
-      const bool hit = a > 0.f;
-      if (!__any_sync(0xffffffffu, hit)) continue;
-      float v_u = 0.f, v_v = 0.f, v_a11 = 0.f, v_a12 = 0.f, v_a22 = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
-      if (hit) {
-        const float cb = s_cb[j];
-        const float Ti = T / (1.f - a);
-        T = Ti;
-        const float w = a * Ti;
-        v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
-        const float dalpha = Ti * (g0 * (r1.z - rc0) + g1 * (r1.w - rc1) + g2 * (cb - rc2));
-        rc0 = fmaf(a, r1.z - rc0, rc0);
-        rc1 = fmaf(a, r1.w - rc1, rc1);
-        rc2 = fmaf(a, cb - rc2, rc2);
-        const float draw = (araw <= rp.alpha_max) ? dalpha : 0.f;   // clamp_max passes on <=
-        v_op = draw * gval;
-        const float dq = -0.5f * araw * draw;                       // d/dq of op*exp(-q/2)
-        const float B2 = 2.f * r0.w;
-        v_u = -dq * (2.f * r0.z * du + B2 * dv);
-        v_v = -dq * (2.f * r1.x * dv + B2 * du);
-        v_a11 = dq * du * du;
-        v_a12 = dq * 2.f * du * dv;
-        v_a22 = dq * dv * dv;
+    for (int chunk = ((cnt - 1) >> 5) << 5; chunk >= 0; chunk -= 32) {
+      if (boff + (uint32_t)chunk >= wlast) continue;        // nobody in this warp consumed these splats
+      const int jt = chunk + lane;
+      bool touch = false;
+      if (jt < cnt) {
+        const float4 t0 = s0[jt];
+        const float2 te = s_ext[jt];
+        touch = (fabsf(t0.x - wcx) <= te.x + 3.5f) && (fabsf(t0.y - wcy) <= te.y + 1.5f);
       }
-      v_u = warp_sum(v_u); v_v = warp_sum(v_v); v_a11 = warp_sum(v_a11); v_a12 = warp_sum(v_a12);
-      v_a22 = warp_sum(v_a22); v_op = warp_sum(v_op); v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
-      if (lane == 0) {
-        float* sg = s_grad[j];
-        atomicAdd(sg + 0, v_u); atomicAdd(sg + 1, v_v); atomicAdd(sg + 2, v_a11); atomicAdd(sg + 3, v_a12);
-        atomicAdd(sg + 4, v_a22); atomicAdd(sg + 5, v_op); atomicAdd(sg + 6, v_r); atomicAdd(sg + 7, v_g);
-        atomicAdd(sg + 8, v_b);
+      unsigned m = __ballot_sync(0xffffffffu, touch);
+      while (m) {
+        const int bit = 31 - __clz(m);
+        m &= ~(1u << bit);
+        const int j = chunk + bit;
+        const bool active = (boff + (uint32_t)j) < last;
+        float a = 0.f, du = 0.f, dv = 0.f, gval = 0.f, araw = 0.f;
+        const float4 r0 = s0[j], r1 = s1[j];
+        if (active) a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
+        const bool hit = a > 0.f;
+        if (!__any_sync(0xffffffffu, hit)) continue;
+        float v_u = 0.f, v_v = 0.f, v_a11 = 0.f, v_a12 = 0.f, v_a22 = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+        if (hit) {
+          const float cb = s_cb[j];
+          const float Ti = T / (1.f - a);
+          T = Ti;
+          const float w = a * Ti;
+          v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
+          const float dalpha = Ti * (g0 * (r1.z - rc0) + g1 * (r1.w - rc1) + g2 * (cb - rc2));
+          rc0 = fmaf(a, r1.z - rc0, rc0);
+          rc1 = fmaf(a, r1.w - rc1, rc1);
+          rc2 = fmaf(a, cb - rc2, rc2);
+          const float draw = (araw <= rp.alpha_max) ? dalpha : 0.f;   // clamp_max passes on <=
+          v_op = draw * gval;
+          const float dq = -0.5f * araw * draw;                       // d/dq of op*exp(-q/2)
+          const float B2 = 2.f * r0.w;
+          v_u = -dq * (2.f * r0.z * du + B2 * dv);
+          v_v = -dq * (2.f * r1.x * dv + B2 * du);
+          v_a11 = dq * du * du;
+          v_a12 = dq * 2.f * du * dv;
+          v_a22 = dq * dv * dv;
+        }
+        v_u = warp_sum(v_u); v_v = warp_sum(v_v); v_a11 = warp_sum(v_a11); v_a12 = warp_sum(v_a12);
+        v_a22 = warp_sum(v_a22); v_op = warp_sum(v_op); v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
+        if (lane == 0) {
+          float* sg = s_grad[j];
+          atomicAdd(sg + 0, v_u); atomicAdd(sg + 1, v_v); atomicAdd(sg + 2, v_a11); atomicAdd(sg + 3, v_a12);
+          atomicAdd(sg + 4, v_a22); atomicAdd(sg + 5, v_op); atomicAdd(sg + 6, v_r); atomicAdd(sg + 7, v_g);
+          atomicAdd(sg + 8, v_b);
+        }
       }
     }
     __syncthreads();

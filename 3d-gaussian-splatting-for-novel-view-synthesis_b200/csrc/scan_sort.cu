@@ -82,25 +82,36 @@ __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint
     if (w < warp) warp_off += t;
     tile_sum += t;
   }
-  if (tid == 0) {
+  if (warp == 0) {
+    // decoupled look-back, 32 predecessors per step (lane l inspects tile j - l)
     uint32_t prefix = 0;
     if (tile == 0) {
-      st_status64(status + tile, (2ull << 32) | tile_sum);
+      if (lane == 0) st_status64(status + tile, (2ull << 32) | tile_sum);
     } else {
-      st_status64(status + tile, (1ull << 32) | tile_sum);
+      if (lane == 0) st_status64(status + tile, (1ull << 32) | tile_sum);
       int j = (int)tile - 1;
       while (true) {
-        const unsigned long long s = ld_status64(status + j);
+        const int idx = j - lane;
+        const unsigned long long s = (idx >= 0) ? ld_status64(status + idx) : (2ull << 32);  // virtual prefix 0
         const uint32_t flag = (uint32_t)(s >> 32);
-        if (flag == 0) { __nanosleep(32); continue; }
-        prefix += (uint32_t)s;
-        if (flag == 2) break;
-        --j;
+        const unsigned ready = __ballot_sync(0xffffffffu, flag != 0);
+        const unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
+        const int p = pref ? (__ffs(pref) - 1) : 32;                  // nearest inclusive prefix
+        const unsigned need = (p >= 31) ? 0xffffffffu : ((2u << p) - 1u);
+        if ((ready & need) != need) { __nanosleep(20); continue; }    // someone before it is not posted yet
+        uint32_t c = (lane <= p) ? (uint32_t)s : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        prefix += c;
+        if (p < 32) break;
+        j -= 32;
       }
-      st_status64(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
+      if (lane == 0) st_status64(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
     }
-    s_prefix = prefix;
-    if (total_out && tile == (n - 1) / kScanTile) *total_out = prefix + tile_sum;
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (total_out && tile == (n - 1) / kScanTile) *total_out = prefix + tile_sum;
+    }
   }
   __syncthreads();
   const uint32_t off = s_prefix + warp_off + (inc - sum);
@@ -258,27 +269,46 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
       st_status32(st, (2u << 30) | cnt);
     } else {
       st_status32(st, (1u << 30) | cnt);
+      // decoupled look-back with kLookBack predecessor loads in flight per step (a serial walk costs one
+      // L2 round trip per predecessor, which is what the whole first wave of blocks has to do)
+      constexpr int kLookBack = 16;
       int j = (int)vbid - 1;
-      while (true) {
-        const uint32_t sv = ld_status32(status + (size_t)j * kRadix + tid);
-        const uint32_t flag = sv >> 30;
-        if (flag == 0) { __nanosleep(32); continue; }
-        excl += sv & 0x3FFFFFFFu;
-        if (flag == 2) break;
-        --j;
+      bool found = false;
+      while (!found) {
+        uint32_t sv[kLookBack];
+#pragma unroll
+        for (int k = 0; k < kLookBack; ++k) {
+          const int idx = j - k;
+          sv[k] = (idx >= 0) ? ld_status32(status + (size_t)idx * kRadix + tid) : (2u << 30);  // virtual prefix 0
+        }
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < kLookBack; ++k) {
+          const uint32_t flag = sv[k] >> 30;
+          if (!found && used == k && flag != 0) {
+            excl += sv[k] & 0x3FFFFFFFu;
+            used = k + 1;
+            found = (flag == 2);
+          }
+        }
+        j -= used;
+        if (used == 0) __nanosleep(20);
       }
       st_status32(st, (2u << 30) | (excl + cnt));
     }
     // block-level exclusive scan of cnt over the 256 digits
-    s_scan[tid] = cnt;
-    __syncthreads();
-    for (int d = 1; d < kRadix; d <<= 1) {
-      const uint32_t add = (tid >= d) ? s_scan[tid - d] : 0u;
-      __syncthreads();
-      s_scan[tid] += add;
-      __syncthreads();
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
     }
-    const uint32_t dstart = s_scan[tid] - cnt;
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) woff += (w < warp) ? s_scan[w] : 0u;
+    const uint32_t dstart = woff + inc - cnt;
     s_digit_start[tid] = dstart;
     s_delta[tid] = gbase[tid] + excl - dstart;
   }
