@@ -1,0 +1,85 @@
+"""CPU: host-side multi-GPU logic with world_size=2 over gloo (views sharding, gradient all-reduce,
+tile-row band assembly).  The render itself is faked by the oracle here - the GPU path is covered by the
+`-m gpu` tests; this checks the partitioning and the collectives' bookkeeping."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from b200gs.dist import allreduce_gradients, render_tile_row_sharded, shard_tile_rows, shard_views
+
+
+def test_shard_views_round_robin():
+    assert shard_views(10, 0, 4) == [0, 4, 8] and shard_views(10, 3, 4) == [3, 7]
+    got = sorted(v for r in range(8) for v in shard_views(21, r, 8))
+    assert got == list(range(21))
+
+
+@pytest.mark.parametrize("rows,world", [(135, 8), (68, 8), (53, 4), (3, 8), (1, 1), (16, 5)])
+def test_shard_tile_rows_even(rows, world):
+    bands = shard_tile_rows(rows, world)
+    assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == rows
+    assert all(b[1] == n[0] for b, n in zip(bands, bands[1:]))
+    sizes = [e - b for b, e in bands]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_tile_rows_weighted():
+    w = [1] * 10 + [100] * 2 + [1] * 10
+    bands = shard_tile_rows(22, 2, w)
+    assert bands[0][0] == 0 and bands[-1][1] == 22 and bands[0][1] == bands[1][0]
+    load = [sum(w[b:e]) for b, e in bands]
+    assert abs(load[0] - load[1]) <= 100
+    assert shard_tile_rows(22, 2, [0] * 22) == shard_tile_rows(22, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # data-parallel gradients: each rank differentiates its own views, all-reduce sums them
+        p = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
+        q = torch.nn.Parameter(torch.ones(4))
+        views = shard_views(5, rank, world)
+        loss = sum(((v + 1) * p).sum() for v in views)
+        loss.backward()                     # q gets no gradient on purpose
+        allreduce_gradients([p, q])
+        out[f"p{rank}"] = p.grad.clone()
+        out[f"q{rank}"] = q.grad.clone()
+        # tile-row bands: a fake renderer paints its band with rank+1; the assembled frame has every row set
+        H, W, rows = 40, 8, 3
+
+        def fake_render(tile_rows):
+            img = torch.zeros(H, W, 3)
+            b, e = tile_rows
+            img[b * 16:min(e * 16, H)] = float(rank + 1)
+            return img
+        out[f"img{rank}"] = render_tile_row_sharded(fake_render, rows)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_and_bands():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        out = dict(out)
+    expect = torch.full((2, 3), float(sum(v + 1 for v in range(5))))
+    for r in range(world):
+        assert torch.equal(out[f"p{r}"], expect)
+        assert torch.equal(out[f"q{r}"], torch.zeros(4))
+        img = out[f"img{r}"]
+        assert torch.equal(img[:32], torch.full((32, 8, 3), 1.0))       # rows 0-1 -> rank 0 (2 of 3 tile rows)
+        assert torch.equal(img[32:], torch.full((8, 8, 3), 2.0))        # row 2 -> rank 1
