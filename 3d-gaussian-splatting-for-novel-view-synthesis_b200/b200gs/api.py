@@ -31,6 +31,75 @@ def _fusion_enabled() -> bool:
     return os.environ.get("B200GS_FUSE", "1") != "0"
 
 
+def _lazy_enabled() -> bool:
+    return os.environ.get("B200GS_LAZY", "1") != "0"
+
+
+_META_GETTERS = {"shape", "dtype", "device", "requires_grad", "ndim", "is_cuda", "layout", "is_leaf", "names",
+                 "is_sparse", "is_quantized", "is_meta", "grad_fn", "_version", "is_nested"}
+_META_METHODS = {"size", "dim", "numel", "ndimension", "nelement", "element_size", "is_floating_point",
+                 "is_complex", "is_contiguous", "get_device", "stride", "storage_offset", "__len__"}
+
+
+class _Deferred(torch.Tensor):
+    """Result of `build_sigma_from_params` / `evaluate_sh` whose kernel has not run yet.
+
+    It has the right shape/dtype/device and behaves like the tensor it stands for: the first torch
+    operation that touches it runs the stand-alone kernel (with autograd recorded) and proceeds on the
+    real tensor.  `render` recognises it and, when it can fuse, never materialises it - so the
+    reference's call sequence costs one fused preprocess kernel instead of three passes over the
+    parameters."""
+
+    @staticmethod
+    def __new__(cls, thunk, shape, dtype, device, requires_grad):
+        t = torch.Tensor._make_wrapper_subclass(cls, shape, dtype=dtype, device=device, requires_grad=False)
+        t._thunk, t._value, t._grad_mode, t._wants_grad = thunk, None, torch.is_grad_enabled(), requires_grad
+        return t
+
+    def materialize(self) -> torch.Tensor:
+        if self._value is None:
+            with torch.set_grad_enabled(self._grad_mode):
+                self._value = self._thunk()
+            src = getattr(self, _TAG, None)
+            if src is not None:
+                setattr(self._value, _TAG, src)
+            self._thunk = None
+        return self._value
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        owner = getattr(func, "__self__", None)
+        if name == "__get__" and getattr(owner, "__name__", "") in _META_GETTERS and \
+                getattr(owner, "__name__", "") not in ("requires_grad", "grad_fn", "is_leaf"):
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        if name in _META_METHODS:
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        unwrap = lambda x: x.materialize() if isinstance(x, _Deferred) else x
+        args = torch.utils._pytree.tree_map(unwrap, args)
+        kwargs = torch.utils._pytree.tree_map(unwrap, kwargs)
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        # reached only when something bypasses __torch_function__: same policy, materialise and go on
+        unwrap = lambda x: x.materialize().detach() if isinstance(x, _Deferred) else x
+        args = torch.utils._pytree.tree_map(unwrap, args)
+        kwargs = torch.utils._pytree.tree_map(unwrap, kwargs or {})
+        return func(*args, **kwargs)
+
+    def __repr__(self):
+        return f"_Deferred({'pending' if self._value is None else 'materialized'}, shape={tuple(self.shape)})"
+
+
+def _real(t):
+    return t.materialize() if isinstance(t, _Deferred) else t
+
+
 class _Source:
     """What a derived tensor was computed from (weak references + version counters)."""
 
@@ -51,7 +120,13 @@ class _Source:
 def build_sigma_from_params(scale_raw: torch.Tensor, q_raw: torch.Tensor) -> torch.Tensor:
     """Sigma = R S S^T R^T with s = max(exp(scale_raw), 1e-6), q normalised (gaussian.py:71-127)."""
     ops._require_cuda(scale_raw, "scale_raw")
-    sigma = ops._BuildSigma.apply(scale_raw, q_raw)
+    if _lazy_enabled() and _fusion_enabled():
+        n = scale_raw.shape[0]
+        needs = torch.is_grad_enabled() and (scale_raw.requires_grad or q_raw.requires_grad)
+        sigma = _Deferred(lambda: ops._BuildSigma.apply(scale_raw, q_raw), (n, 3, 3), scale_raw.dtype,
+                          scale_raw.device, needs)
+    else:
+        sigma = ops._BuildSigma.apply(scale_raw, q_raw)
     setattr(sigma, _TAG, _Source(scale_raw, q_raw))
     return sigma
 
@@ -61,8 +136,12 @@ def evaluate_sh(f_dc: torch.Tensor, f_rest: torch.Tensor, points: torch.Tensor, 
     ops._require_cuda(points, "points")
     if f_rest.dim() != 2 or f_rest.shape[1] != 45:
         raise RuntimeError(f"evaluate_sh expects f_rest of shape [N,45], got {tuple(f_rest.shape)}")
-    c2w_d = c2w.to(device=points.device)
-    color = ops._EvaluateSH.apply(f_dc, f_rest, points, c2w_d)
+    if _lazy_enabled() and _fusion_enabled():
+        needs = torch.is_grad_enabled() and (f_dc.requires_grad or f_rest.requires_grad or points.requires_grad)
+        color = _Deferred(lambda: ops._EvaluateSH.apply(f_dc, f_rest, points, c2w.to(device=points.device)),
+                          (points.shape[0], 3), points.dtype, points.device, needs)
+    else:
+        color = ops._EvaluateSH.apply(f_dc, f_rest, points, c2w.to(device=points.device))
     setattr(color, _TAG, _Source(f_dc, f_rest, points, c2w))
     return color
 
@@ -95,7 +174,7 @@ def render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
             f_dc, f_rest = got[0], got[1]
     strict = os.environ.get("B200GS_STRICT_OFFSCREEN", "1") != "0"
     image = ops._Rasterize.apply(pos, opacity_raw,
-                                 scale_raw, q_raw, None if scale_raw is not None else sigma,
-                                 f_dc, f_rest, None if f_dc is not None else color,
+                                 scale_raw, q_raw, None if scale_raw is not None else _real(sigma),
+                                 f_dc, f_rest, None if f_dc is not None else _real(color),
                                  c2w_d, cfg, strict)
     return image if image.dtype == pos.dtype else image.to(pos.dtype)

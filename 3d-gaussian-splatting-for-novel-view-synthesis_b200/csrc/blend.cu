@@ -163,6 +163,21 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
+  // which of the nine totals this lane ends up holding after the halving reduction (-1: none):
+  // index within the half-warp's five values = 3*h8 + (h8 ? h4 : 2*h4 + h2 ...) - see the steps below
+  int slot = -1;
+  {
+    const int h16 = (lane >> 4) & 1, h8 = (lane >> 3) & 1, h4 = (lane >> 2) & 1, h2 = (lane >> 1) & 1;
+    // step 8: h8=0 keeps x0,x1,x2 ; h8=1 keeps x3,x4,-.  step 4: h4=0 keeps y0,y1 ; h4=1 keeps y2,-.
+    // step 2: h2=0 keeps z0 ; h2=1 keeps z1.
+    int y = h4 ? 2 : h2;                 // index among (y0,y1,y2) ; (y2 only valid when h2 == 0)
+    bool ok = !(h4 && h2);
+    int x = h8 ? 3 + y : y;              // index among x0..x4 ; h8=1 has only x3,x4
+    if (h8 && y >= 2) ok = false;
+    int v = h16 ? 5 + x : x;             // 0..4 = u,v,A11,A12,A22 ; 5..8 = op,r,g,b ; 9 = padding
+    if (v >= 9) ok = false;
+    if (ok && (lane & 1) == 0) slot = v;
+  }
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, T = 1.f;
   uint32_t last = 0;
   if (pc.inside) {
@@ -240,14 +255,49 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
           v_a12 = dq * 2.f * du * dv;
           v_a22 = dq * dv * dv;
         }
-        v_u = warp_sum(v_u); v_v = warp_sum(v_v); v_a11 = warp_sum(v_a11); v_a12 = warp_sum(v_a12);
-        v_a22 = warp_sum(v_a22); v_op = warp_sum(v_op); v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
-        if (lane == 0) {
-          float* sg = s_grad[j];
-          atomicAdd(sg + 0, v_u); atomicAdd(sg + 1, v_v); atomicAdd(sg + 2, v_a11); atomicAdd(sg + 3, v_a12);
-          atomicAdd(sg + 4, v_a22); atomicAdd(sg + 5, v_op); atomicAdd(sg + 6, v_r); atomicAdd(sg + 7, v_g);
-          atomicAdd(sg + 8, v_b);
+        // Reduce the 9 per-pixel values over the warp by recursive halving: at every step a lane keeps
+        // one half of its values and trades the other half with its partner, so 12 shuffles (instead of
+        // 45) leave each total in one lane pair; those lanes then add into shared memory in parallel.
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+        float a0, a1, a2, a3, a4;
+        {
+          const float k0 = h16 ? v_op : v_u,   t0 = h16 ? v_u : v_op;
+          const float k1 = h16 ? v_r : v_v,    t1 = h16 ? v_v : v_r;
+          const float k2 = h16 ? v_g : v_a11,  t2 = h16 ? v_a11 : v_g;
+          const float k3 = h16 ? v_b : v_a12,  t3 = h16 ? v_a12 : v_b;
+          const float k4 = h16 ? 0.f : v_a22,  t4 = h16 ? v_a22 : 0.f;
+          a0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+          a1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
+          a2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
+          a3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
+          a4 = k4 + __shfl_xor_sync(0xffffffffu, t4, 16);
         }
+        // low half-warp: (u, v, A11, A12, A22)   high half-warp: (op, r, g, b, 0)
+        float b0, b1, b2;
+        {
+          const float k0 = h8 ? a3 : a0, t0 = h8 ? a0 : a3;
+          const float k1 = h8 ? a4 : a1, t1 = h8 ? a1 : a4;
+          const float k2 = h8 ? 0.f : a2, t2 = h8 ? a2 : 0.f;
+          b0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
+          b1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
+          b2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 8);
+        }
+        // h8 = 0: (x0, x1, x2)   h8 = 1: (x3, x4, 0)   of the half-warp's five values
+        float c0, c1;
+        {
+          const float k0 = h4 ? b2 : b0, t0 = h4 ? b0 : b2;
+          const float k1 = h4 ? 0.f : b1, t1 = h4 ? b1 : 0.f;
+          c0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
+          c1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
+        }
+        // h4 = 0: (y0, y1)   h4 = 1: (y2, 0)
+        float d0;
+        {
+          const float k0 = h2 ? c1 : c0, t0 = h2 ? c0 : c1;
+          d0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2);
+        }
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+        if (slot >= 0) atomicAdd(&s_grad[j][slot], d0);
       }
     }
     __syncthreads();

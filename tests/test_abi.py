@@ -82,3 +82,25 @@ def test_install_rebinds_reference_shaped_package(monkeypatch):
     finally:
         b200gs.uninstall()
     assert mods["render"].render() == "reference"
+
+
+def test_deferred_tensor_behaves_like_its_value():
+    """evaluate_sh / build_sigma_from_params return deferred tensors; anything but `render` that touches one
+    must see the real values, with autograd intact."""
+    from b200gs.api import _Deferred
+    a = torch.arange(6.).reshape(2, 3).requires_grad_(True)
+    calls = []
+
+    def thunk():
+        calls.append(1)
+        return a * 2
+    d = _Deferred(thunk, (2, 3), torch.float32, torch.device("cpu"), True)
+    assert d.shape == (2, 3) and d.dtype == torch.float32 and d.dim() == 2 and d.size(1) == 3 and len(d) == 2
+    assert not calls, "metadata access must not run the kernel"
+    (d + 1).sum().backward()
+    assert calls == [1] and torch.equal(a.grad, torch.full((2, 3), 2.0))
+    assert torch.equal(d, a * 2) and torch.equal(d[1], (a * 2)[1]) and d.detach().numpy().sum() == 30.0
+    assert calls == [1], "materialises once"
+    with torch.no_grad():
+        e = _Deferred(lambda: a * 3, (2, 3), torch.float32, torch.device("cpu"), False)
+    assert not (e * 1.0).requires_grad      # grad mode captured at creation
