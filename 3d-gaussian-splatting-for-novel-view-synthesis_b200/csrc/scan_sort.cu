@@ -7,6 +7,8 @@
 // Both kernels hand out "virtual" block ids through an atomic ticket so that block v only ever waits
 // on blocks < v that are already resident: the look-back cannot deadlock whatever the hardware's
 // block scheduling order is.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs {
@@ -205,132 +207,180 @@ __global__ void __launch_bounds__(kRadix) sort_scan_hist_kernel(uint32_t* __rest
   h[t] = s[t] - mine;
 }
 
-__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+// One onesweep pass.  288 threads: warps 0-7 (256 threads) rank and move 4096 keys, warp 8 runs the
+// decoupled look-back for all 256 digits (8 digits per lane, 4 predecessors per digit in flight) WHILE
+// the others do the expensive stable ranking and the shared-memory reorder, so the look-back latency -
+// which a synchronised wave of blocks pays in full, wave after wave - is off the critical path.
+constexpr int kSortBlock = kSortThreads + 32;
+constexpr int kLbBatch = 4;
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int shift, int bits,
     const uint32_t* __restrict__ gbase /*[256] exclusive*/, uint32_t* __restrict__ status, uint32_t* ticket) {
   __shared__ uint32_t s_warp_hist[kSortWarps][kRadix + 1];
   __shared__ uint32_t s_keys[kSortTile];
   __shared__ uint32_t s_vals[kSortTile];
+  __shared__ uint32_t s_hist[kRadix];          // digit counts of this block (early counts)
+  __shared__ uint32_t s_excl[kRadix];          // digit counts of all earlier blocks (look-back result)
   __shared__ uint32_t s_digit_start[kRadix];
-  __shared__ uint32_t s_delta[kRadix];
-  __shared__ uint32_t s_scan[kRadix];
+  __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_vbid;
 
   const uint32_t n = eff_count(n_host, n_dev);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_lb = warp == kSortWarps;
   if (tid == 0) s_vbid = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kSortWarps * (kRadix + 1); i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
+  for (int i = tid; i < kSortWarps * (kRadix + 1); i += kSortBlock) (&s_warp_hist[0][0])[i] = 0;
+  if (tid < kRadix) s_hist[tid] = 0;
   __syncthreads();
   const uint32_t vbid = s_vbid;
   const uint32_t base = vbid * (uint32_t)kSortTile;
   if (base >= n) return;   // uniform for the whole block
   const uint32_t mask = (1u << bits) - 1u;
   const uint32_t lane_lt = (1u << lane) - 1u;
+  const bool full = base + (uint32_t)kSortTile <= n;
 
-  // ---- load (warp-striped: item i of lane l sits at warp_base + 32 i + l) and rank ---------------------
+  // ---- load (warp-striped: item i of lane l sits at warp_base + 32 i + l) + early digit counts ------------
   const uint32_t warp_base = base + warp * (32 * kSortItems);
   uint32_t key[kSortItems];
-  uint32_t rank[kSortItems];
+  uint32_t val[kSortItems];
+  if (!is_lb) {
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const uint32_t idx = warp_base + i * 32 + lane;
-    key[i] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
-  }
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const uint32_t idx = warp_base + i * 32 + lane;
-    const uint32_t d = (idx < n) ? ((key[i] >> shift) & mask) : (uint32_t)kRadix;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) {
-      old = s_warp_hist[warp][d];
-      s_warp_hist[warp][d] = old + __popc(peers);
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t idx = warp_base + i * 32 + lane;
+      key[i] = (full || idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
     }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = old + __popc(peers & lane_lt);
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t idx = warp_base + i * 32 + lane;
+      val[i] = vals_in ? ((full || idx < n) ? vals_in[idx] : 0u) : idx;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t idx = warp_base + i * 32 + lane;
+      if (full || idx < n) atomicAdd(&s_hist[(key[i] >> shift) & mask], 1u);
+    }
   }
   __syncthreads();
 
-  // ---- per digit (thread d): exclusive offsets across warps, block count, look-back ----------------------
-  uint32_t cnt = 0;
-  {
+  if (is_lb) {
+    // ---- decoupled look-back: lane handles digits lane + 32 k ------------------------------------------------
+    uint32_t cnt[8], excl[8];
+    int j[8];
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t t = s_warp_hist[w][tid];
-      s_warp_hist[w][tid] = cnt;
-      cnt += t;
+    for (int k = 0; k < 8; ++k) {
+      cnt[k] = s_hist[lane + 32 * k];
+      excl[k] = 0;
+      j[k] = (int)vbid - 1;
+      st_status32(status + (size_t)vbid * kRadix + lane + 32 * k, ((vbid == 0 ? 2u : 1u) << 30) | cnt[k]);
     }
-    uint32_t* st = status + (size_t)vbid * kRadix + tid;
-    uint32_t excl = 0;
-    if (vbid == 0) {
-      st_status32(st, (2u << 30) | cnt);
-    } else {
-      st_status32(st, (1u << 30) | cnt);
-      // decoupled look-back with kLookBack predecessor loads in flight per step (a serial walk costs one
-      // L2 round trip per predecessor, which is what the whole first wave of blocks has to do)
-      constexpr int kLookBack = 16;
-      int j = (int)vbid - 1;
-      bool found = false;
-      while (!found) {
-        uint32_t sv[kLookBack];
+    unsigned open = (vbid == 0) ? 0u : 0xFFu;
+    while (open) {
+      uint32_t sv[8][kLbBatch];
 #pragma unroll
-        for (int k = 0; k < kLookBack; ++k) {
-          const int idx = j - k;
-          sv[k] = (idx >= 0) ? ld_status32(status + (size_t)idx * kRadix + tid) : (2u << 30);  // virtual prefix 0
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int b = 0; b < kLbBatch; ++b) {
+          const int idx = j[k] - b;
+          sv[k][b] = ((open >> k) & 1u) && idx >= 0 ? ld_status32(status + (size_t)idx * kRadix + lane + 32 * k)
+                                                    : (2u << 30);   // closed chain / before block 0: prefix 0
         }
-        int used = 0;
+      bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < kLookBack; ++k) {
-          const uint32_t flag = sv[k] >> 30;
-          if (!found && used == k && flag != 0) {
-            excl += sv[k] & 0x3FFFFFFFu;
-            used = k + 1;
-            found = (flag == 2);
+      for (int k = 0; k < 8; ++k) {
+        if ((open >> k) & 1u) {
+          int used = 0;
+          bool found = false;
+#pragma unroll
+          for (int b = 0; b < kLbBatch; ++b) {
+            const uint32_t flag = sv[k][b] >> 30;
+            if (!found && used == b && flag != 0) {
+              excl[k] += sv[k][b] & 0x3FFFFFFFu;
+              used = b + 1;
+              found = (flag == 2);
+            }
           }
+          j[k] -= used;
+          progressed |= used > 0;
+          if (found) open &= ~(1u << k);
         }
-        j -= used;
-        if (used == 0) __nanosleep(20);
       }
-      st_status32(st, (2u << 30) | (excl + cnt));
+      if (!progressed) __nanosleep(40);
     }
-    // block-level exclusive scan of cnt over the 256 digits
-    uint32_t inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+    for (int k = 0; k < 8; ++k) {
+      if (vbid != 0) st_status32(status + (size_t)vbid * kRadix + lane + 32 * k, (2u << 30) | (excl[k] + cnt[k]));
+      s_excl[lane + 32 * k] = excl[k];
     }
-    if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
+  } else {
+    // ---- stable ranking (see the comment on match.any + atomics below) -------------------------------------
+    // Per round (one key per lane): `match.any` gives the set of lanes holding the same digit ("peers");
+    // the lowest peer adds the group size to the warp's digit counter with a shared-memory atomic that
+    // returns the running count.  Rounds only depend on each other through those atomics (same-address
+    // atomics of one warp retire in program order), so the 16 rounds pipeline.
+    uint32_t rank[kSortItems];
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) woff += (w < warp) ? s_scan[w] : 0u;
-    const uint32_t dstart = woff + inc - cnt;
-    s_digit_start[tid] = dstart;
-    s_delta[tid] = gbase[tid] + excl - dstart;
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t idx = warp_base + i * 32 + lane;
+      const bool valid = full || idx < n;
+      // invalid tail keys get digit 256: they only match each other and never touch a counter
+      const uint32_t d = valid ? ((key[i] >> shift) & mask) : (uint32_t)kRadix;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t old = 0;
+      if (valid && (peers & lane_lt) == 0u) old = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
+      old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+      rank[i] = old + __popc(peers & lane_lt);
+    }
+    named_bar_sync(1, kSortThreads);
+    // ---- per digit (thread d): exclusive offsets across warps, start of the digit in the sorted block -------
+    {
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t t = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = cnt;
+        cnt += t;
+      }
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane == 31) s_scan[warp] = inc;
+      named_bar_sync(1, kSortThreads);
+      uint32_t woff = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) woff += (w < warp) ? s_scan[w] : 0u;
+      s_digit_start[tid] = woff + inc - cnt;
+    }
+    named_bar_sync(1, kSortThreads);
+    // ---- scatter into shared memory in sorted order -----------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t idx = warp_base + i * 32 + lane;
+      if (full || idx < n) {
+        const uint32_t d = (key[i] >> shift) & mask;
+        const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[i];
+        s_keys[pos] = key[i];
+        s_vals[pos] = val[i];
+      }
+    }
   }
-  __syncthreads();
+  __syncthreads();   // reorder done AND look-back done
 
-  // ---- scatter into shared memory in sorted order, then stream out in digit runs -------------------------
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const uint32_t idx = warp_base + i * 32 + lane;
-    if (idx < n) {
-      const uint32_t d = (key[i] >> shift) & mask;
-      const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[i];
-      s_keys[pos] = key[i];
-      s_vals[pos] = vals_in ? vals_in[idx] : idx;
-    }
-  }
+  // ---- stream out in digit runs: global position = gbase[d] + earlier blocks' count + offset within the digit ----
+  if (tid < kRadix) s_hist[tid] = gbase[tid] + s_excl[tid] - s_digit_start[tid];   // s_hist reused as delta
   __syncthreads();
   const uint32_t in_block = min((uint32_t)kSortTile, n - base);
-  for (uint32_t p = tid; p < in_block; p += kSortThreads) {
+  for (uint32_t p = tid; p < in_block; p += kSortBlock) {
     const uint32_t k = s_keys[p];
-    const uint32_t d = (k >> shift) & mask;
-    const uint32_t dst = s_delta[d] + p;
+    const uint32_t dst = s_hist[(k >> shift) & mask] + p;
     keys_out[dst] = k;
     vals_out[dst] = s_vals[p];
   }
@@ -371,8 +421,8 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
   uint32_t *ko = keys_b, *vo = vals_b;
   for (int p = 0; p < sp.num; ++p) {
     uint32_t* status = status0 + (size_t)p * (nblk + 1) * kRadix;
-    onesweep_pass_kernel<<<(int)nblk, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, n_dev, sp.shift[p], sp.bits[p],
-                                                           ghist + p * kRadix, status, tickets + p);
+    onesweep_pass_kernel<<<(int)nblk, kSortBlock, 0, s>>>(ki, vi, ko, vo, n, n_dev, sp.shift[p], sp.bits[p],
+                                                         ghist + p * kRadix, status, tickets + p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ki = ko; vi = vo;
