@@ -43,7 +43,7 @@ class Sizes(Structure):
 
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
-                ("n_in_frustum", c_uint32), ("reserved", c_uint32 * 12)]
+                ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("reserved", c_uint32 * 11)]
 
 
 # every symbol include/b200gs.h declares: name -> (restype, argtypes)

@@ -28,9 +28,9 @@ int fail_cuda(cudaError_t e, const char* where) {
   } while (0)
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
-enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_RANGES, R_BLEND_FWD, R_BLEND_BWD,
+enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
               R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_COUNT };
-const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_pairs", "tile_sort", "tile_ranges",
+const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
                                      "evaluate_sh_bwd", "build_sigma_bwd"};
 struct ProfRec { int region; cudaEvent_t a, b; };
@@ -108,11 +108,17 @@ int make_gauss(const b200gs_gaussians* g, gs::GaussIn& o) {
   return B200GS_OK;
 }
 
-// where the tile sort leaves its result: pass 0 writes the *_alt buffers, so odd pass counts end there
-struct SortedLists { const uint32_t* keys; const uint32_t* vals; };
-SortedLists sorted_lists(void* isect_ws, const gs::IsectLayout& IL, int n_tiles) {
-  const int passes = (tile_bits(n_tiles) + 7) / 8;
-  SortedLists s;
+int super_dims(const gs::RenderParams& rp, int& super_x, int& super_y) {
+  super_x = gs::ceil_div(rp.tiles_x, gs::kSuperX);
+  super_y = gs::ceil_div(rp.tiles_y, gs::kSuperY);
+  return super_x * super_y;
+}
+
+// where the supertile sort leaves its result: pass 0 writes the *_alt buffers, so odd pass counts end there
+struct SortedSuper { const uint32_t* keys; const uint32_t* vals; };
+SortedSuper sorted_super(void* isect_ws, const gs::IsectLayout& IL, int n_super_tiles) {
+  const int passes = (tile_bits(n_super_tiles) + 7) / 8;
+  SortedSuper s;
   if (passes % 2 == 0) { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals); }
   else { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt); }
   return s;
@@ -247,8 +253,8 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
                              (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
                              &in_a, s));
     if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
-    PCU(R_SCAN, 1, gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
-                                 gs::ws_ptr<uint32_t>(frame_ws, L.offsets), (uint32_t)gi.n, &stats->n_isect,
+    PCU(R_SCAN, 1, gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.super_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
+                                 gs::ws_ptr<uint32_t>(frame_ws, L.offsets), (uint32_t)gi.n, &stats->n_super,
                                  gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
   }
   if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
@@ -268,18 +274,29 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   if (!isect_ws || isect_bytes < IL.total) return fail(B200GS_ERR_WORKSPACE, "isect workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
-  const int n_tiles = rp.tiles_x * rp.tiles_y;
+  int super_x, super_y;
+  const int n_super_tiles = super_dims(rp, super_x, super_y);
   uint32_t* keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys);
   uint32_t* vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals);
-  PCU(R_EMIT, 1, gs::launch_emit_pairs(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
-                           gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), gs::ws_ptr<uint2>(frame_ws, L.rect),
-                           rp.tiles_x, isect_capacity, keys, vals, stats, s));
+  uint32_t* lists = gs::ws_ptr<uint32_t>(isect_ws, IL.lists);
+  PCU(R_EMIT, 1, gs::launch_emit_super(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
+                                       gs::ws_ptr<uint32_t>(frame_ws, L.super_touched), gs::ws_ptr<uint2>(frame_ws, L.rect),
+                                       super_x, isect_capacity, keys, vals, stats, s));
   int in_a = 0;
-  PCU(R_TILE_SORT, 2 + (tile_bits(n_tiles) + 7) / 8, gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
-                           gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_isect, 0,
-                           tile_bits(n_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s));
-  const SortedLists sl = sorted_lists(isect_ws, IL, n_tiles);
-  PCU(R_RANGES, 1, gs::launch_tile_ranges(sl.keys, isect_capacity, stats, gs::ws_ptr<uint2>(frame_ws, L.ranges), n_tiles, s));
+  PCU(R_TILE_SORT, 2 + (tile_bits(n_super_tiles) + 7) / 8,
+      gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
+                            gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_super, 0,
+                            tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s));
+  const SortedSuper ss = sorted_super(isect_ws, IL, n_super_tiles);
+  {
+    ProfScope _scope(R_SPLIT, s, 2);
+    CU(gs::launch_split_super(false, ss.keys, ss.vals, gs::ws_ptr<uint2>(frame_ws, L.rect), isect_capacity, stats, super_x,
+                              super_y, rp.tiles_x, rp.tiles_y, gs::ws_ptr<uint32_t>(frame_ws, L.tile_count),
+                              gs::ws_ptr<uint2>(frame_ws, L.ranges), lists, s));
+    CU(gs::launch_split_super(true, ss.keys, ss.vals, gs::ws_ptr<uint2>(frame_ws, L.rect), isect_capacity, stats, super_x,
+                              super_y, rp.tiles_x, rp.tiles_y, gs::ws_ptr<uint32_t>(frame_ws, L.tile_count),
+                              gs::ws_ptr<uint2>(frame_ws, L.ranges), lists, s));
+  }
   // pixels of tiles outside this rank's band are not touched; the whole image is zeroed first so that
   // "pixels in empty tiles stay 0" (render.py:318) also holds for bands
   if (rp.row_begin == 0 && rp.row_end == rp.tiles_y) {
@@ -287,7 +304,7 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   } else {
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }
-  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, sl.vals, image_out, s));
+  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s));
   if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
   return B200GS_OK;
 }
@@ -317,8 +334,7 @@ int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, 
       return fail(B200GS_ERR_ARG, "grads.q_raw must be 16-byte aligned");
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const SortedLists sl = sorted_lists(isect_ws, IL, rp.tiles_x * rp.tiles_y);
-  PCU(R_BLEND_BWD, 1, gs::launch_blend_bwd(rp, frame_ws, L, sl.vals, grad_image, gi.n, s));
+  PCU(R_BLEND_BWD, 1, gs::launch_blend_bwd(rp, frame_ws, L, gs::ws_ptr<uint32_t>(isect_ws, IL.lists), grad_image, gi.n, s));
   PCU(R_PREPROCESS_BWD, 1, gs::launch_preprocess_bwd(gi, gg, cam->c2w, rp, frame_ws, L, s));
   return B200GS_OK;
 }
@@ -404,10 +420,9 @@ int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const vo
   if (count > isect_capacity) return fail(B200GS_ERR_ARG, "count > capacity");
   cudaStream_t s = (cudaStream_t)stream;
   const int n_tiles = gs::ceil_div(W, gs::kTile) * gs::ceil_div(H, gs::kTile);
-  const SortedLists sl = sorted_lists(const_cast<void*>(isect_ws), IL, n_tiles);
   if (count) {
-    if (list_tile) copy_u32_kernel<<<(count + 255) / 256, 256, 0, s>>>(sl.keys, list_tile, count);
-    if (list_id) copy_u32_kernel<<<(count + 255) / 256, 256, 0, s>>>(sl.vals, list_id, count);
+    if (list_tile) CU(gs::launch_fill_list_tiles(gs::ws_ptr<uint2>(frame_ws, L.ranges), n_tiles, count, list_tile, s));
+    if (list_id) copy_u32_kernel<<<(count + 255) / 256, 256, 0, s>>>(gs::ws_ptr<uint32_t>(isect_ws, IL.lists), list_id, count);
   }
   if (ranges) copy_ranges_kernel<<<gs::ceil_div(n_tiles, 256), 256, 0, s>>>(gs::ws_ptr<uint2>(frame_ws, L.ranges), ranges, n_tiles);
   CU(cudaGetLastError());

@@ -10,6 +10,7 @@
 namespace gs {
 
 constexpr int kTile = 16;
+constexpr int kSuperX = 8, kSuperY = 4;   // a supertile is 8x4 tiles (128x64 px): 32 tiles = one 32-bit mask
 constexpr uint32_t kCulledKey = 0xFFFFFFFFu;
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -36,13 +37,15 @@ struct FrameLayout {
   size_t depth_key;       // u32[n]  float bits of z, 0xFFFFFFFF when culled
   size_t rect;            // uint2[n] packed u16 tile rect: x = tu0 | tu1<<16, y = tv0 | tv1<<16
   size_t tiles_touched;   // u32[n]
+  size_t super_touched;   // u32[n]  number of supertiles the tile rect overlaps
   size_t sort_key_alt;    // u32[n]  depth-sort ping-pong buffers (depth_key itself stays intact)
   size_t sort_key_alt2;   // u32[n]
   size_t order;           // u32[n]  Gaussian ids in depth order (sorted values)
   size_t order_alt;       // u32[n]
-  size_t offsets;         // u32[n]  exclusive scan of tiles_touched in depth order
+  size_t offsets;         // u32[n]  exclusive scan of super_touched in depth order
   size_t grad_acc;        // float[n*12] blend-backward accumulators (u,v,A11,A12,A22,op,r,g,b,+pad)
   size_t ranges;          // uint2[tiles] (start,end) per tile
+  size_t tile_count;      // u32[supertiles*4*32] entries per tile and list quarter, supertile-major
   size_t final_T;         // float[P]
   size_t n_contrib;       // u32[P]  (#list entries consumed) | channel-overflow bits 29..31
   size_t scratch;         // scan + sort scratch (sized for max(n, isect) users at call time)
@@ -51,8 +54,9 @@ struct FrameLayout {
 };
 
 struct IsectLayout {
-  size_t keys, keys_alt;  // u32[cap] tile ids
-  size_t vals, vals_alt;  // u32[cap] Gaussian ids
+  size_t keys, keys_alt;  // u32[cap] supertile ids of the (supertile, Gaussian) pairs
+  size_t vals, vals_alt;  // u32[cap] Gaussian ids of the pairs
+  size_t lists;           // u32[cap] per-tile depth-sorted Gaussian ids (grouped by supertile)
   size_t scratch;         // sort scratch for cap entries
   size_t scratch_bytes;
   size_t total;
@@ -78,6 +82,7 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.depth_key = take(N * 4);
   L.rect = take(N * 8);
   L.tiles_touched = take(N * 4);
+  L.super_touched = take(N * 4);
   L.sort_key_alt = take(N * 4);
   L.sort_key_alt2 = take(N * 4);
   L.order = take(N * 4);
@@ -85,6 +90,7 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.offsets = take(N * 4);
   L.grad_acc = take(N * 12 * 4);
   L.ranges = take(tiles * 8);
+  L.tile_count = take((size_t)ceil_div(ceil_div(W, kTile), kSuperX) * ceil_div(ceil_div(H, kTile), kSuperY) * 32 * 4 * 4 /* kSplitParts */);
   L.final_T = take(P * 4);
   L.n_contrib = take(P * 4);
   const size_t a = scan_scratch_bytes((uint32_t)N), b = sort_scratch_bytes((uint32_t)N);
@@ -101,6 +107,7 @@ inline IsectLayout isect_layout(uint32_t cap) {
   const size_t C = cap > 0 ? cap : 1;
   L.keys = take(C * 4); L.keys_alt = take(C * 4);
   L.vals = take(C * 4); L.vals_alt = take(C * 4);
+  L.lists = take(C * 4);
   L.scratch_bytes = sort_scratch_bytes((uint32_t)C);
   L.scratch = take(L.scratch_bytes);
   L.total = off;
@@ -144,11 +151,15 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
                               const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
                               size_t scratch_bytes, int* result_in_a, cudaStream_t s);
 
-cudaError_t launch_emit_pairs(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* tiles_touched,
-                              const uint2* rect, int tiles_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+cudaError_t launch_emit_super(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* super_touched,
+                              const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
                               b200gs_frame_stats* stats, cudaStream_t s);
-cudaError_t launch_tile_ranges(const uint32_t* keys, uint32_t capacity, const b200gs_frame_stats* stats,
-                               uint2* ranges, int n_tiles, cudaStream_t s);
+cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t* vals, const uint2* rect,
+                               uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y,
+                               int tiles_x, int tiles_y, uint32_t* tile_count, uint2* ranges, uint32_t* lists,
+                               cudaStream_t s);
+cudaError_t launch_fill_list_tiles(const uint2* ranges, int n_tiles, uint32_t count, int32_t* list_tile,
+                                   cudaStream_t s);
 
 cudaError_t launch_blend_fwd(const RenderParams& rp, const void* frame_ws, const FrameLayout& L, const uint32_t* vals,
                              float* image, cudaStream_t s);

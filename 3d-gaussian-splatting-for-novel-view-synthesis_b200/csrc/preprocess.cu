@@ -54,6 +54,7 @@ struct FrameView {
   uint32_t* depth_key;
   uint2* rect;
   uint32_t* tiles_touched;
+  uint32_t* super_touched;
   float* grad_acc;
   b200gs_frame_stats* stats;
 };
@@ -91,11 +92,13 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
   __shared__ __align__(16) float s_col[kPreBlock * 3];
   __shared__ __align__(16) float s_rest[RAW_SH ? kPreBlock * 45 : 4];
   __shared__ float s_c2w[16];
+  __shared__ uint32_t s_tiles;
 
   const int n0 = blockIdx.x * kPreBlock;
   const int count = min(kPreBlock, g.n - n0);
   const int tid = threadIdx.x;
   if (tid < 16) s_c2w[tid] = c2w[tid];
+  if (tid == 0) s_tiles = 0;
   stage_rows<3>(g.pos, s_pos, n0, count);
   if (RAW_COV) stage_rows<3>(g.scale_raw, s_cov, n0, count); else stage_rows<9>(g.sigma, s_cov, n0, count);
   if (RAW_SH) { stage_rows<3>(g.f_dc, s_col, n0, count); stage_rows<45>(g.f_rest, s_rest, n0, count); }
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
   __syncthreads();
   const int i = n0 + tid;
   bool vis = false, past_s7 = false;
+  uint32_t my_tiles = 0;
   if (tid < count) {
     const Pose ps = make_pose(s_c2w);
     const float p[3] = {s_pos[3 * tid], s_pos[3 * tid + 1], s_pos[3 * tid + 2]};
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
     if (!vis) {
       f.depth_key[i] = kCulledKey;
       f.tiles_touched[i] = 0;
+      f.super_touched[i] = 0;
     } else {
       float rgb[3];
       if (RAW_SH) {
@@ -147,6 +152,8 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
       f.depth_key[i] = __float_as_uint(o.z);
       f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
       f.tiles_touched[i] = (uint32_t)tiles;
+      my_tiles = (uint32_t)tiles;
+      f.super_touched[i] = tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -155,6 +162,11 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
     if (m) atomicAdd(&f.stats->n_visible, (uint32_t)__popc(m));
     if (m7) atomicAdd(&f.stats->n_in_frustum, (uint32_t)__popc(m7));
   }
+  // I = sum of tile counts: one global atomic per block
+  const uint32_t warp_tiles = __reduce_add_sync(0xffffffffu, my_tiles);
+  if ((threadIdx.x & 31) == 0 && warp_tiles) atomicAdd(&s_tiles, warp_tiles);
+  __syncthreads();
+  if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +291,7 @@ static FrameView make_view(void* ws, const FrameLayout& L) {
   f.depth_key = ws_ptr<uint32_t>(ws, L.depth_key);
   f.rect = ws_ptr<uint2>(ws, L.rect);
   f.tiles_touched = ws_ptr<uint32_t>(ws, L.tiles_touched);
+  f.super_touched = ws_ptr<uint32_t>(ws, L.super_touched);
   f.grad_acc = ws_ptr<float>(ws, L.grad_acc);
   f.stats = ws_ptr<b200gs_frame_stats>(ws, L.header);
   return f;

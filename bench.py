@@ -167,7 +167,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "torch_threads": torch.get_num_threads(),
                              "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -426,13 +426,31 @@ def run_b200gs(args):
         "clocks": clocks,
         "cpu_baseline": cpu_base,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the ONE JSON line on the real stdout (libraries such as NCCL print banners on fd 1, so fd 1 is
+    pointed at stderr for the duration of the run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -446,6 +464,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"),
                os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_REAL_STDOUT, 1)
         return subprocess.call(cmd)
     if args.impl == "reference":
         return run_reference(args)

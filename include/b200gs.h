@@ -97,7 +97,8 @@ typedef struct b200gs_frame_stats {
   uint32_t overflow;   /* 1 if I exceeded isect_capacity in rasterize */
   uint32_t n_in_frustum; /* survivors of S1-S7 (before the on-screen test; render.py:235 raises when
                             this is > 0 but n_visible == 0) */
-  uint32_t reserved[12];
+  uint32_t n_super;    /* (supertile, Gaussian) pairs: the number of keys the binning sort handles */
+  uint32_t reserved[11];
 } b200gs_frame_stats;
 
 int b200gs_abi_version(void);

@@ -141,8 +141,14 @@ def test_forward_against_golden(gs, name, fused):
     assert np.array_equal(rect[vis], ex["rect"][vis])
     assert np.array_equal(cnt[vis], ex["tiles_touched"][vis])
     assert frame.n_isect == int(cnt.sum()) == ex["list_id"].shape[0]
-    assert np.array_equal(ex["list_tile"], tile) and np.array_equal(ex["list_id"], ids)
-    assert np.array_equal(ex["ranges"], ranges)
+    # the lists are stored grouped by supertile: a STABLE regrouping by tile id must give exactly the
+    # (tile, depth, id)-ordered list, i.e. every tile's list is bit-exact and in depth order
+    regroup = np.argsort(ex["list_tile"], kind="stable")
+    assert np.array_equal(ex["list_tile"][regroup], tile) and np.array_equal(ex["list_id"][regroup], ids)
+    r = ex["ranges"].astype(np.int64)
+    assert np.array_equal(r[:, 1] - r[:, 0], ranges[:, 1] - ranges[:, 0])
+    for t in np.flatnonzero(r[:, 1] > r[:, 0])[:: max(1, r.shape[0] // 64)]:
+        assert (ex["list_tile"][r[t, 0]:r[t, 1]] == t).all()
     order = ex["depth_order"][: int(vis.sum())]
     assert np.array_equal(order, np.lexsort((np.arange(n), np.where(vis, ex["depth"], np.inf)))[: int(vis.sum())])
     # (b) against the reference: survivors, depth, radii, rects, counts, per-tile lists
@@ -284,7 +290,8 @@ def test_full_size_invariants(gs, n, W, H, ls):
     vis = ex["tiles_touched"] >= 0
     assert frame.n_visible == int(vis.sum())
     assert frame.n_isect == int(ex["tiles_touched"][vis].sum()) == ex["list_id"].shape[0]
-    lt, li = ex["list_tile"].astype(np.int64), ex["list_id"].astype(np.int64)
+    regroup = np.argsort(ex["list_tile"], kind="stable")                   # stored grouped by supertile
+    lt, li = ex["list_tile"][regroup].astype(np.int64), ex["list_id"][regroup].astype(np.int64)
     assert (np.diff(lt) >= 0).all()                                        # grouped by tile
     z = ex["depth"][li]
     same = lt[1:] == lt[:-1]
@@ -295,6 +302,8 @@ def test_full_size_invariants(gs, n, W, H, ls):
     nonempty = r[:, 1] > r[:, 0]
     assert int((r[:, 1] - r[:, 0]).sum()) == frame.n_isect
     assert np.array_equal(np.unique(lt), np.flatnonzero(nonempty))
+    starts = np.sort(r[nonempty, 0])
+    assert np.array_equal(np.sort(r[nonempty, 1])[:-1], starts[1:]) and starts[0] == 0   # ranges tile the buffer
     # every (tile, id) pair lies inside the Gaussian's tile rect, and each pair appears once
     tx, ty = lt % ((W + 15) // 16), lt // ((W + 15) // 16)
     rc = ex["rect"][li]
