@@ -1,0 +1,101 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): NCCL data-parallel gradients equal the
+single-GPU sum over the same views, and a tile-row sharded frame equals the full frame bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+PARAMS = ("pos", "scale_raw", "q_raw", "opacity_raw", "f_dc", "f_rest")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _views(n_views, W, H):
+    from oracle import gs_oracle as O
+    return [O.make_camera(W, H, view=v, n_views=n_views) for v in range(n_views)]
+
+
+def _loss_for_views(gs, leaves, cams, views, W, H, dev, n_total):
+    sigma = gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+    total = None
+    for v in views:
+        cam = cams[v]
+        c2w = cam["c2w"].to(dev)
+        col = gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        img = gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        w = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(100 + v)).to(dev)
+        term = (img * w).sum() / n_total          # each view's loss is divided by the GLOBAL batch (train.py:514-521)
+        total = term if total is None else total + term
+    return total
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    import b200gs
+    from b200gs.dist import allreduce_gradients, render_tile_row_sharded, shard_views
+    from oracle import gs_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        W, H, n_views = 320, 200, 4
+        sc = O.make_scene(20000, seed=5, log_scale=-3.6)
+        cams = _views(n_views, W, H)
+        leaves = {k: sc[k].to(dev).requires_grad_(True) for k in PARAMS}
+        loss = _loss_for_views(b200gs, leaves, cams, shard_views(n_views, rank, world), W, H, dev, n_views)
+        loss.backward()
+        allreduce_gradients(leaves.values())
+        out[f"grads{rank}"] = {k: leaves[k].grad.cpu() for k in PARAMS}
+        # tile-row sharded single frame
+        with torch.no_grad():
+            c2w = cams[1]["c2w"].to(dev)
+            sigma = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+            col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+            fn = lambda tile_rows: b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[1]["fx"],
+                                                 cams[1]["fy"], cams[1]["cx"], cams[1]["cy"], tile_rows=tile_rows)
+            out[f"img{rank}"] = render_tile_row_sharded(fn, (H + 15) // 16).cpu()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dp_gradients_and_tile_row_bands_match_single_gpu():
+    import torch.multiprocessing as mp
+    import b200gs
+    from oracle import gs_oracle as O
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        out = dict(out)
+    # single-GPU reference: all views on one device
+    dev = torch.device("cuda", 0)
+    W, H, n_views = 320, 200, 4
+    sc = O.make_scene(20000, seed=5, log_scale=-3.6)
+    cams = _views(n_views, W, H)
+    leaves = {k: sc[k].to(dev).requires_grad_(True) for k in PARAMS}
+    _loss_for_views(b200gs, leaves, cams, list(range(n_views)), W, H, dev, n_views).backward()
+    for k in PARAMS:
+        ref = leaves[k].grad.cpu()
+        for r in range(world):
+            got = out[f"grads{r}"][k]
+            err = float((got - ref).abs().max() / ref.abs().max())
+            assert err <= 1e-5, (k, r, err)          # float atomics reorder sums: not bit-exact
+        assert torch.equal(out["grads0"][k], out["grads1"][k])    # the all-reduce leaves identical replicas
+    with torch.no_grad():
+        c2w = cams[1]["c2w"].to(dev)
+        sigma = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        full = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[1]["fx"], cams[1]["fy"],
+                             cams[1]["cx"], cams[1]["cy"]).cpu()
+    assert torch.equal(out["img0"], full) and torch.equal(out["img1"], full)
