@@ -10,6 +10,8 @@
 //
 // Compiled with -fmad=false: the projection feeds floor()/ceil() decisions that must not depend on
 // the compiler's contraction choices; FMAs are written explicitly (fmaf) where wanted.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs {
@@ -170,6 +172,151 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Blackwell path of the fully-raw forward (the headline route): a persistent kernel, one CTA loop over
+// 128-Gaussian chunks, whose six input rows-blocks are fetched with 1-D bulk async copies
+// (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP) into a double buffer, so the
+// copy of chunk k+1 overlaps the math of chunk k and no thread spends issue slots on address arithmetic.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct __align__(128) PreStage {
+  float rest[kPreBlock * 45];   // 23040 B
+  float quat[kPreBlock * 4];    //  2048 B
+  float pos[kPreBlock * 3];     //  1536 B
+  float scale[kPreBlock * 3];
+  float dc[kPreBlock * 3];
+  float opac[kPreBlock];        //   512 B
+};
+constexpr uint32_t kPreStageBytes = kPreBlock * (45 + 4 + 3 + 3 + 3 + 1) * 4;
+
+__global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
+                                                                       RenderParams rp, FrameView f, int n_chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PreStage* stage = reinterpret_cast<PreStage*>(smem_raw);       // [2]
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ float s_c2w[16];
+  __shared__ uint32_t s_tiles;
+  const int tid = threadIdx.x;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  if (tid == 0) {
+    s_tiles = 0;
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const Pose ps = make_pose(s_c2w);
+
+  // full chunks go through the bulk-copy engine; a ragged last chunk is staged by the threads
+  auto issue = [&](int chunk, int buf) {
+    const size_t n0 = (size_t)chunk * kPreBlock;
+    PreStage& st = stage[buf];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+    mbar_expect_tx(&s_bar[buf], kPreStageBytes);
+    bulk_g2s(st.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
+    bulk_g2s(st.quat, g.q_raw + n0 * 4, kPreBlock * 4 * 4, &s_bar[buf]);
+    bulk_g2s(st.pos, g.pos + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.scale, g.scale_raw + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.opac, g.opacity_raw + n0, kPreBlock * 4, &s_bar[buf]);
+  };
+  auto is_full = [&](int chunk) { return (chunk + 1) * kPreBlock <= g.n; };
+
+  int chunk = blockIdx.x;
+  if (chunk < n_chunks && is_full(chunk) && tid == 0) issue(chunk, 0);
+  uint32_t vis_count = 0, s7_count = 0, tiles_sum = 0;   // per-thread tallies, reduced once at the end
+  for (int it = 0; chunk < n_chunks; ++it, chunk += gridDim.x) {
+    const int buf = it & 1;
+    const int next = chunk + gridDim.x;
+    if (next < n_chunks && is_full(next) && tid == 0) issue(next, buf ^ 1);
+    PreStage& st = stage[buf];
+    const int n0 = chunk * kPreBlock;
+    const int count = min(kPreBlock, g.n - n0);
+    if (is_full(chunk)) {
+      mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
+    } else {
+      stage_rows<45>(g.f_rest, st.rest, n0, count);
+      stage_rows<4>(g.q_raw, st.quat, n0, count);
+      stage_rows<3>(g.pos, st.pos, n0, count);
+      stage_rows<3>(g.scale_raw, st.scale, n0, count);
+      stage_rows<3>(g.f_dc, st.dc, n0, count);
+      stage_rows<1>(g.opacity_raw, st.opac, n0, count);
+      __syncthreads();
+    }
+    if (tid < count) {
+      const int i = n0 + tid;
+      const float p[3] = {st.pos[3 * tid], st.pos[3 * tid + 1], st.pos[3 * tid + 2]};
+      const float sr[3] = {st.scale[3 * tid], st.scale[3 * tid + 1], st.scale[3 * tid + 2]};
+      const float4 q4 = reinterpret_cast<const float4*>(st.quat)[tid];
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+      QuatScale qs;
+      quat_scale_forward(sr, q, qs);
+      float full[9];
+      sigma_full(qs, full);
+      const Cov3 S = sym_from_full(full);
+      Projection o;
+      const bool vis = project_gaussian(p, S, st.opac[tid], ps, rp, o);
+      s7_count += (vis || o.offscreen) ? 1u : 0u;
+      if (!vis) {
+        f.depth_key[i] = kCulledKey;
+        f.tiles_touched[i] = 0;
+        f.super_touched[i] = 0;
+      } else {
+        ++vis_count;
+        const ViewDir vd = view_dir(p, ps.cam);
+        float Y[16], acc[3], rgb[3];
+        sh_basis(vd.d, Y);
+        sh_color(&st.dc[3 * tid], &st.rest[45 * tid], Y, rgb, acc);
+        int tv0 = max(o.tv0, rp.row_begin), tv1 = min(o.tv1, rp.row_end - 1);
+        const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
+        if (tiles == 0) { tv0 = 0; tv1 = 0; }
+        float eu, ev;
+        conic_extent(o.A11, o.A12, o.A22, rp.chi2, eu, ev);
+        f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
+        f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
+        f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
+        f.depth_key[i] = __float_as_uint(o.z);
+        f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
+        f.tiles_touched[i] = (uint32_t)tiles;
+        tiles_sum += (uint32_t)tiles;
+        f.super_touched[i] =
+            tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
+      }
+    }
+    __syncthreads();   // everyone is done with stage[buf] before it is refilled (two iterations from now)
+  }
+  // frame counters: one atomic per warp / block for the whole persistent loop
+  const uint32_t wv = __reduce_add_sync(0xffffffffu, vis_count), w7 = __reduce_add_sync(0xffffffffu, s7_count);
+  const uint32_t wt = __reduce_add_sync(0xffffffffu, tiles_sum);
+  if ((tid & 31) == 0) {
+    if (wv) atomicAdd(&f.stats->n_visible, wv);
+    if (w7) atomicAdd(&f.stats->n_in_frustum, w7);
+    if (wt) atomicAdd(&s_tiles, wt);
+  }
+  __syncthreads();
+  if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward: recompute the forward from the inputs, chain the 9 per-Gaussian gradients that the blend
 // backward accumulated (grad_acc[n][12]) down to the leaves.  Dense outputs (zeros when culled).
 // ------------------------------------------------------------------------------------------------
@@ -285,6 +432,165 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_bwd_kernel(GaussIn g, Ga
   else unstage_rows<3>(gg.color, s_col, n0, count);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blackwell path of the fully-raw backward: same persistent double-buffered bulk-copy pipeline as the
+// forward, inputs + grad_acc in, and the six gradient row-blocks written back from shared memory with bulk
+// async stores (cp.async.bulk shared -> global), so both directions run on the copy engine.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+
+struct __align__(128) PreStageBwd {
+  PreStage in;                       // inputs, overwritten in place by the gradients of the same shape
+  float acc[kPreBlock * 12];         // grad_acc rows (6144 B)
+};
+constexpr uint32_t kPreStageBwdBytes = kPreStageBytes + kPreBlock * 12 * 4;
+
+__global__ void __launch_bounds__(kPreBlock) preprocess_bwd_tma_kernel(GaussIn g, GaussGrad gg,
+                                                                       const float* __restrict__ c2w,
+                                                                       RenderParams rp, FrameView f, int n_chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PreStageBwd* stage = reinterpret_cast<PreStageBwd*>(smem_raw);       // [2]
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ float s_c2w[16];
+  const int tid = threadIdx.x;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const Pose ps = make_pose(s_c2w);
+
+  auto issue = [&](int chunk, int buf) {
+    const size_t n0 = (size_t)chunk * kPreBlock;
+    PreStageBwd& st = stage[buf];
+    // the bulk stores that drained this buffer two iterations ago must have finished READING it
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&s_bar[buf], kPreStageBwdBytes);
+    bulk_g2s(st.in.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
+    bulk_g2s(st.in.quat, g.q_raw + n0 * 4, kPreBlock * 4 * 4, &s_bar[buf]);
+    bulk_g2s(st.in.pos, g.pos + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.in.scale, g.scale_raw + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.in.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.in.opac, g.opacity_raw + n0, kPreBlock * 4, &s_bar[buf]);
+    bulk_g2s(st.acc, f.grad_acc + n0 * 12, kPreBlock * 12 * 4, &s_bar[buf]);
+  };
+  auto is_full = [&](int chunk) { return (chunk + 1) * kPreBlock <= g.n; };
+
+  int chunk = blockIdx.x;
+  if (chunk < n_chunks && is_full(chunk) && tid == 0) issue(chunk, 0);
+  for (int it = 0; chunk < n_chunks; ++it, chunk += gridDim.x) {
+    const int buf = it & 1;
+    const int next = chunk + gridDim.x;
+    if (next < n_chunks && is_full(next) && tid == 0) issue(next, buf ^ 1);
+    PreStageBwd& st = stage[buf];
+    const int n0 = chunk * kPreBlock;
+    const int count = min(kPreBlock, g.n - n0);
+    const bool full = is_full(chunk);
+    if (full) {
+      mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
+    } else {
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+      stage_rows<45>(g.f_rest, st.in.rest, n0, count);
+      stage_rows<4>(g.q_raw, st.in.quat, n0, count);
+      stage_rows<3>(g.pos, st.in.pos, n0, count);
+      stage_rows<3>(g.scale_raw, st.in.scale, n0, count);
+      stage_rows<3>(g.f_dc, st.in.dc, n0, count);
+      stage_rows<1>(g.opacity_raw, st.in.opac, n0, count);
+      stage_rows<12>(f.grad_acc, st.acc, n0, count);
+      __syncthreads();
+    }
+    float gp[3] = {0.f, 0.f, 0.f}, g_op = 0.f, g_sr[3] = {0.f, 0.f, 0.f}, g_q[4] = {0.f, 0.f, 0.f, 0.f};
+    float g_dc[3] = {0.f, 0.f, 0.f}, g_acc[3] = {0.f, 0.f, 0.f};
+    float Y[16];
+    bool vis = false;
+    if (tid < count) {
+      const float p[3] = {st.in.pos[3 * tid], st.in.pos[3 * tid + 1], st.in.pos[3 * tid + 2]};
+      const float sr[3] = {st.in.scale[3 * tid], st.in.scale[3 * tid + 1], st.in.scale[3 * tid + 2]};
+      const float4 q4 = reinterpret_cast<const float4*>(st.in.quat)[tid];
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+      QuatScale qs;
+      quat_scale_forward(sr, q, qs);
+      float fullm[9];
+      sigma_full(qs, fullm);
+      const Cov3 S = sym_from_full(fullm);
+      Projection o;
+      vis = project_gaussian(p, S, st.in.opac[tid], ps, rp, o);
+      if (vis) {
+        const float4 a0 = reinterpret_cast<const float4*>(st.acc)[3 * tid];
+        const float4 a1 = reinterpret_cast<const float4*>(st.acc)[3 * tid + 1];
+        const float4 a2 = reinterpret_cast<const float4*>(st.acc)[3 * tid + 2];
+        SplatGrad sg;
+        sg.u = a0.x; sg.v = a0.y; sg.A11 = a0.z; sg.A12 = a0.w; sg.A22 = a1.x; sg.op = a1.y;
+        const float g_rgb[3] = {a1.z, a1.w, a2.x};
+        float G[9];
+        project_backward(p, S, ps, rp, o, sg, gp, G, g_op);
+        quat_scale_backward(qs, q, G, g_sr, g_q);
+        const ViewDir vd = view_dir(p, ps.cam);
+        sh_basis(vd.d, Y);
+        float rgb[3], acc[3], gY[16];
+        sh_color(&st.in.dc[3 * tid], &st.in.rest[45 * tid], Y, rgb, acc);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gY[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          g_acc[c] = g_rgb[c] * rgb[c] * (1.f - rgb[c]);
+          g_dc[c] = g_acc[c] * Y[0];
+#pragma unroll
+          for (int k = 1; k < 16; ++k) gY[k] = fmaf(g_acc[c], st.in.rest[45 * tid + 15 * c + k - 1], gY[k]);
+        }
+        float gd[3], gpv[3];
+        sh_basis_backward(vd.d, gY, gd);
+        view_dir_backward(vd, gd, gpv);
+        gp[0] += gpv[0]; gp[1] += gpv[1]; gp[2] += gpv[2];
+      }
+    }
+    __syncthreads();   // all inputs consumed: the stage now becomes the output staging area
+    if (tid < count) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        st.in.pos[3 * tid + c] = gp[c];
+        st.in.scale[3 * tid + c] = g_sr[c];
+        st.in.dc[3 * tid + c] = g_dc[c];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) st.in.rest[45 * tid + 15 * c + k - 1] = vis ? g_acc[c] * Y[k] : 0.f;
+      }
+      reinterpret_cast<float4*>(st.in.quat)[tid] = make_float4(g_q[0], g_q[1], g_q[2], g_q[3]);
+      st.in.opac[tid] = g_op;
+    }
+    if (full) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the generic writes visible to the copy engine
+      __syncthreads();
+      if (tid == 0) {
+        const size_t b = (size_t)n0;
+        bulk_s2g(gg.f_rest + b * 45, st.in.rest, kPreBlock * 45 * 4);
+        bulk_s2g(gg.q_raw + b * 4, st.in.quat, kPreBlock * 4 * 4);
+        bulk_s2g(gg.pos + b * 3, st.in.pos, kPreBlock * 3 * 4);
+        bulk_s2g(gg.scale_raw + b * 3, st.in.scale, kPreBlock * 3 * 4);
+        bulk_s2g(gg.f_dc + b * 3, st.in.dc, kPreBlock * 3 * 4);
+        bulk_s2g(gg.opacity_raw + b, st.in.opac, kPreBlock * 4);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      __syncthreads();
+      unstage_rows<45>(gg.f_rest, st.in.rest, n0, count);
+      unstage_rows<4>(gg.q_raw, st.in.quat, n0, count);
+      unstage_rows<3>(gg.pos, st.in.pos, n0, count);
+      unstage_rows<3>(gg.scale_raw, st.in.scale, n0, count);
+      unstage_rows<3>(gg.f_dc, st.in.dc, n0, count);
+      unstage_rows<1>(gg.opacity_raw, st.in.opac, n0, count);
+      __syncthreads();
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+}
+
 static FrameView make_view(void* ws, const FrameLayout& L) {
   FrameView f;
   f.rec0 = ws_ptr<float4>(ws, L.rec0); f.rec1 = ws_ptr<float4>(ws, L.rec1); f.rec2 = ws_ptr<float4>(ws, L.rec2);
@@ -303,6 +609,21 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
   const FrameView f = make_view(ws, L);
   const int grid = ceil_div(g.n, kPreBlock);
   const bool rc = g.scale_raw != nullptr, rs = g.f_dc != nullptr;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  static const bool no_tma = getenv("B200GS_NO_TMA") != nullptr;
+  if (rc && rs && !no_tma && aligned16(g.pos) && aligned16(g.scale_raw) && aligned16(g.q_raw) && aligned16(g.f_dc) &&
+      aligned16(g.f_rest) && aligned16(g.opacity_raw)) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
+    }
+    const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
+    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid);
+    return cudaGetLastError();
+  }
   if (rc && rs) preprocess_fwd_kernel<true, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
   else if (rc && !rs) preprocess_fwd_kernel<true, false><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
   else if (!rc && rs) preprocess_fwd_kernel<false, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
@@ -316,6 +637,22 @@ cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const f
   const FrameView f = make_view(ws, L);
   const int grid = ceil_div(g.n, kPreBlock);
   const bool rc = g.scale_raw != nullptr, rs = g.f_dc != nullptr;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  static const bool no_tma = getenv("B200GS_NO_TMA") != nullptr;
+  if (rc && rs && !no_tma && aligned16(g.pos) && aligned16(g.scale_raw) && aligned16(g.q_raw) && aligned16(g.f_dc) &&
+      aligned16(g.f_rest) && aligned16(g.opacity_raw) && aligned16(gg.pos) && aligned16(gg.scale_raw) &&
+      aligned16(gg.q_raw) && aligned16(gg.f_dc) && aligned16(gg.f_rest) && aligned16(gg.opacity_raw)) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(preprocess_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStageBwd));
+    }
+    const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;
+    preprocess_bwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStageBwd), s>>>(g, gg, c2w, rp, f, grid);
+    return cudaGetLastError();
+  }
   if (rc && rs) preprocess_bwd_kernel<true, true><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
   else if (rc && !rs) preprocess_bwd_kernel<true, false><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
   else if (!rc && rs) preprocess_bwd_kernel<false, true><<<grid, kPreBlock, 0, s>>>(g, gg, c2w, rp, f);
