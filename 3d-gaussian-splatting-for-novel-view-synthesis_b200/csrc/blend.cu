@@ -41,6 +41,14 @@ __device__ __forceinline__ float splat_alpha(const float4& r0, const float4& r1,
   return (a >= rp.alpha_cutoff) ? a : 0.f;
 }
 
+// Can this splat contribute to any pixel of the warp's 8x4 block (centre wcx, wcy)?  Bounding box of the
+// effective ellipse { q <= min(chi2, 2 ln(opacity / alpha_cutoff)) } (extents precomputed per splat,
+// conservative) against the block.  (An exact ellipse-vs-rectangle test was measured: it costs more than
+// the few extra visits it removes.)  One lane evaluates one splat.
+__device__ __forceinline__ bool splat_touches_block(const float4& r0, float eu, float ev, float wcx, float wcy) {
+  return (fabsf(r0.x - wcx) <= eu + 3.5f) && (fabsf(r0.y - wcy) <= ev + 1.5f);
+}
+
 __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams rp, const uint2* __restrict__ ranges,
                                                                   const uint32_t* __restrict__ vals,
                                                                   const float4* __restrict__ rec0,
@@ -79,8 +87,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
       const int jt = chunk + lane;
       bool touch = false;
       if (jt < cnt) {
-        const float4 t0 = s0[jt], t2 = s2[jt];
-        touch = (fabsf(t0.x - wcx) <= t2.y + 3.5f) && (fabsf(t0.y - wcy) <= t2.z + 1.5f);
+        const float4 t2 = s2[jt];
+        touch = splat_touches_block(s0[jt], t2.y, t2.z, wcx, wcy);
       }
       unsigned m = __ballot_sync(0xffffffffu, touch);
       while (m) {
@@ -219,9 +227,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
       const int jt = chunk + lane;
       bool touch = false;
       if (jt < cnt) {
-        const float4 t0 = s0[jt];
         const float2 te = s_ext[jt];
-        touch = (fabsf(t0.x - wcx) <= te.x + 3.5f) && (fabsf(t0.y - wcy) <= te.y + 1.5f);
+        touch = splat_touches_block(s0[jt], te.x, te.y, wcx, wcy);
       }
       unsigned m = __ballot_sync(0xffffffffu, touch);
       while (m) {

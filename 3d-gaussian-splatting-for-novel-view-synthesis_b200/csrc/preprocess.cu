@@ -73,9 +73,14 @@ __device__ __forceinline__ void sh_color(const float* coef_dc, const float* coef
   }
 }
 
-// tight half-extents of { q <= chi2 } for the per-warp culling in the blend kernels (conservative)
-__device__ __forceinline__ void conic_extent(float A11, float A12, float A22, float chi2, float& eu, float& ev) {
+// Conservative half-extents of the region where the splat can contribute, for the per-warp culling in the
+// blend kernels: { q <= chi2 } intersected with { opacity * exp(-q/2) >= alpha_cutoff }, i.e.
+// q <= min(chi2, 2 ln(opacity / alpha_cutoff)).  A splat whose opacity is below the cutoff never contributes.
+__device__ __forceinline__ void conic_extent(float A11, float A12, float A22, float chi2, float op, float alpha_cutoff,
+                                             float& eu, float& ev) {
   const float detc = A11 * A22 - A12 * A12;
+  if (alpha_cutoff > 0.f) chi2 = fminf(chi2, 2.f * logf(op / alpha_cutoff) * 1.0005f + 1e-3f);
+  if (!(chi2 > 0.f)) { eu = -1e30f; ev = -1e30f; return; }
   if (detc > 0.f && isfinite(detc)) {
     eu = sqrtf(chi2 * A22 / detc) * 1.001f + 0.01f;
     ev = sqrtf(chi2 * A11 / detc) * 1.001f + 0.01f;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
       const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
       if (tiles == 0) { tv0 = 0; tv1 = 0; }
       float eu, ev;
-      conic_extent(o.A11, o.A12, o.A22, rp.chi2, eu, ev);
+      conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
       f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
       f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
       f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
         const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
         if (tiles == 0) { tv0 = 0; tv1 = 0; }
         float eu, ev;
-        conic_extent(o.A11, o.A12, o.A22, rp.chi2, eu, ev);
+        conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
         f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
         f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
         f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
