@@ -102,6 +102,7 @@ class Frame:
         self.n_isect = 0
         self.n_visible = 0
         self.n_in_frustum = 0
+        self.n_super = 0
 
     # -- forward ----------------------------------------------------------------------------------------
     def render(self, mode: Optional[str] = None) -> torch.Tensor:
@@ -143,6 +144,7 @@ class Frame:
     def _read_stats(self, stats: torch.Tensor):
         s = FrameStats.from_buffer_copy(stats.numpy().tobytes())
         self.n_isect, self.n_visible, self.n_in_frustum = int(s.n_isect), int(s.n_visible), int(s.n_in_frustum)
+        self.n_super = int(s.n_super)
 
     def _rasterize(self, lib, n, H, W, capacity, image, stats, st):
         sizes = Sizes()

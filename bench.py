@@ -174,20 +174,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # b200gs arm
 # ---------------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, V, I, P, tiles):
+def algorithmic_bytes(N, V, I, P, tiles, S=0):
     """Compulsory HBM bytes per kernel group for one view (each stage reads its inputs once and writes its
-    outputs once; a sort counts as one read + one write of its pairs whatever the pass count) - DESIGN.md."""
+    outputs once; a sort counts as one read + one write of its pairs whatever the pass count) - DESIGN.md.
+    S = number of (supertile, Gaussian) pairs."""
     return {
-        "preprocess_fwd": 236 * N + 64 * V + 8 * (N - V),
+        "emit_super": 12 * N + 8 * V + 8 * S,
+        "super_sort": 8 * S + 8 * S,
+        "split_tiles": 2 * (4 * S + 8 * S) + 4 * I + 8 * tiles,
+        "preprocess_fwd": 236 * N + 68 * V + 12 * (N - V),
         "evaluate_sh": 204 * N + 12 * N,
         "depth_sort": 4 * N + 8 * N,
         "scan": 4 * N + 4 * N + 4 * N,
-        "emit_pairs": 12 * N + 8 * V + 8 * I,
-        "tile_sort": 8 * I + 8 * I,
-        "tile_ranges": 4 * I + 8 * tiles,
         "blend_fwd": 4 * I + 36 * I + 12 * P + 8 * P,
         "blend_bwd": 4 * I + 36 * I + 36 * I + 12 * P + 8 * P,
-        "preprocess_bwd": 236 * N + 36 * V + 236 * N,
+        "preprocess_bwd": 236 * N + 48 * N + 236 * N,
         "build_sigma": 28 * N + 36 * N,
     }
 
@@ -336,7 +337,7 @@ def run_b200gs(args):
         cfg = ops.RenderConfig(H=H, W=W, fx=intr["fx"], fy=intr["fy"], cx=intr["cx"], cy=intr["cy"])
         fr = ops.Frame(g, keep, cfg, c2w_dev[0], dev)
         fr.render("sync")
-    V, I, N, P = fr.n_visible, fr.n_isect, wl["n"], H * W
+    V, I, N, P, S = fr.n_visible, fr.n_isect, wl["n"], H * W, fr.n_super
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
 
     # ---- e2e through the C ABI with HOST buffers (whole Gaussian set uploaded every call) -------------------------
@@ -375,7 +376,7 @@ def run_b200gs(args):
         return 0
 
     hbm, peak_src, sm_max = peaks()
-    bytes_model = algorithmic_bytes(N, V, I, P, tiles)
+    bytes_model = algorithmic_bytes(N, V, I, P, tiles, S)
     table = {}
     for name, (ms, calls) in {**train_regions, **fwd_regions}.items():
         b = bytes_model.get(name)
@@ -396,7 +397,7 @@ def run_b200gs(args):
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_render / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I,
+        "config": {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I, "super_pairs_view0": S,
                    "parallelism": f"frames/views sharded round-robin over {world} rank(s); Gaussians replicated",
                    "capacity_mode": os.environ.get("B200GS_CAPACITY_MODE"),
                    "l2_policy": "inputs larger than L2: every step streams 236 MB of parameters (L2 = 126 MB) and a different view"},
