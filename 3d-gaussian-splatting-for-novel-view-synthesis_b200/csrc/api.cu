@@ -253,9 +253,6 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
                              (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
                              &in_a, s));
     if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
-    PCU(R_SCAN, 1, gs::launch_exclusive_scan(gs::ws_ptr<uint32_t>(frame_ws, L.super_touched), gs::ws_ptr<uint32_t>(frame_ws, L.order),
-                                 gs::ws_ptr<uint32_t>(frame_ws, L.offsets), (uint32_t)gi.n, &stats->n_super,
-                                 gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
   }
   if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
   return B200GS_OK;
@@ -279,14 +276,16 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   uint32_t* keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys);
   uint32_t* vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals);
   uint32_t* lists = gs::ws_ptr<uint32_t>(isect_ws, IL.lists);
-  PCU(R_EMIT, 1, gs::launch_emit_super(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
-                                       gs::ws_ptr<uint32_t>(frame_ws, L.super_touched), gs::ws_ptr<uint2>(frame_ws, L.rect),
-                                       super_x, isect_capacity, keys, vals, stats, s));
+  PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
+                                            gs::ws_ptr<uint2>(frame_ws, L.rect), super_x, isect_capacity, keys, vals, stats,
+                                            tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes,
+                                            gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
   int in_a = 0;
-  PCU(R_TILE_SORT, 2 + (tile_bits(n_super_tiles) + 7) / 8,
+  PCU(R_TILE_SORT, 1 + (tile_bits(n_super_tiles) + 7) / 8,
       gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
                             gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_super, 0,
-                            tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s));
+                            tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s,
+                            /*hist_ready=*/true));
   const SortedSuper ss = sorted_super(isect_ws, IL, n_super_tiles);
   {
     ProfScope _scope(R_SPLIT, s, 2);

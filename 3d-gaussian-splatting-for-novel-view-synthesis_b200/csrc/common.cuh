@@ -69,6 +69,7 @@ struct FrameHeader {
 
 size_t scan_scratch_bytes(uint32_t n);
 size_t sort_scratch_bytes(uint32_t n);
+size_t scan_emit_scratch_bytes(uint32_t n);
 
 inline FrameLayout frame_layout(int n, int H, int W) {
   FrameLayout L;
@@ -93,7 +94,9 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.tile_count = take((size_t)ceil_div(ceil_div(W, kTile), kSuperX) * ceil_div(ceil_div(H, kTile), kSuperY) * 32 * 4 * 4 /* kSplitParts */);
   L.final_T = take(P * 4);
   L.n_contrib = take(P * 4);
-  const size_t a = scan_scratch_bytes((uint32_t)N), b = sort_scratch_bytes((uint32_t)N);
+  size_t a = scan_scratch_bytes((uint32_t)N);
+  const size_t b = sort_scratch_bytes((uint32_t)N), c = scan_emit_scratch_bytes((uint32_t)N);
+  if (c > a) a = c;
   L.scratch_bytes = a > b ? a : b;
   L.scratch = take(L.scratch_bytes);
   L.total = off;
@@ -149,7 +152,12 @@ cudaError_t launch_exclusive_scan(const uint32_t* in, const uint32_t* gather_idx
 cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_a,
                               uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
                               const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
-                              size_t scratch_bytes, int* result_in_a, cudaStream_t s);
+                              size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready = false);
+cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t* super_touched, const uint2* rect,
+                                   int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+                                   b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
+                                   size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
+                                   cudaStream_t s);
 
 cudaError_t launch_emit_super(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* super_touched,
                               const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,

@@ -43,6 +43,37 @@ size_t scan_scratch_bytes(uint32_t n) {
   return 256 + tiles * 8;
 }
 
+// Decoupled look-back executed by one warp: posts this tile's aggregate, sums the aggregates of the
+// predecessors (32 per step, lane l inspects tile j - l) down to the nearest inclusive prefix, posts the
+// inclusive prefix and returns the exclusive one (valid in every lane).
+__device__ __forceinline__ uint32_t scan_lookback(unsigned long long* status, uint32_t tile, uint32_t tile_sum, int lane) {
+  uint32_t prefix = 0;
+  if (tile == 0) {
+    if (lane == 0) st_status64(status + tile, (2ull << 32) | tile_sum);
+    return 0;
+  }
+  if (lane == 0) st_status64(status + tile, (1ull << 32) | tile_sum);
+  int j = (int)tile - 1;
+  while (true) {
+    const int idx = j - lane;
+    const unsigned long long s = (idx >= 0) ? ld_status64(status + idx) : (2ull << 32);  // virtual prefix 0
+    const uint32_t flag = (uint32_t)(s >> 32);
+    const unsigned ready = __ballot_sync(0xffffffffu, flag != 0);
+    const unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
+    const int p = pref ? (__ffs(pref) - 1) : 32;                  // nearest inclusive prefix
+    const unsigned need = (p >= 31) ? 0xffffffffu : ((2u << p) - 1u);
+    if ((ready & need) != need) { __nanosleep(20); continue; }    // someone before it is not posted yet
+    uint32_t c = (lane <= p) ? (uint32_t)s : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    prefix += c;
+    if (p < 32) break;
+    j -= 32;
+  }
+  if (lane == 0) st_status64(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
+  return prefix;
+}
+
 // out[i] = sum_{j<i} in[gather ? gather[j] : j];  *total_out = sum of everything.
 __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t* __restrict__ in,
                                                                       const uint32_t* __restrict__ gather,
@@ -85,31 +116,7 @@ __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint
     tile_sum += t;
   }
   if (warp == 0) {
-    // decoupled look-back, 32 predecessors per step (lane l inspects tile j - l)
-    uint32_t prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) st_status64(status + tile, (2ull << 32) | tile_sum);
-    } else {
-      if (lane == 0) st_status64(status + tile, (1ull << 32) | tile_sum);
-      int j = (int)tile - 1;
-      while (true) {
-        const int idx = j - lane;
-        const unsigned long long s = (idx >= 0) ? ld_status64(status + idx) : (2ull << 32);  // virtual prefix 0
-        const uint32_t flag = (uint32_t)(s >> 32);
-        const unsigned ready = __ballot_sync(0xffffffffu, flag != 0);
-        const unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
-        const int p = pref ? (__ffs(pref) - 1) : 32;                  // nearest inclusive prefix
-        const unsigned need = (p >= 31) ? 0xffffffffu : ((2u << p) - 1u);
-        if ((ready & need) != need) { __nanosleep(20); continue; }    // someone before it is not posted yet
-        uint32_t c = (lane <= p) ? (uint32_t)s : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        prefix += c;
-        if (p < 32) break;
-        j -= 32;
-      }
-      if (lane == 0) st_status64(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
-    }
+    const uint32_t prefix = scan_lookback(status, tile, tile_sum, lane);
     if (lane == 0) {
       s_prefix = prefix;
       if (total_out && tile == (n - 1) / kScanTile) *total_out = prefix + tile_sum;
@@ -386,6 +393,131 @@ __global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
   }
 }
 
+static SortPasses make_passes(int begin_bit, int end_bit) {
+  SortPasses sp;
+  sp.num = (end_bit - begin_bit + 7) / 8;
+  for (int p = 0; p < kMaxPasses; ++p) { sp.shift[p] = 0; sp.bits[p] = 8; }
+  for (int p = 0; p < sp.num; ++p) {
+    sp.shift[p] = begin_bit + 8 * p;
+    sp.bits[p] = (end_bit - sp.shift[p]) < 8 ? (end_bit - sp.shift[p]) : 8;
+  }
+  return sp;
+}
+
+// =================================================================================================
+// Fused binning level 1: exclusive scan of the supertile counts in depth order (decoupled look-back),
+// emission of the (supertile id, Gaussian id) pairs at the scanned offsets, AND the digit histograms the
+// following radix sort needs - one kernel, one pass over the depth-ordered Gaussians.
+// Replaces (reference): render.py:260-281 (expansion) + the implicit offsets of repeat_interleave.
+// =================================================================================================
+constexpr int kSeThreads = 256;
+constexpr int kSeItems = 4;
+constexpr int kSeTile = kSeThreads * kSeItems;   // 1024 depth ranks per block
+
+__global__ void __launch_bounds__(kSeThreads) scan_emit_super_kernel(
+    int n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ super_touched,
+    const uint2* __restrict__ rect, int super_x, uint32_t capacity, uint32_t* __restrict__ keys,
+    uint32_t* __restrict__ vals, b200gs_frame_stats* __restrict__ stats, uint32_t* ticket,
+    unsigned long long* status, SortPasses sp, uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+  __shared__ uint32_t s_warp[kSeThreads / 32];
+  __shared__ uint32_t s_tile, s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kMaxPasses * kRadix; i += kSeThreads) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  if (tile == 0 && tid == 0 && stats->n_isect > capacity) stats->overflow = 1u;   // per-tile lists would not fit
+  const uint32_t r0 = tile * kSeTile + tid * kSeItems;
+  uint32_t id[kSeItems], cnt[kSeItems], excl[kSeItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kSeItems; ++k) {
+    const uint32_t r = r0 + k;
+    id[k] = (r < (uint32_t)n) ? order[r] : 0u;
+    cnt[k] = (r < (uint32_t)n) ? super_touched[id[k]] : 0u;
+    excl[k] = sum;
+    sum += cnt[k];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kSeThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) warp_off += t;
+    tile_sum += t;
+  }
+  if (warp == 0) {
+    const uint32_t prefix = scan_lookback(status, tile, tile_sum, lane);
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (tile == (uint32_t)(n - 1) / kSeTile) stats->n_super = prefix + tile_sum;
+    }
+  }
+  __syncthreads();
+  const uint32_t base = s_prefix + warp_off + (inc - sum);
+#pragma unroll
+  for (int k = 0; k < kSeItems; ++k) {
+    if (cnt[k] == 0) continue;
+    uint32_t off = base + excl[k];
+    if (off + cnt[k] > capacity || off + cnt[k] < off) {   // does not fit: flag it, never write out of bounds
+      stats->overflow = 1u;
+      continue;
+    }
+    const uint2 rc = rect[id[k]];
+    const int sx0 = (rc.x & 0xFFFF) / kSuperX, sx1 = (rc.x >> 16) / kSuperX;
+    const int sy0 = (rc.y & 0xFFFF) / kSuperY, sy1 = (rc.y >> 16) / kSuperY;
+    for (int sy = sy0; sy <= sy1; ++sy)
+      for (int sx = sx0; sx <= sx1; ++sx) {
+        const uint32_t key = (uint32_t)(sy * super_x + sx);
+        keys[off] = key;
+        vals[off] = id[k];
+        ++off;
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; ++p)
+          if (p < sp.num) atomicAdd(&s_hist[p][(key >> sp.shift[p]) & ((1u << sp.bits[p]) - 1u)], 1u);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < kMaxPasses * kRadix; i += kSeThreads) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+}
+
+size_t scan_emit_scratch_bytes(uint32_t n) { return 256 + ((size_t)(n + kSeTile - 1) / kSeTile + 1) * 8; }
+
+// Zeroes `sort_scratch` (tickets, histograms, look-back status of the sort that follows) and `se_scratch`,
+// runs the fused kernel; the sort must then be launched with hist_ready = true on the same scratch.
+cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t* super_touched, const uint2* rect,
+                                   int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+                                   b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
+                                   size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
+                                   cudaStream_t s) {
+  if (sort_scratch_bytes_ < sort_scratch_bytes(capacity) || se_scratch_bytes < scan_emit_scratch_bytes((uint32_t)(n > 0 ? n : 1)))
+    return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(sort_scratch, 0, sort_scratch_bytes(capacity), s);
+  if (e != cudaSuccess) return e;
+  if (n <= 0) return cudaSuccess;
+  e = cudaMemsetAsync(se_scratch, 0, scan_emit_scratch_bytes((uint32_t)n), s);
+  if (e != cudaSuccess) return e;
+  uint32_t* ghist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sort_scratch) + 256);
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(se_scratch);
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(se_scratch) + 256);
+  const SortPasses sp = make_passes(0, sort_bits);
+  scan_emit_super_kernel<<<(n + kSeTile - 1) / kSeTile, kSeThreads, 0, s>>>(n, order, super_touched, rect, super_x,
+                                                                          capacity, keys, vals, stats, ticket, status,
+                                                                          sp, ghist);
+  return cudaGetLastError();
+}
+
 // Sorts on key bits [begin_bit, end_bit) with ceil(bits/8) passes.  Pass 0 reads (keys_src, vals_src) and
 // writes (keys_b, vals_b); later passes ping-pong b -> a -> b ...  `*result_in_a` tells where the sorted
 // data ended up (a for an even pass count, b for an odd one).  keys_src may alias keys_a (then the
@@ -395,27 +527,24 @@ __global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
 cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_a,
                               uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
                               const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
-                              size_t scratch_bytes, int* result_in_a, cudaStream_t s) {
+                              size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready) {
   if (end_bit <= begin_bit || end_bit - begin_bit > 8 * kMaxPasses) return cudaErrorInvalidValue;
   if (scratch_bytes < sort_scratch_bytes(n)) return cudaErrorInvalidValue;
-  SortPasses sp;
-  sp.num = (end_bit - begin_bit + 7) / 8;
-  for (int p = 0; p < kMaxPasses; ++p) { sp.shift[p] = 0; sp.bits[p] = 8; }
-  for (int p = 0; p < sp.num; ++p) {
-    sp.shift[p] = begin_bit + 8 * p;
-    sp.bits[p] = (end_bit - sp.shift[p]) < 8 ? (end_bit - sp.shift[p]) : 8;
-  }
+  const SortPasses sp = make_passes(begin_bit, end_bit);
   if (result_in_a) *result_in_a = (sp.num % 2 == 0) ? 1 : 0;
   if (n == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), s);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (!hist_ready) {     // otherwise the producer of the keys zeroed the scratch and filled the histograms
+    e = cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), s);
+    if (e != cudaSuccess) return e;
+  }
   uint32_t* tickets = reinterpret_cast<uint32_t*>(scratch);
   uint32_t* ghist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 256);
   uint32_t* status0 = ghist + kMaxPasses * kRadix;
   const size_t nblk = sort_blocks(n);
   int hgrid = (int)((n + kSortThreads * 8 - 1) / (kSortThreads * 8));
   if (hgrid > 148 * 8) hgrid = 148 * 8;
-  sort_histogram_kernel<<<hgrid, kSortThreads, 0, s>>>(keys_src, n, n_dev, sp, ghist);
+  if (!hist_ready) sort_histogram_kernel<<<hgrid, kSortThreads, 0, s>>>(keys_src, n, n_dev, sp, ghist);
   sort_scan_hist_kernel<<<sp.num, kRadix, 0, s>>>(ghist);
   const uint32_t *ki = keys_src, *vi = vals_src;
   uint32_t *ko = keys_b, *vo = vals_b;
