@@ -244,14 +244,17 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
   CU(cudaMemsetAsync(stats, 0, sizeof(b200gs_frame_stats), s));
   if (gi.n > 0) {
-    PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s));
+    bool hist_done = false;
+    CU(gs::radix_sort_prepare(gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, (uint32_t)gi.n, s));
+    PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s,
+                                                       gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch)), &hist_done));
     // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
     int in_a = 0;
-    PCU(R_DEPTH_SORT, 6, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
+    PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
                              gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2), gs::ws_ptr<uint32_t>(frame_ws, L.order),
                              gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
                              (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
-                             &in_a, s));
+                             &in_a, s, hist_done));
     if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
   }
   if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
@@ -281,7 +284,7 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
                                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes,
                                             gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
   int in_a = 0;
-  PCU(R_TILE_SORT, 1 + (tile_bits(n_super_tiles) + 7) / 8,
+  PCU(R_TILE_SORT, (tile_bits(n_super_tiles) + 7) / 8,
       gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
                             gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_super, 0,
                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s,

@@ -135,8 +135,13 @@ struct GaussGrad {
   float *pos, *opacity_raw, *scale_raw, *q_raw, *sigma, *f_dc, *f_rest, *color;
 };
 
+// depth_hist (optional): [4][256] zeroed counters; when the kernel variant can, it accumulates the digit
+// histograms of the depth keys there and sets *hist_done (the depth sort then skips its histogram pass).
 cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const RenderParams& rp, void* frame_ws,
-                                  const FrameLayout& L, cudaStream_t s);
+                                  const FrameLayout& L, cudaStream_t s, uint32_t* depth_hist = nullptr,
+                                  bool* hist_done = nullptr);
+cudaError_t radix_sort_prepare(void* scratch, size_t scratch_bytes, uint32_t n, cudaStream_t s);
+uint32_t* radix_sort_hist(void* scratch);
 cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const float* c2w, const RenderParams& rp,
                                   void* frame_ws, const FrameLayout& L, cudaStream_t s);
 cudaError_t launch_build_sigma(int n, const float* scale_raw, const float* q_raw, float* sigma, cudaStream_t s);

@@ -214,14 +214,17 @@ struct __align__(128) PreStage {
 constexpr uint32_t kPreStageBytes = kPreBlock * (45 + 4 + 3 + 3 + 3 + 1) * 4;
 
 __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
-                                                                       RenderParams rp, FrameView f, int n_chunks) {
+                                                                       RenderParams rp, FrameView f, int n_chunks,
+                                                                       uint32_t* __restrict__ depth_hist) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PreStage* stage = reinterpret_cast<PreStage*>(smem_raw);       // [2]
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
+  __shared__ uint32_t s_dh[4][256];      // digit histograms of the depth keys (the depth sort's 4 passes)
   const int tid = threadIdx.x;
   if (tid < 16) s_c2w[tid] = c2w[tid];
+  for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
   if (tid == 0) {
     s_tiles = 0;
     mbar_init(&s_bar[0], 1);
@@ -281,6 +284,11 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       Projection o;
       const bool vis = project_gaussian(p, S, st.opac[tid], ps, rp, o);
       s7_count += (vis || o.offscreen) ? 1u : 0u;
+      if (depth_hist) {
+        const uint32_t dk = vis ? __float_as_uint(o.z) : kCulledKey;
+        atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
+        atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
+      }
       if (!vis) {
         f.depth_key[i] = kCulledKey;
         f.tiles_touched[i] = 0;
@@ -319,6 +327,11 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
   }
   __syncthreads();
   if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
+  if (depth_hist)
+    for (int i = tid; i < 4 * 256; i += kPreBlock) {
+      const uint32_t c = (&s_dh[0][0])[i];
+      if (c) atomicAdd(&depth_hist[i], c);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,7 +622,8 @@ static FrameView make_view(void* ws, const FrameLayout& L) {
 }
 
 cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const RenderParams& rp, void* ws,
-                                  const FrameLayout& L, cudaStream_t s) {
+                                  const FrameLayout& L, cudaStream_t s, uint32_t* depth_hist, bool* hist_done) {
+  if (hist_done) *hist_done = false;
   if (g.n <= 0) return cudaSuccess;
   const FrameView f = make_view(ws, L);
   const int grid = ceil_div(g.n, kPreBlock);
@@ -626,7 +640,8 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
       cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
     }
     const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
-    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid);
+    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
+    if (hist_done) *hist_done = depth_hist != nullptr;
     return cudaGetLastError();
   }
   if (rc && rs) preprocess_fwd_kernel<true, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);

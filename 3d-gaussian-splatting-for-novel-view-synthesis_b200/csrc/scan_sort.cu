@@ -228,12 +228,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 __global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int shift, int bits,
-    const uint32_t* __restrict__ gbase /*[256] exclusive*/, uint32_t* __restrict__ status, uint32_t* ticket) {
+    const uint32_t* __restrict__ ghist /*[256] digit counts of this pass*/, uint32_t* __restrict__ status, uint32_t* ticket) {
   __shared__ uint32_t s_warp_hist[kSortWarps][kRadix + 1];
   __shared__ uint32_t s_keys[kSortTile];
   __shared__ uint32_t s_vals[kSortTile];
   __shared__ uint32_t s_hist[kRadix];          // digit counts of this block (early counts)
   __shared__ uint32_t s_excl[kRadix];          // digit counts of all earlier blocks (look-back result)
+  __shared__ uint32_t s_gbase[kRadix];         // exclusive scan of the global digit histogram
   __shared__ uint32_t s_digit_start[kRadix];
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_vbid;
@@ -276,6 +277,21 @@ __global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
   __syncthreads();
 
   if (is_lb) {
+    // ---- global digit offsets: exclusive scan of the 256-bin histogram (lane owns digits 8 lane .. 8 lane + 7) ---
+    {
+      uint32_t h[8], run = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { h[k] = ghist[8 * lane + k]; run += h[k]; }
+      uint32_t inc = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      uint32_t acc = inc - run;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s_gbase[8 * lane + k] = acc; acc += h[k]; }
+    }
     // ---- decoupled look-back: lane handles digits lane + 32 k ------------------------------------------------
     uint32_t cnt[8], excl[8];
     int j[8];
@@ -382,7 +398,7 @@ __global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
   __syncthreads();   // reorder done AND look-back done
 
   // ---- stream out in digit runs: global position = gbase[d] + earlier blocks' count + offset within the digit ----
-  if (tid < kRadix) s_hist[tid] = gbase[tid] + s_excl[tid] - s_digit_start[tid];   // s_hist reused as delta
+  if (tid < kRadix) s_hist[tid] = s_gbase[tid] + s_excl[tid] - s_digit_start[tid];   // s_hist reused as delta
   __syncthreads();
   const uint32_t in_block = min((uint32_t)kSortTile, n - base);
   for (uint32_t p = tid; p < in_block; p += kSortBlock) {
@@ -518,6 +534,14 @@ cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t*
   return cudaGetLastError();
 }
 
+// Zeroes the sort scratch so that a producer kernel can accumulate the digit histograms (radix_sort_hist)
+// before launch_radix_sort(..., hist_ready = true).
+cudaError_t radix_sort_prepare(void* scratch, size_t scratch_bytes, uint32_t n, cudaStream_t s) {
+  if (scratch_bytes < sort_scratch_bytes(n)) return cudaErrorInvalidValue;
+  return cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), s);
+}
+uint32_t* radix_sort_hist(void* scratch) { return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 256); }
+
 // Sorts on key bits [begin_bit, end_bit) with ceil(bits/8) passes.  Pass 0 reads (keys_src, vals_src) and
 // writes (keys_b, vals_b); later passes ping-pong b -> a -> b ...  `*result_in_a` tells where the sorted
 // data ended up (a for an even pass count, b for an odd one).  keys_src may alias keys_a (then the
@@ -545,7 +569,6 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
   int hgrid = (int)((n + kSortThreads * 8 - 1) / (kSortThreads * 8));
   if (hgrid > 148 * 8) hgrid = 148 * 8;
   if (!hist_ready) sort_histogram_kernel<<<hgrid, kSortThreads, 0, s>>>(keys_src, n, n_dev, sp, ghist);
-  sort_scan_hist_kernel<<<sp.num, kRadix, 0, s>>>(ghist);
   const uint32_t *ki = keys_src, *vi = vals_src;
   uint32_t *ko = keys_b, *vo = vals_b;
   for (int p = 0; p < sp.num; ++p) {
