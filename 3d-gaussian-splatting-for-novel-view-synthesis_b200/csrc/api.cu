@@ -136,7 +136,7 @@ __global__ void export_kernel(int n, const float4* rec0, const float4* rec1, con
                c = vis ? rec2[i] : make_float4(0, 0, 0, 0);
   if (xy) { xy[2 * i] = a.x; xy[2 * i + 1] = a.y; }
   if (depth) depth[i] = vis ? __uint_as_float(depth_key[i]) : -1.f;
-  if (conic) { conic[3 * i] = a.z; conic[3 * i + 1] = a.w; conic[3 * i + 2] = b.x; }
+  if (conic) { conic[3 * i] = a.z; conic[3 * i + 1] = 0.5f * a.w; conic[3 * i + 2] = b.x; }   // rec0.w = 2*A12
   if (opacity) opacity[i] = b.y;
   if (color) { color[3 * i] = b.z; color[3 * i + 1] = b.w; color[3 * i + 2] = c.x; }
   if (radius) radius[i] = vis ? (int32_t)c.w : 0;

@@ -28,14 +28,32 @@ __device__ __forceinline__ PixelCoord pixel_of_thread(const RenderParams& rp, in
 
 // alpha of one splat at one pixel; identical instruction sequence in forward and backward.
 // Returns 0 when the splat does not contribute (render.py:362-374).
+// Shared-memory reads with an explicit 32-bit shared address: keeps the per-visit address arithmetic to one
+// IMAD (the generic-pointer form re-derives the shared window base inside the loop).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {   // q <= chi2 keeps the argument far from the denormal range
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float splat_alpha(const float4& r0, const float4& r1, float pxf, float pyf,
                                              const RenderParams& rp, float& du, float& dv, float& gval,
                                              float& araw) {
   du = pxf - r0.x;
   dv = pyf - r0.y;
-  const float q = fmaf(r1.x * dv, dv, fmaf((2.f * r0.w) * du, dv, (r0.z * du) * du));
+  const float q = fmaf(r1.x * dv, dv, fmaf(r0.w * du, dv, (r0.z * du) * du));   // r0.w holds 2*A12
   if (!(q <= rp.chi2)) return 0.f;
-  gval = __expf(-0.5f * q);
+  gval = ex2_ftz(q * -0.72134752044448170368f);   // exp(-q/2)
   araw = r1.y * gval;
   const float a = fminf(araw, rp.alpha_max);
   return (a >= rp.alpha_cutoff) ? a : 0.f;
@@ -57,21 +75,29 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
                                                                   float* __restrict__ image,
                                                                   float* __restrict__ final_T,
                                                                   uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 s0[kBlendThreads], s1[kBlendThreads], s2[kBlendThreads];
+  __shared__ float4 s_rec[3][kBlendThreads];      // [0] = rec0, [1] = rec1, [2] = rec2 of the staged batch
+  float4* const s0 = s_rec[0];
+  float4* const s1 = s_rec[1];
+  float4* const s2 = s_rec[2];
+  uint32_t sa0;   // opaque copy of the shared address: stops the compiler re-deriving it inside the visit loop
+  asm volatile("mov.u32 %0, %1;" : "=r"(sa0) : "r"((uint32_t)__cvta_generic_to_shared(s_rec)));
+  constexpr uint32_t kRecStride = kBlendThreads * 16;
   const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
-  float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  // T is the true transmittance (stored for the backward); Tl is its "live" copy that drops to 0 once
+  // T <= 5e-5 (render.py:387: a splat contributes iff the transmittance BEFORE it is > 5e-5), so a finished
+  // pixel needs no branch in the visit loop: its weights are simply zero.
+  float T = 1.f, Tl = pc.inside ? 1.f : 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t last = 0;
-  bool done = !pc.inside;
   // centre of this warp's 8x4 pixel block: a splat can only touch the block if its centre lies within
-  // (ext_u + 3.5, ext_v + 1.5) of it, where ext_* are the conservative half-extents of {q <= chi2}
+  // (ext_u + 3.5, ext_v + 1.5) of it, where ext_* are the conservative half-extents of its footprint
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
   for (uint32_t base = range.x; base < range.y; base += kBlendThreads) {
-    if (__syncthreads_count(done) == kBlendThreads) break;
+    if (__syncthreads_count(Tl == 0.f) == kBlendThreads) break;
     const uint32_t idx = base + threadIdx.x;
     if (idx < range.y) {
       const uint32_t id = vals[idx];
@@ -81,8 +107,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
     }
     __syncthreads();
     const int cnt = (int)min((uint32_t)kBlendThreads, range.y - base);
+    const uint32_t list_off = base - range.x + 1u;
     for (int chunk = 0; chunk < cnt; chunk += 32) {
-      if (__all_sync(0xffffffffu, done)) break;
+      if (__all_sync(0xffffffffu, Tl == 0.f)) break;
       // each lane tests one splat of the chunk against the warp's pixel block
       const int jt = chunk + lane;
       bool touch = false;
@@ -94,19 +121,18 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
       while (m) {
         const int j = chunk + __ffs(m) - 1;
         m &= m - 1;
-        if (!done) {
-          const float4 r0 = s0[j], r1 = s1[j];
-          float du, dv, gval, araw;
-          const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
-          if (a > 0.f) {
-            const float w = a * T;
-            C0 = fmaf(w, r1.z, C0);
-            C1 = fmaf(w, r1.w, C1);
-            C2 = fmaf(w, s2[j].x, C2);
-            T *= (1.f - a);
-            last = (base - range.x) + (uint32_t)j + 1u;
-            done = !(T > 5e-5f);   // render.py:387: the next splat contributes only if T is still > 5e-5
-          }
+        const uint32_t aj = sa0 + (uint32_t)j * 16u;
+        const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
+        float du, dv, gval, araw;
+        const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
+        if (a > 0.f && Tl > 0.f) {
+          const float w = a * Tl;
+          C0 = fmaf(w, r1.z, C0);
+          C1 = fmaf(w, r1.w, C1);
+          C2 = fmaf(w, lds_f(aj + 2 * kRecStride), C2);
+          T = Tl * (1.f - a);
+          last = list_off + (uint32_t)j;
+          Tl = (T > 5e-5f) ? T : 0.f;
         }
       }
     }
@@ -158,7 +184,12 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
                                                                   const float* __restrict__ final_T,
                                                                   const uint32_t* __restrict__ n_contrib,
                                                                   float* __restrict__ grad_acc) {
-  __shared__ float4 s0[kBlendThreads], s1[kBlendThreads];
+  __shared__ float4 s_rec[2][kBlendThreads];
+  float4* const s0 = s_rec[0];
+  float4* const s1 = s_rec[1];
+  uint32_t sa0;   // opaque copy of the shared address: stops the compiler re-deriving it inside the visit loop
+  asm volatile("mov.u32 %0, %1;" : "=r"(sa0) : "r"((uint32_t)__cvta_generic_to_shared(s_rec)));
+  constexpr uint32_t kRecStride = kBlendThreads * 16;
   __shared__ float s_cb[kBlendThreads];
   __shared__ float2 s_ext[kBlendThreads];
   __shared__ uint32_t s_id[kBlendThreads];
@@ -237,7 +268,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
         const int j = chunk + bit;
         const bool active = (boff + (uint32_t)j) < last;
         float a = 0.f, du = 0.f, dv = 0.f, gval = 0.f, araw = 0.f;
-        const float4 r0 = s0[j], r1 = s1[j];
+        const uint32_t aj = sa0 + (uint32_t)j * 16u;
+        const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
         if (active) a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
         const bool hit = a > 0.f;
         if (!__any_sync(0xffffffffu, hit)) continue;
@@ -255,7 +287,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
           const float draw = (araw <= rp.alpha_max) ? dalpha : 0.f;   // clamp_max passes on <=
           v_op = draw * gval;
           const float dq = -0.5f * araw * draw;                       // d/dq of op*exp(-q/2)
-          const float B2 = 2.f * r0.w;
+          const float B2 = r0.w;            // 2*A12
           v_u = -dq * (2.f * r0.z * du + B2 * dv);
           v_v = -dq * (2.f * r1.x * dv + B2 * du);
           v_a11 = dq * du * du;

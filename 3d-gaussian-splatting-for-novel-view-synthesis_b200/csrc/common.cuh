@@ -33,7 +33,7 @@ __device__ __forceinline__ float ld_stream_f(const float* p) {
 // Frame workspace: header | per-Gaussian | per-tile | per-pixel.   Everything 256-byte aligned.
 struct FrameLayout {
   size_t header;          // b200gs_frame_stats (64 B) + scan/sort bookkeeping
-  size_t rec0, rec1, rec2;  // float4[n] each: (u,v,A11,A12) (A22,op,r,g) (b,ext_u,ext_v,radius)
+  size_t rec0, rec1, rec2;  // float4[n] each: (u,v,A11,2*A12) (A22,op,r,g) (b,ext_u,ext_v,radius)
   size_t depth_key;       // u32[n]  float bits of z, 0xFFFFFFFF when culled
   size_t rect;            // uint2[n] packed u16 tile rect: x = tu0 | tu1<<16, y = tv0 | tv1<<16
   size_t tiles_touched;   // u32[n]

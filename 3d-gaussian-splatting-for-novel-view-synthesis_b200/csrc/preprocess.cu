@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
       if (tiles == 0) { tv0 = 0; tv1 = 0; }
       float eu, ev;
       conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
-      f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
+      f.rec0[i] = make_float4(o.u, o.v, o.A11, 2.f * o.A12);
       f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
       f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
       f.depth_key[i] = __float_as_uint(o.z);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
         if (tiles == 0) { tv0 = 0; tv1 = 0; }
         float eu, ev;
         conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
-        f.rec0[i] = make_float4(o.u, o.v, o.A11, o.A12);
+        f.rec0[i] = make_float4(o.u, o.v, o.A11, 2.f * o.A12);
         f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
         f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
         f.depth_key[i] = __float_as_uint(o.z);
