@@ -74,13 +74,31 @@ class RenderConfig:
 _pinned_stats = {}
 
 
-def _stats_buffer(device) -> torch.Tensor:
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _pinned_stats.get(key)
-    if buf is None:
+def _stats_buffer(device, stream_handle: int):
+    """(pinned int32[16] tensor, numpy view of it, data pointer) for this device/stream."""
+    key = (device.index, stream_handle)
+    ent = _pinned_stats.get(key)
+    if ent is None:
         buf = torch.zeros(16, dtype=torch.int32).pin_memory()
-        _pinned_stats[key] = buf
-    return buf
+        ent = (buf, buf.numpy(), ctypes.c_void_p(buf.data_ptr()))
+        _pinned_stats[key] = ent
+    return ent
+
+
+_sizes_cache = {}
+
+
+def _sizes(lib, n: int, H: int, W: int, capacity: int):
+    key = (n, H, W, capacity)
+    got = _sizes_cache.get(key)
+    if got is None:
+        sz = Sizes()
+        _lib.check(lib.b200gs_workspace_sizes(n, H, W, capacity, ctypes.byref(sz)), "workspace_sizes")
+        got = (int(sz.frame_bytes), int(sz.isect_bytes))
+        if len(_sizes_cache) > 4096:
+            _sizes_cache.clear()
+        _sizes_cache[key] = got
+    return got
 
 
 # Intersection-capacity policy.  "sync" (default): read I back between project and rasterize (one
@@ -111,49 +129,55 @@ class Frame:
         n = int(self.g.n)
         H, W = int(self.cfg.H), int(self.cfg.W)
         mode = mode or os.environ.get("B200GS_CAPACITY_MODE", "sync")
-        sizes = Sizes()
-        _lib.check(lib.b200gs_workspace_sizes(n, H, W, 0, ctypes.byref(sizes)), "workspace_sizes")
-        self.frame_ws = torch.empty(sizes.frame_bytes, dtype=torch.uint8, device=dev)
-        stats = _stats_buffer(dev)
-        st = _stream(dev)
+        stream = torch.cuda.current_stream(dev)
+        st = ctypes.c_void_p(stream.cuda_stream)
+        frame_bytes, _ = _sizes(lib, n, H, W, 0)
+        self.frame_ws = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+        _, stats_np, stats_ptr = _stats_buffer(dev, stream.cuda_stream)
         image = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
-                                             sizes.frame_bytes, None if spec_cap else ctypes.c_void_p(stats.data_ptr()),
-                                             st), "render_project")
+                                             frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
         if spec_cap:
-            self._rasterize(lib, n, H, W, spec_cap, image, stats, st)
-            torch.cuda.current_stream(dev).synchronize()
-            self._read_stats(stats)
+            self._rasterize(lib, n, H, W, spec_cap, image, stats_ptr, st)
+            stream.synchronize()
+            self._read_stats(stats_np)
             if self.n_isect > spec_cap:           # did not fit: redo with exact buffers
-                self._rasterize(lib, n, H, W, self._grow(self.n_isect), image, stats, st)
-                torch.cuda.current_stream(dev).synchronize()
-                self._read_stats(stats)
+                self._rasterize(lib, n, H, W, self._grow(self.n_isect), image, stats_ptr, st)
+                stream.synchronize()
+                self._read_stats(stats_np)
         else:
-            torch.cuda.current_stream(dev).synchronize()
-            self._read_stats(stats)
+            stream.synchronize()
+            self._read_stats(stats_np)
             self._rasterize(lib, n, H, W, self._grow(self.n_isect) if mode == "speculative" else max(self.n_isect, 1),
-                            image, None, st)
+                            image, stats_ptr, st)
+            self._stats_pending = (stream, stats_np)     # n_super is only known after rasterize
         return image
+
+    def refresh_stats(self):
+        """Counters written by the rasterize phase (n_super); synchronises the stream."""
+        pend = getattr(self, "_stats_pending", None)
+        if pend is not None:
+            pend[0].synchronize()
+            self._read_stats(pend[1])
+            self._stats_pending = None
 
     def _grow(self, need: int) -> int:
         cap = max(int(need * 1.25) + 1024, _high_water.get(self.device.index, 0))
         _high_water[self.device.index] = cap
         return cap
 
-    def _read_stats(self, stats: torch.Tensor):
-        s = FrameStats.from_buffer_copy(stats.numpy().tobytes())
-        self.n_isect, self.n_visible, self.n_in_frustum = int(s.n_isect), int(s.n_visible), int(s.n_in_frustum)
-        self.n_super = int(s.n_super)
+    def _read_stats(self, arr):
+        # b200gs_frame_stats: n_isect, n_visible, overflow, n_in_frustum, n_super (uint32 each)
+        self.n_isect, self.n_visible = int(arr[0]) & 0xFFFFFFFF, int(arr[1]) & 0xFFFFFFFF
+        self.n_in_frustum, self.n_super = int(arr[3]) & 0xFFFFFFFF, int(arr[4]) & 0xFFFFFFFF
 
-    def _rasterize(self, lib, n, H, W, capacity, image, stats, st):
-        sizes = Sizes()
-        _lib.check(lib.b200gs_workspace_sizes(n, H, W, capacity, ctypes.byref(sizes)), "workspace_sizes")
+    def _rasterize(self, lib, n, H, W, capacity, image, stats_ptr, st):
+        frame_bytes, isect_bytes = _sizes(lib, n, H, W, capacity)
         self.capacity = capacity
-        self.isect_ws = torch.empty(sizes.isect_bytes, dtype=torch.uint8, device=self.device)
-        _lib.check(lib.b200gs_render_rasterize(ctypes.byref(self.cam), n, _ptr(self.frame_ws), self.frame_ws.numel(),
-                                               _ptr(self.isect_ws), sizes.isect_bytes, capacity, _ptr(image),
-                                               None if stats is None else ctypes.c_void_p(stats.data_ptr()), st),
+        self.isect_ws = torch.empty(isect_bytes, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.b200gs_render_rasterize(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
+                                               _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr, st),
                    "render_rasterize")
 
     # -- backward ---------------------------------------------------------------------------------------
@@ -167,6 +191,7 @@ class Frame:
     # -- introspection (parity tests) -------------------------------------------------------------------
     def export(self):
         lib = _lib.load()
+        self.refresh_stats()
         n, dev = int(self.g.n), self.device
         H, W = int(self.cfg.H), int(self.cfg.W)
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)

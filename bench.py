@@ -337,6 +337,7 @@ def run_b200gs(args):
         cfg = ops.RenderConfig(H=H, W=W, fx=intr["fx"], fy=intr["fy"], cx=intr["cx"], cy=intr["cy"])
         fr = ops.Frame(g, keep, cfg, c2w_dev[0], dev)
         fr.render("sync")
+        fr.refresh_stats()
     V, I, N, P, S = fr.n_visible, fr.n_isect, wl["n"], H * W, fr.n_super
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
 
