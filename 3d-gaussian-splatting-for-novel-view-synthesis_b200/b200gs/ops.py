@@ -85,6 +85,21 @@ def _stats_buffer(device, stream_handle: int):
     return ent
 
 
+_stats_events = {}
+
+
+def _stats_event(device, stream):
+    """(torch event, raw cudaEvent_t) the library records once a frame's counters are final."""
+    key = (device.index, stream.cuda_stream)
+    ent = _stats_events.get(key)
+    if ent is None:
+        ev = torch.cuda.Event()
+        ev.record(stream)                       # torch creates the CUDA event lazily, on first record
+        ent = (ev, ctypes.c_void_p(ev.cuda_event))
+        _stats_events[key] = ent
+    return ent
+
+
 _sizes_cache = {}
 
 
@@ -121,6 +136,7 @@ class Frame:
         self.n_visible = 0
         self.n_in_frustum = 0
         self.n_super = 0
+        self.overflow = False
 
     # -- forward ----------------------------------------------------------------------------------------
     def render(self, mode: Optional[str] = None) -> torch.Tensor:
@@ -139,10 +155,14 @@ class Frame:
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
                                              frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
         if spec_cap:
-            self._rasterize(lib, n, H, W, spec_cap, image, stats_ptr, st)
-            stream.synchronize()
+            # the whole frame is queued; the host only waits until the counters are final (end of the binning
+            # scan), not for the sort / split / blend kernels behind it, so the next frame can be queued
+            # while this one is still running
+            ev, ev_ptr = _stats_event(dev, stream)
+            self._rasterize(lib, n, H, W, spec_cap, image, stats_ptr, st, ev_ptr)
+            ev.synchronize()
             self._read_stats(stats_np)
-            if self.n_isect > spec_cap:           # did not fit: redo with exact buffers
+            if self.n_isect > spec_cap or self.overflow:     # did not fit: redo with exact buffers
                 self._rasterize(lib, n, H, W, self._grow(self.n_isect), image, stats_ptr, st)
                 stream.synchronize()
                 self._read_stats(stats_np)
@@ -171,13 +191,15 @@ class Frame:
         # b200gs_frame_stats: n_isect, n_visible, overflow, n_in_frustum, n_super (uint32 each)
         self.n_isect, self.n_visible = int(arr[0]) & 0xFFFFFFFF, int(arr[1]) & 0xFFFFFFFF
         self.n_in_frustum, self.n_super = int(arr[3]) & 0xFFFFFFFF, int(arr[4]) & 0xFFFFFFFF
+        self.overflow = int(arr[2]) != 0
 
-    def _rasterize(self, lib, n, H, W, capacity, image, stats_ptr, st):
+    def _rasterize(self, lib, n, H, W, capacity, image, stats_ptr, st, stats_event=None):
         frame_bytes, isect_bytes = _sizes(lib, n, H, W, capacity)
         self.capacity = capacity
         self.isect_ws = torch.empty(isect_bytes, dtype=torch.uint8, device=self.device)
-        _lib.check(lib.b200gs_render_rasterize(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
-                                               _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr, st),
+        _lib.check(lib.b200gs_render_rasterize_ev(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
+                                                  _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr,
+                                                  stats_event, st),
                    "render_rasterize")
 
     # -- backward ---------------------------------------------------------------------------------------

@@ -264,6 +264,13 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
 int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
                             size_t isect_bytes, uint32_t isect_capacity, float* image_out,
                             b200gs_frame_stats* stats_host, void* stream) {
+  return b200gs_render_rasterize_ev(cam, n, frame_ws, frame_bytes, isect_ws, isect_bytes, isect_capacity, image_out,
+                                    stats_host, nullptr, stream);
+}
+
+int b200gs_render_rasterize_ev(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
+                               size_t isect_bytes, uint32_t isect_capacity, float* image_out,
+                               b200gs_frame_stats* stats_host, void* stats_event, void* stream) {
   gs::RenderParams rp;
   int rc = make_params(cam, rp);
   if (rc) return rc;
@@ -279,10 +286,16 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
   uint32_t* keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys);
   uint32_t* vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals);
   uint32_t* lists = gs::ws_ptr<uint32_t>(isect_ws, IL.lists);
+  // a frame that overflowed a speculative capacity is rasterized again with exact buffers: start clean
+  CU(cudaMemsetAsync(&stats->overflow, 0, sizeof(uint32_t), s));
   PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
                                             gs::ws_ptr<uint2>(frame_ws, L.rect), super_x, isect_capacity, keys, vals, stats,
                                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes,
                                             gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
+  // every counter (I, V, pair count, overflow) is final here: hand them to the host now, so that it can
+  // decide about a capacity overflow while the rest of the frame is still running
+  if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
+  if (stats_event) CU(cudaEventRecord((cudaEvent_t)stats_event, s));
   int in_a = 0;
   PCU(R_TILE_SORT, (tile_bits(n_super_tiles) + 7) / 8,
       gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
@@ -307,7 +320,6 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }
   PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s));
-  if (stats_host) CU(cudaMemcpyAsync(stats_host, stats, sizeof(b200gs_frame_stats), cudaMemcpyDeviceToHost, s));
   return B200GS_OK;
 }
 

@@ -2,9 +2,17 @@
 //
 // Replaces (reference): render.py:317-410 (S16-S17, the Python loop over tiles) and its autograd.
 // One 256-thread CTA per 16x16 tile; each warp owns an 8x4 pixel block.  Splat records of the tile's
-// depth-sorted list are staged 256 at a time into shared memory (3 x float4 per splat, read back as
-// warp-wide broadcasts), every pixel walks the batch front to back, and the CTA stops as soon as every
-// pixel's transmittance is <= 5e-5 (render.py:387: a splat contributes iff T *before* it is > 5e-5).
+// depth-sorted list are staged 256 at a time into shared memory, every warp first compacts the batch to
+// the splats whose footprint can touch its pixel block (one splat per lane, ballot + prefix popcount into
+// a per-warp list of shared addresses), then every pixel walks that list front to back, and the CTA stops
+// as soon as every pixel's transmittance is <= 5e-5 (render.py:387: a splat contributes iff T *before* it
+// is > 5e-5).
+//
+// Staged form of a splat (computed once per (tile, splat) while staging, so the per-(pixel, splat) visit
+// is as short as possible): with c = -log2(e)/2 the exponent of  alpha_raw = op * exp(-q/2) = 2^e  is
+//     e = c*A11*du^2 + c*2*A12*du*dv + c*A22*dv^2 + log2(op)
+// and both gates of render.py:362-374 collapse into one compare:
+//     q <= chi2  and  min(alpha_raw, alpha_max) >= alpha_cutoff   <=>   e >= max(c*chi2 + log2(op), log2(alpha_cutoff)).
 //
 // Roofline: FP32 issue + MUFU.EX2; HBM traffic is the 36-B record gather per
 // intersection plus 12 B/pixel of output.
@@ -13,7 +21,10 @@
 namespace gs {
 
 constexpr int kBlendThreads = 256;
+constexpr int kBlendWarps = kBlendThreads / 32;
 constexpr uint32_t kCountMask = 0x1FFFFFFFu;
+constexpr float kExpScale = -0.72134752044448170368f;   // -log2(e)/2 : exp(-q/2) = 2^(kExpScale*q)
+constexpr uint32_t kRecStride = kBlendThreads * 16;      // bytes between the staged float4 planes
 
 struct PixelCoord { int px, py; bool inside; };
 
@@ -26,45 +37,90 @@ __device__ __forceinline__ PixelCoord pixel_of_thread(const RenderParams& rp, in
   return p;
 }
 
-// alpha of one splat at one pixel; identical instruction sequence in forward and backward.
-// Returns 0 when the splat does not contribute (render.py:362-374).
-// Shared-memory reads with an explicit 32-bit shared address: keeps the per-visit address arithmetic to one
-// IMAD (the generic-pointer form re-derives the shared window base inside the loop).
+// Shared-memory reads with an explicit 32-bit shared address (the per-warp lists hold such addresses).
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ float lds_f(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ float ex2_ftz(float x) {   // q <= chi2 keeps the argument far from the denormal range
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ex2_ftz(float x) {   // arguments are >= log2(alpha_cutoff): far from the denormal range
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-__device__ __forceinline__ float splat_alpha(const float4& r0, const float4& r1, float pxf, float pyf,
-                                             const RenderParams& rp, float& du, float& dv, float& gval,
-                                             float& araw) {
-  du = pxf - r0.x;
-  dv = pyf - r0.y;
-  const float q = fmaf(r1.x * dv, dv, fmaf(r0.w * du, dv, (r0.z * du) * du));   // r0.w holds 2*A12
-  if (!(q <= rp.chi2)) return 0.f;
-  gval = ex2_ftz(q * -0.72134752044448170368f);   // exp(-q/2)
-  araw = r1.y * gval;
-  const float a = fminf(araw, rp.alpha_max);
-  return (a >= rp.alpha_cutoff) ? a : 0.f;
+// Shared address of a __shared__ object as an opaque register value: stops the compiler from re-deriving
+// the shared window base (S2UR/ULEA chains) inside the visit loops.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  uint32_t a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return a;
+}
+
+// log2 of the alpha cutoff as the lower bound of the exponent; +inf when nothing can pass
+// (alpha_cutoff > alpha_max), -inf / NaN-free "everything passes" for a non-positive cutoff.
+__device__ __forceinline__ float cutoff_exponent(const RenderParams& rp) {
+  if (!(rp.alpha_cutoff <= rp.alpha_max)) return __int_as_float(0x7f800000);
+  if (!(rp.alpha_cutoff > 0.f)) return __int_as_float(0xff800000);
+  return __log2f(rp.alpha_cutoff);
+}
+
+// rec0 = (u, v, A11, 2*A12), rec1 = (A22, op, r, g)  ->  s0 = (u, v, c*A11, c*2*A12), s1 = (c*A22, log2 op, gate, r)
+__device__ __forceinline__ void stage_splat(const float4& a0, const float4& a1, float chi2c, float cut_e,
+                                            float4& s0, float4& s1) {
+  const float lop = __log2f(a1.y);
+  s0 = make_float4(a0.x, a0.y, kExpScale * a0.z, kExpScale * a0.w);
+  s1 = make_float4(kExpScale * a1.x, lop, fmaxf(chi2c + lop, cut_e), a1.z);
+}
+
+// exponent e of alpha_raw = 2^e at pixel offset (du, dv) from the splat centre
+__device__ __forceinline__ float splat_exponent(const float4& s0, const float4& s1, float du, float dv) {
+  const float t1 = fmaf(s0.z, du, s0.w * dv);
+  const float t2 = fmaf(s1.x * dv, dv, s1.y);
+  return fmaf(du, t1, t2);
 }
 
 // Can this splat contribute to any pixel of the warp's 8x4 block (centre wcx, wcy)?  Bounding box of the
 // effective ellipse { q <= min(chi2, 2 ln(opacity / alpha_cutoff)) } (extents precomputed per splat,
 // conservative) against the block.  (An exact ellipse-vs-rectangle test was measured: it costs more than
 // the few extra visits it removes.)  One lane evaluates one splat.
-__device__ __forceinline__ bool splat_touches_block(const float4& r0, float eu, float ev, float wcx, float wcy) {
-  return (fabsf(r0.x - wcx) <= eu + 3.5f) && (fabsf(r0.y - wcy) <= ev + 1.5f);
+__device__ __forceinline__ bool splat_touches_block(float u, float v, float eu, float ev, float wcx, float wcy) {
+  return (fabsf(u - wcx) <= eu + 3.5f) && (fabsf(v - wcy) <= ev + 1.5f);
+}
+
+// Compacts the staged splats [0, lim) that can touch this warp's pixel block into the warp's list (shared
+// addresses of their s0 entries, in list order).  s_ext = (ext_u, ext_v) per staged splat.  Returns the count.
+__device__ __forceinline__ uint32_t compact_touching(uint32_t sa0, uint32_t sa_ext, uint32_t ext_stride,
+                                                     uint32_t sa_list, int lim, int lane, float wcx, float wcy) {
+  uint32_t nw = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int chunk = 0; chunk < lim; chunk += 32) {
+    const int jt = chunk + lane;
+    bool touch = false;
+    if (jt < lim) {
+      const float2 c = lds_f2(sa0 + (uint32_t)jt * 16u);
+      const float2 e = lds_f2(sa_ext + (uint32_t)jt * ext_stride);
+      touch = splat_touches_block(c.x, c.y, e.x, e.y, wcx, wcy);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, touch);
+    if (touch) sts_u32(sa_list + (nw + __popc(m & lt)) * 4u, sa0 + (uint32_t)jt * 16u);
+    nw += __popc(m);
+  }
+  __syncwarp();
+  return nw;
 }
 
 __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams rp, const uint2* __restrict__ ranges,
@@ -75,25 +131,21 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
                                                                   float* __restrict__ image,
                                                                   float* __restrict__ final_T,
                                                                   uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 s_rec[3][kBlendThreads];      // [0] = rec0, [1] = rec1, [2] = rec2 of the staged batch
-  float4* const s0 = s_rec[0];
-  float4* const s1 = s_rec[1];
-  float4* const s2 = s_rec[2];
-  uint32_t sa0;   // opaque copy of the shared address: stops the compiler re-deriving it inside the visit loop
-  asm volatile("mov.u32 %0, %1;" : "=r"(sa0) : "r"((uint32_t)__cvta_generic_to_shared(s_rec)));
-  constexpr uint32_t kRecStride = kBlendThreads * 16;
+  __shared__ float4 s_rec[3][kBlendThreads];      // staged s0, s1, s2 = (g, b, ext_u, ext_v)
+  __shared__ uint32_t s_list[kBlendWarps][kBlendThreads];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sa0 = smem_addr(s_rec);
+  const uint32_t sa_list = smem_addr(&s_list[warp][0]);
   const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
+  const float amax = rp.alpha_max, chi2c = kExpScale * rp.chi2, cut_e = cutoff_exponent(rp);
   // T is the true transmittance (stored for the backward); Tl is its "live" copy that drops to 0 once
-  // T <= 5e-5 (render.py:387: a splat contributes iff the transmittance BEFORE it is > 5e-5), so a finished
-  // pixel needs no branch in the visit loop: its weights are simply zero.
+  // T <= 5e-5 (render.py:387: a splat contributes iff the transmittance BEFORE it is > 5e-5).
   float T = 1.f, Tl = pc.inside ? 1.f : 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  uint32_t last = 0;
-  // centre of this warp's 8x4 pixel block: a splat can only touch the block if its centre lies within
-  // (ext_u + 3.5, ext_v + 1.5) of it, where ext_* are the conservative half-extents of its footprint
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t last16 = 0;     // 16 * (1-based list position of the last contributor)
+  // centre of this warp's 8x4 pixel block
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
   for (uint32_t base = range.x; base < range.y; base += kBlendThreads) {
@@ -101,37 +153,35 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
     const uint32_t idx = base + threadIdx.x;
     if (idx < range.y) {
       const uint32_t id = vals[idx];
-      s0[threadIdx.x] = rec0[id];
-      s1[threadIdx.x] = rec1[id];
-      s2[threadIdx.x] = rec2[id];
+      const float4 a0 = rec0[id], a1 = rec1[id], a2 = rec2[id];
+      float4 t0, t1;
+      stage_splat(a0, a1, chi2c, cut_e, t0, t1);
+      s_rec[0][threadIdx.x] = t0;
+      s_rec[1][threadIdx.x] = t1;
+      s_rec[2][threadIdx.x] = make_float4(a1.w, a2.x, a2.y, a2.z);
     }
     __syncthreads();
     const int cnt = (int)min((uint32_t)kBlendThreads, range.y - base);
-    const uint32_t list_off = base - range.x + 1u;
-    for (int chunk = 0; chunk < cnt; chunk += 32) {
+    if (__all_sync(0xffffffffu, Tl == 0.f)) continue;     // this warp is finished (the barrier above still counts it)
+    const uint32_t nw = compact_touching(sa0, sa0 + 2 * kRecStride + 8u, 16u, sa_list, cnt, lane, wcx, wcy);
+    const uint32_t lastbase = (base - range.x + 1u) * 16u - sa0;
+    for (uint32_t i = 0; i < nw;) {
       if (__all_sync(0xffffffffu, Tl == 0.f)) break;
-      // each lane tests one splat of the chunk against the warp's pixel block
-      const int jt = chunk + lane;
-      bool touch = false;
-      if (jt < cnt) {
-        const float4 t2 = s2[jt];
-        touch = splat_touches_block(s0[jt], t2.y, t2.z, wcx, wcy);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, touch);
-      while (m) {
-        const int j = chunk + __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t aj = sa0 + (uint32_t)j * 16u;
+      const uint32_t iend = min(i + 8u, nw);
+      for (; i < iend; ++i) {
+        const uint32_t aj = lds_u32(sa_list + i * 4u);
         const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
-        float du, dv, gval, araw;
-        const float a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
-        if (a > 0.f && Tl > 0.f) {
+        const float du = pxf - r0.x, dv = pyf - r0.y;
+        const float e = splat_exponent(r0, r1, du, dv);
+        if (e >= r1.z && Tl > 0.f) {
+          const float a = fminf(ex2_ftz(e), amax);
           const float w = a * Tl;
-          C0 = fmaf(w, r1.z, C0);
-          C1 = fmaf(w, r1.w, C1);
-          C2 = fmaf(w, lds_f(aj + 2 * kRecStride), C2);
-          T = Tl * (1.f - a);
-          last = list_off + (uint32_t)j;
+          const float2 gb = lds_f2(aj + 2 * kRecStride);
+          C0 = fmaf(w, r1.w, C0);
+          C1 = fmaf(w, gb.x, C1);
+          C2 = fmaf(w, gb.y, C2);
+          T = fmaf(-a, Tl, Tl);
+          last16 = aj + lastbase;
           Tl = (T > 5e-5f) ? T : 0.f;
         }
       }
@@ -139,7 +189,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
   }
   if (pc.inside) {
     const size_t pix = (size_t)pc.py * rp.W + pc.px;
-    uint32_t flags = last;
+    uint32_t flags = last16 >> 4;
     if (C0 > 1.f) flags |= 1u << 29;
     if (C1 > 1.f) flags |= 1u << 30;
     if (C2 > 1.f) flags |= 1u << 31;
@@ -165,16 +215,13 @@ cudaError_t launch_blend_fwd(const RenderParams& rp, const void* ws, const Frame
 
 // ------------------------------------------------------------------------------------------------
 // Backward.  Walks each tile's list back to front from the last contributor, recomputing alpha and
-// recovering T_i = T_{i+1} / (1 - alpha_i).  Per-splat gradients (u, v, A11, A12, A22, opacity, r, g, b)
-// are reduced over the warp's 32 pixels with shuffles, accumulated per batch in shared memory, and
-// flushed with one global atomic per splat and component per tile.
+// recovering T_i = T_{i+1} / (1 - alpha_i).  Per (pixel, splat) it forms dL/dq (q = the Mahalanobis form)
+// and its first and second moments in the pixel offset, plus dL/dcolour:
+//     grad_acc row = (Mx, My, Mxx, Mxy, Myy, M0, r, g, b),  M0 = sum dL/dq, Mx = sum dL/dq*du, Mxy = sum dL/dq*du*dv, ...
+// from which the per-Gaussian pass (preprocess backward, splat_grad_from_moments) derives dL/d(u, v, conic,
+// opacity) - that algebra is per Gaussian, not per pixel.  The nine values are reduced over the warp's 32
+// pixels by recursive halving (12 shuffles) and added to grad_acc with one coalesced RED per (warp, splat).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams rp, const uint2* __restrict__ ranges,
                                                                   const uint32_t* __restrict__ vals,
                                                                   const float4* __restrict__ rec0,
@@ -184,26 +231,22 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
                                                                   const float* __restrict__ final_T,
                                                                   const uint32_t* __restrict__ n_contrib,
                                                                   float* __restrict__ grad_acc) {
-  __shared__ float4 s_rec[2][kBlendThreads];
-  float4* const s0 = s_rec[0];
-  float4* const s1 = s_rec[1];
-  uint32_t sa0;   // opaque copy of the shared address: stops the compiler re-deriving it inside the visit loop
-  asm volatile("mov.u32 %0, %1;" : "=r"(sa0) : "r"((uint32_t)__cvta_generic_to_shared(s_rec)));
-  constexpr uint32_t kRecStride = kBlendThreads * 16;
-  __shared__ float s_cb[kBlendThreads];
+  __shared__ float4 s_rec[3][kBlendThreads];      // staged s0, s1, s2 = (g, b, -, Gaussian id bits)
   __shared__ float2 s_ext[kBlendThreads];
-  __shared__ uint32_t s_id[kBlendThreads];
-  __shared__ float s_grad[kBlendThreads][9];
+  __shared__ uint32_t s_list[kBlendWarps][kBlendThreads];
   __shared__ uint32_t s_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sa0 = smem_addr(s_rec);
+  const uint32_t sa_ext = smem_addr(s_ext);
+  const uint32_t sa_list = smem_addr(&s_list[warp][0]);
   const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float amax = rp.alpha_max, chi2c = kExpScale * rp.chi2, cut_e = cutoff_exponent(rp);
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
-  // which of the nine totals this lane ends up holding after the halving reduction (-1: none):
-  // index within the half-warp's five values = 3*h8 + (h8 ? h4 : 2*h4 + h2 ...) - see the steps below
+  // which of the nine totals this lane ends up holding after the halving reduction (-1: none)
   int slot = -1;
   {
     const int h16 = (lane >> 4) & 1, h8 = (lane >> 3) & 1, h4 = (lane >> 2) & 1, h2 = (lane >> 1) & 1;
@@ -213,7 +256,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
     bool ok = !(h4 && h2);
     int x = h8 ? 3 + y : y;              // index among x0..x4 ; h8=1 has only x3,x4
     if (h8 && y >= 2) ok = false;
-    int v = h16 ? 5 + x : x;             // 0..4 = u,v,A11,A12,A22 ; 5..8 = op,r,g,b ; 9 = padding
+    int v = h16 ? 5 + x : x;             // 0..4 = Mx,My,Mxx,Mxy,Myy ; 5..8 = M0,r,g,b ; 9 = padding
     if (v >= 9) ok = false;
     if (ok && (lane & 1) == 0) slot = v;
   }
@@ -237,118 +280,98 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
   const uint32_t max_last = s_max;
   if (max_last == 0) return;
   float rc0 = 0.f, rc1 = 0.f, rc2 = 0.f;   // colour accumulated behind the current splat, normalised by T_{i+1}
+  float* const my_acc = grad_acc + (slot >= 0 ? slot : 0);
   const int nb = (int)((max_last + kBlendThreads - 1) / kBlendThreads);
   for (int b = nb - 1; b >= 0; --b) {
     const uint32_t boff = (uint32_t)b * kBlendThreads;
     const int cnt = (int)min((uint32_t)kBlendThreads, max_last - boff);
+    if (b != nb - 1) __syncthreads();      // every warp is done with the previous batch
     if ((int)threadIdx.x < cnt) {
       const uint32_t id = vals[range.x + boff + threadIdx.x];
-      s_id[threadIdx.x] = id;
-      s0[threadIdx.x] = rec0[id];
-      s1[threadIdx.x] = rec1[id];
-      const float4 t2 = rec2[id];
-      s_cb[threadIdx.x] = t2.x;
-      s_ext[threadIdx.x] = make_float2(t2.y, t2.z);
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s_grad[threadIdx.x][k] = 0.f;
-    __syncthreads();
-    for (int chunk = ((cnt - 1) >> 5) << 5; chunk >= 0; chunk -= 32) {
-      if (boff + (uint32_t)chunk >= wlast) continue;        // nobody in this warp consumed these splats
-      const int jt = chunk + lane;
-      bool touch = false;
-      if (jt < cnt) {
-        const float2 te = s_ext[jt];
-        touch = splat_touches_block(s0[jt], te.x, te.y, wcx, wcy);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, touch);
-      while (m) {
-        const int bit = 31 - __clz(m);
-        m &= ~(1u << bit);
-        const int j = chunk + bit;
-        const bool active = (boff + (uint32_t)j) < last;
-        float a = 0.f, du = 0.f, dv = 0.f, gval = 0.f, araw = 0.f;
-        const uint32_t aj = sa0 + (uint32_t)j * 16u;
-        const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
-        if (active) a = splat_alpha(r0, r1, pxf, pyf, rp, du, dv, gval, araw);
-        const bool hit = a > 0.f;
-        if (!__any_sync(0xffffffffu, hit)) continue;
-        float v_u = 0.f, v_v = 0.f, v_a11 = 0.f, v_a12 = 0.f, v_a22 = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
-        if (hit) {
-          const float cb = s_cb[j];
-          const float Ti = T / (1.f - a);
-          T = Ti;
-          const float w = a * Ti;
-          v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
-          const float dalpha = Ti * (g0 * (r1.z - rc0) + g1 * (r1.w - rc1) + g2 * (cb - rc2));
-          rc0 = fmaf(a, r1.z - rc0, rc0);
-          rc1 = fmaf(a, r1.w - rc1, rc1);
-          rc2 = fmaf(a, cb - rc2, rc2);
-          const float draw = (araw <= rp.alpha_max) ? dalpha : 0.f;   // clamp_max passes on <=
-          v_op = draw * gval;
-          const float dq = -0.5f * araw * draw;                       // d/dq of op*exp(-q/2)
-          const float B2 = r0.w;            // 2*A12
-          v_u = -dq * (2.f * r0.z * du + B2 * dv);
-          v_v = -dq * (2.f * r1.x * dv + B2 * du);
-          v_a11 = dq * du * du;
-          v_a12 = dq * 2.f * du * dv;
-          v_a22 = dq * dv * dv;
-        }
-        // Reduce the 9 per-pixel values over the warp by recursive halving: at every step a lane keeps
-        // one half of its values and trades the other half with its partner, so 12 shuffles (instead of
-        // 45) leave each total in one lane pair; those lanes then add into shared memory in parallel.
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-        float a0, a1, a2, a3, a4;
-        {
-          const float k0 = h16 ? v_op : v_u,   t0 = h16 ? v_u : v_op;
-          const float k1 = h16 ? v_r : v_v,    t1 = h16 ? v_v : v_r;
-          const float k2 = h16 ? v_g : v_a11,  t2 = h16 ? v_a11 : v_g;
-          const float k3 = h16 ? v_b : v_a12,  t3 = h16 ? v_a12 : v_b;
-          const float k4 = h16 ? 0.f : v_a22,  t4 = h16 ? v_a22 : 0.f;
-          a0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
-          a1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
-          a2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
-          a3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
-          a4 = k4 + __shfl_xor_sync(0xffffffffu, t4, 16);
-        }
-        // low half-warp: (u, v, A11, A12, A22)   high half-warp: (op, r, g, b, 0)
-        float b0, b1, b2;
-        {
-          const float k0 = h8 ? a3 : a0, t0 = h8 ? a0 : a3;
-          const float k1 = h8 ? a4 : a1, t1 = h8 ? a1 : a4;
-          const float k2 = h8 ? 0.f : a2, t2 = h8 ? a2 : 0.f;
-          b0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
-          b1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
-          b2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 8);
-        }
-        // h8 = 0: (x0, x1, x2)   h8 = 1: (x3, x4, 0)   of the half-warp's five values
-        float c0, c1;
-        {
-          const float k0 = h4 ? b2 : b0, t0 = h4 ? b0 : b2;
-          const float k1 = h4 ? 0.f : b1, t1 = h4 ? b1 : 0.f;
-          c0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
-          c1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
-        }
-        // h4 = 0: (y0, y1)   h4 = 1: (y2, 0)
-        float d0;
-        {
-          const float k0 = h2 ? c1 : c0, t0 = h2 ? c0 : c1;
-          d0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2);
-        }
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-        if (slot >= 0) atomicAdd(&s_grad[j][slot], d0);
-      }
+      const float4 a0 = rec0[id], a1 = rec1[id], a2 = rec2[id];
+      float4 t0, t1;
+      stage_splat(a0, a1, chi2c, cut_e, t0, t1);
+      s_rec[0][threadIdx.x] = t0;
+      s_rec[1][threadIdx.x] = t1;
+      s_rec[2][threadIdx.x] = make_float4(a1.w, a2.x, 0.f, __uint_as_float(id));
+      s_ext[threadIdx.x] = make_float2(a2.y, a2.z);
     }
     __syncthreads();
-    if ((int)threadIdx.x < cnt) {
-      float* dst = grad_acc + (size_t)s_id[threadIdx.x] * 12;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float v = s_grad[threadIdx.x][k];
-        if (v != 0.f) atomicAdd(dst + k, v);
+    if (wlast <= boff) continue;                                     // nobody in this warp consumed these splats
+    const int lim = (int)min((uint32_t)cnt, wlast - boff);
+    const uint32_t nw = compact_touching(sa0, sa_ext, 8u, sa_list, lim, lane, wcx, wcy);
+    // splat j of this batch was consumed by this pixel iff boff + j < last  <=>  its s0 address < last_addr
+    const int last_addr = (int)sa0 + ((int)last - (int)boff) * 16;
+    for (uint32_t i = nw; i-- > 0;) {
+      const uint32_t aj = lds_u32(sa_list + i * 4u);
+      const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
+      const float du = pxf - r0.x, dv = pyf - r0.y;
+      const float e = splat_exponent(r0, r1, du, dv);
+      const bool hit = ((int)aj < last_addr) && (e >= r1.z);
+      if (!__any_sync(0xffffffffu, hit)) continue;
+      const float4 r2 = lds_f4(aj + 2 * kRecStride);
+      float mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f, m0 = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+      if (hit) {
+        const float araw = ex2_ftz(e);
+        const float a = fminf(araw, amax);
+        const float Ti = __fdividef(T, 1.f - a);
+        T = Ti;
+        const float w = a * Ti;
+        v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
+        const float d0c = r1.w - rc0, d1c = r2.x - rc1, d2c = r2.y - rc2;
+        const float dalpha = Ti * fmaf(g2, d2c, fmaf(g1, d1c, g0 * d0c));
+        rc0 = fmaf(a, d0c, rc0);
+        rc1 = fmaf(a, d1c, rc1);
+        rc2 = fmaf(a, d2c, rc2);
+        const float draw = (araw <= amax) ? dalpha : 0.f;            // clamp_max passes on <=
+        m0 = -0.5f * araw * draw;                                    // dL/dq: d/dq of op*exp(-q/2)
+        mx = m0 * du; my = m0 * dv;
+        mxx = mx * du; mxy = mx * dv; myy = my * dv;
       }
+      // Reduce the 9 per-pixel values over the warp by recursive halving: at every step a lane keeps
+      // one half of its values and trades the other half with its partner, so 12 shuffles (instead of
+      // 45) leave each total in one lane pair; those lanes then issue one RED.
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+      float a0, a1, a2, a3, a4;
+      {
+        const float k0 = h16 ? m0 : mx,    t0 = h16 ? mx : m0;
+        const float k1 = h16 ? v_r : my,   t1 = h16 ? my : v_r;
+        const float k2 = h16 ? v_g : mxx,  t2 = h16 ? mxx : v_g;
+        const float k3 = h16 ? v_b : mxy,  t3 = h16 ? mxy : v_b;
+        const float k4 = h16 ? 0.f : myy,  t4 = h16 ? myy : 0.f;
+        a0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+        a1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
+        a2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
+        a3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
+        a4 = k4 + __shfl_xor_sync(0xffffffffu, t4, 16);
+      }
+      // low half-warp: (Mx, My, Mxx, Mxy, Myy)   high half-warp: (M0, r, g, b, 0)
+      float b0, b1, b2;
+      {
+        const float k0 = h8 ? a3 : a0, t0 = h8 ? a0 : a3;
+        const float k1 = h8 ? a4 : a1, t1 = h8 ? a1 : a4;
+        const float k2 = h8 ? 0.f : a2, t2 = h8 ? a2 : 0.f;
+        b0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
+        b1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
+        b2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 8);
+      }
+      // h8 = 0: (x0, x1, x2)   h8 = 1: (x3, x4, 0)   of the half-warp's five values
+      float c0, c1;
+      {
+        const float k0 = h4 ? b2 : b0, t0 = h4 ? b0 : b2;
+        const float k1 = h4 ? 0.f : b1, t1 = h4 ? b1 : 0.f;
+        c0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
+        c1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
+      }
+      // h4 = 0: (y0, y1)   h4 = 1: (y2, 0)
+      float d0;
+      {
+        const float k0 = h2 ? c1 : c0, t0 = h2 ? c0 : c1;
+        d0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2);
+      }
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+      if (slot >= 0) atomicAdd(my_acc + (size_t)__float_as_uint(r2.w) * 12, d0);
     }
-    __syncthreads();
   }
 }
 

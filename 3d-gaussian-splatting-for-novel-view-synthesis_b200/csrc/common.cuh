@@ -43,7 +43,7 @@ struct FrameLayout {
   size_t order;           // u32[n]  Gaussian ids in depth order (sorted values)
   size_t order_alt;       // u32[n]
   size_t offsets;         // u32[n]  exclusive scan of super_touched in depth order
-  size_t grad_acc;        // float[n*12] blend-backward accumulators (u,v,A11,A12,A22,op,r,g,b,+pad)
+  size_t grad_acc;        // float[n*12] blend-backward accumulators (Mx,My,Mxx,Mxy,Myy,M0,r,g,b,+pad): moments of dL/dq
   size_t ranges;          // uint2[tiles] (start,end) per tile
   size_t tile_count;      // u32[supertiles*4*32] entries per tile and list quarter, supertile-major
   size_t final_T;         // float[P]

@@ -370,6 +370,22 @@ GS_HD bool project_gaussian(const float p[3], const Cov3& S, float opacity_raw, 
 // Gradients that arrive from the blend backward, per Gaussian.
 struct SplatGrad { float u, v, A11, A12, A22, op; };
 
+// The blend backward accumulates, per Gaussian, the moments of dL/dq (q = the Mahalanobis form of
+// render.py:362) over the pixels the splat contributed to, with du = px - u, dv = py - v:
+//   M0 = sum dL/dq,  Mx = sum dL/dq du,  My = sum dL/dq dv,  Mxx = sum dL/dq du^2,  Mxy = sum dL/dq du dv,  Myy = ...
+// q = A11 du^2 + 2 A12 du dv + A22 dv^2 and alpha_raw = op exp(-q/2) (so dL/dop = -2 dL/dq / op pixel by pixel) give
+GS_HD SplatGrad splat_grad_from_moments(const Projection& o, float Mx, float My, float Mxx, float Mxy, float Myy,
+                                        float M0) {
+  SplatGrad g;
+  g.u = -(2.f * o.A11 * Mx + 2.f * o.A12 * My);
+  g.v = -(2.f * o.A22 * My + 2.f * o.A12 * Mx);
+  g.A11 = Mxx;
+  g.A12 = 2.f * Mxy;
+  g.A22 = Myy;
+  g.op = -2.f * M0 / o.op;
+  return g;
+}
+
 // Backward of project_gaussian.  `o` is the recomputed forward.  Outputs: g_p (adds the projection
 // part), G (dL/dSigma, full symmetric row-major 3x3), g_opacity_raw.
 GS_HD void project_backward(const float p[3], const Cov3& S, const Pose& ps, const RenderParams& rp,

@@ -389,8 +389,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_bwd_kernel(GaussIn g, Ga
       const float4 a0 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i];
       const float4 a1 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i + 1];
       const float4 a2 = reinterpret_cast<const float4*>(f.grad_acc)[3 * (size_t)i + 2];
-      SplatGrad sg;
-      sg.u = a0.x; sg.v = a0.y; sg.A11 = a0.z; sg.A12 = a0.w; sg.A22 = a1.x; sg.op = a1.y;
+      const SplatGrad sg = splat_grad_from_moments(o, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y);
       const float g_rgb[3] = {a1.z, a1.w, a2.x};
       float G[9];
       project_backward(p, S, ps, rp, o, sg, gp, G, g_op);
@@ -544,8 +543,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_bwd_tma_kernel(GaussIn g
         const float4 a0 = reinterpret_cast<const float4*>(st.acc)[3 * tid];
         const float4 a1 = reinterpret_cast<const float4*>(st.acc)[3 * tid + 1];
         const float4 a2 = reinterpret_cast<const float4*>(st.acc)[3 * tid + 2];
-        SplatGrad sg;
-        sg.u = a0.x; sg.v = a0.y; sg.A11 = a0.z; sg.A12 = a0.w; sg.A22 = a1.x; sg.op = a1.y;
+        const SplatGrad sg = splat_grad_from_moments(o, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y);
         const float g_rgb[3] = {a1.z, a1.w, a2.x};
         float G[9];
         project_backward(p, S, ps, rp, o, sg, gp, G, g_op);

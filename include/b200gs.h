@@ -135,6 +135,16 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
                             void* isect_ws, size_t isect_bytes, uint32_t isect_capacity,
                             float* image_out, b200gs_frame_stats* stats_host, void* stream);
 
+/* Same call; additionally records `stats_event` (a cudaEvent_t, may be NULL) on `stream` right after the
+ * binning scan, i.e. as soon as every counter of the frame statistics (I, V, pair count, overflow) is
+ * final and on its way to `stats_host`.  A host that sizes the lists speculatively waits for this event
+ * only - not for the end of the frame - to learn whether they fitted, and can queue the next frame while
+ * the sort, split and blend kernels of this one are still running. */
+int b200gs_render_rasterize_ev(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes,
+                               void* isect_ws, size_t isect_bytes, uint32_t isect_capacity,
+                               float* image_out, b200gs_frame_stats* stats_host, void* stats_event,
+                               void* stream);
+
 /* Backward of project+rasterize (scripts/train.py:530): grad_image [H,W,3] -> b200gs_grads.
  * Needs the frame/isect workspaces exactly as the forward left them. */
 int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws,

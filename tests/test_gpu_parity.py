@@ -353,3 +353,27 @@ def test_live_oracle_forward_backward(gs, n, W, H, ls, view, seed):
     for k in PARAMS:
         err = grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy())
         assert err <= 3 * GRAD_TOL if n_bad else err <= GRAD_TOL, (k, err, n_bad)
+
+
+def test_speculative_capacity_overflow_is_redone_with_exact_buffers(gs):
+    """speculative mode sizes the lists from a high-water mark and waits only for the frame's counters;
+    a frame that does not fit must be rasterized again and give the sync-mode picture."""
+    from b200gs import ops
+    from oracle import gs_oracle as O
+    sc = {k: v.cuda() for k, v in O.make_scene(30_000, seed=5, log_scale=-3.5).items()}
+    cam = O.make_camera(320, 200)
+    cam["c2w"] = cam["c2w"].cuda()
+    ref, fr = _render_frame(gs, sc, cam, mode="sync")
+    fr.refresh_stats()
+    assert fr.n_isect > 4000
+    dev = sc["pos"].device.index
+    saved = ops._high_water.get(dev, 0)
+    try:
+        ops._high_water[dev] = 1000                      # far too small for this frame
+        img, fr2 = _render_frame(gs, sc, cam, mode="speculative")
+        assert torch.equal(img, ref) and fr2.n_isect == fr.n_isect and not fr2.overflow
+        assert ops._high_water[dev] >= fr.n_isect        # grown: the next frame fits without a redo
+        img3, _ = _render_frame(gs, sc, cam, mode="speculative")
+        assert torch.equal(img3, ref)
+    finally:
+        ops._high_water[dev] = max(saved, ops._high_water.get(dev, 0))
