@@ -126,7 +126,8 @@ SortedSuper sorted_super(void* isect_ws, const gs::IsectLayout& IL, int n_super_
 
 // --- debug export kernels -------------------------------------------------------------------------
 __global__ void export_kernel(int n, const float4* rec0, const float4* rec1, const float4* rec2,
-                              const uint32_t* depth_key, const uint2* rect, const uint32_t* tiles, float* xy,
+                              const uint32_t* depth_key, const uint2* rect, const uint32_t* radius_in,
+                              const uint32_t* super_touched, float* xy,
                               float* depth, float* conic, float* opacity, float* color, int32_t* radius,
                               int32_t* rect_out, int32_t* tiles_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,18 +135,21 @@ __global__ void export_kernel(int n, const float4* rec0, const float4* rec1, con
   const bool vis = depth_key[i] != gs::kCulledKey;
   const float4 a = vis ? rec0[i] : make_float4(0, 0, 0, 0), b = vis ? rec1[i] : make_float4(0, 0, 0, 0),
                c = vis ? rec2[i] : make_float4(0, 0, 0, 0);
+  const float inv = 1.f / gs::kBlendExpScale;     // the records hold the conic scaled by -log2(e)/2
   if (xy) { xy[2 * i] = a.x; xy[2 * i + 1] = a.y; }
   if (depth) depth[i] = vis ? __uint_as_float(depth_key[i]) : -1.f;
-  if (conic) { conic[3 * i] = a.z; conic[3 * i + 1] = 0.5f * a.w; conic[3 * i + 2] = b.x; }   // rec0.w = 2*A12
-  if (opacity) opacity[i] = b.y;
-  if (color) { color[3 * i] = b.z; color[3 * i + 1] = b.w; color[3 * i + 2] = c.x; }
-  if (radius) radius[i] = vis ? (int32_t)c.w : 0;
+  if (conic) { conic[3 * i] = a.z * inv; conic[3 * i + 1] = 0.5f * a.w * inv; conic[3 * i + 2] = b.x * inv; }
+  if (opacity) opacity[i] = vis ? exp2f(b.y) : 0.f;
+  if (color) { color[3 * i] = b.w; color[3 * i + 1] = c.x; color[3 * i + 2] = c.y; }
+  if (radius) radius[i] = vis ? (int32_t)radius_in[i] : 0;
+  const uint2 r = vis ? rect[i] : make_uint2(0, 0);
   if (rect_out) {
-    const uint2 r = vis ? rect[i] : make_uint2(0, 0);
     rect_out[4 * i] = r.x & 0xFFFF; rect_out[4 * i + 1] = r.x >> 16;
     rect_out[4 * i + 2] = r.y & 0xFFFF; rect_out[4 * i + 3] = r.y >> 16;
   }
-  if (tiles_out) tiles_out[i] = vis ? (int32_t)tiles[i] : -1;
+  // tiles touched = area of the (band-clipped) tile rect; 0 when the band clipping left nothing
+  if (tiles_out)
+    tiles_out[i] = !vis ? -1 : (super_touched[i] ? (int32_t)(((r.x >> 16) - (r.x & 0xFFFF) + 1) * ((r.y >> 16) - (r.y & 0xFFFF) + 1)) : 0);
 }
 
 __global__ void copy_u32_kernel(const uint32_t* src, int32_t* dst, uint32_t n) {
@@ -415,7 +419,7 @@ int b200gs_debug_export(int32_t n, const void* frame_ws, size_t frame_bytes, int
   export_kernel<<<gs::ceil_div(n, 256), 256, 0, s>>>(
       n, gs::ws_ptr<float4>(frame_ws, L.rec0), gs::ws_ptr<float4>(frame_ws, L.rec1), gs::ws_ptr<float4>(frame_ws, L.rec2),
       gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), gs::ws_ptr<uint2>(frame_ws, L.rect),
-      gs::ws_ptr<uint32_t>(frame_ws, L.tiles_touched), xy, depth, conic, opacity, color, radius, rect, tiles_touched);
+      gs::ws_ptr<uint32_t>(frame_ws, L.radius), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched), xy, depth, conic, opacity, color, radius, rect, tiles_touched);
   CU(cudaGetLastError());
   if (depth_order) {
     copy_u32_kernel<<<gs::ceil_div(n, 256), 256, 0, s>>>(gs::ws_ptr<uint32_t>(frame_ws, L.order), depth_order, (uint32_t)n);

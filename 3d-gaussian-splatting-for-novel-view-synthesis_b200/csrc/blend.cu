@@ -8,11 +8,14 @@
 // as soon as every pixel's transmittance is <= 5e-5 (render.py:387: a splat contributes iff T *before* it
 // is > 5e-5).
 //
-// Staged form of a splat (computed once per (tile, splat) while staging, so the per-(pixel, splat) visit
-// is as short as possible): with c = -log2(e)/2 the exponent of  alpha_raw = op * exp(-q/2) = 2^e  is
+// The splat records arrive from preprocess already in the form the per-(pixel, splat) visit wants
+// (write_splat_record, preprocess.cu): with c = -log2(e)/2 the exponent of  alpha_raw = op * exp(-q/2) = 2^e  is
 //     e = c*A11*du^2 + c*2*A12*du*dv + c*A22*dv^2 + log2(op)
 // and both gates of render.py:362-374 collapse into one compare:
 //     q <= chi2  and  min(alpha_raw, alpha_max) >= alpha_cutoff   <=>   e >= max(c*chi2 + log2(op), log2(alpha_cutoff)).
+// The list entries (Gaussian ids) of the next batch are fetched while the current one is blended, so a batch
+// costs one global round trip, not two.  (A cp.async double-buffered staging was measured and dropped: the
+// extra shared memory shrinks L1 and the kernel gets slower - 262 us -> 360 us on the headline frame.)
 //
 // Roofline: FP32 issue + MUFU.EX2; HBM traffic is the 36-B record gather per
 // intersection plus 12 B/pixel of output.
@@ -61,7 +64,6 @@ __device__ __forceinline__ float ex2_ftz(float x) {   // arguments are >= log2(a
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
 // Shared address of a __shared__ object as an opaque register value: stops the compiler from re-deriving
 // the shared window base (S2UR/ULEA chains) inside the visit loops.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
@@ -70,53 +72,29 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return a;
 }
 
-// log2 of the alpha cutoff as the lower bound of the exponent; +inf when nothing can pass
-// (alpha_cutoff > alpha_max), -inf / NaN-free "everything passes" for a non-positive cutoff.
-__device__ __forceinline__ float cutoff_exponent(const RenderParams& rp) {
-  if (!(rp.alpha_cutoff <= rp.alpha_max)) return __int_as_float(0x7f800000);
-  if (!(rp.alpha_cutoff > 0.f)) return __int_as_float(0xff800000);
-  return __log2f(rp.alpha_cutoff);
-}
-
-// rec0 = (u, v, A11, 2*A12), rec1 = (A22, op, r, g)  ->  s0 = (u, v, c*A11, c*2*A12), s1 = (c*A22, log2 op, gate, r)
-__device__ __forceinline__ void stage_splat(const float4& a0, const float4& a1, float chi2c, float cut_e,
-                                            float4& s0, float4& s1) {
-  const float lop = __log2f(a1.y);
-  s0 = make_float4(a0.x, a0.y, kExpScale * a0.z, kExpScale * a0.w);
-  s1 = make_float4(kExpScale * a1.x, lop, fmaxf(chi2c + lop, cut_e), a1.z);
-}
-
-// exponent e of alpha_raw = 2^e at pixel offset (du, dv) from the splat centre
+// exponent e of alpha_raw = 2^e at pixel offset (du, dv) from the splat centre (record layout: preprocess.cu)
 __device__ __forceinline__ float splat_exponent(const float4& s0, const float4& s1, float du, float dv) {
   const float t1 = fmaf(s0.z, du, s0.w * dv);
   const float t2 = fmaf(s1.x * dv, dv, s1.y);
   return fmaf(du, t1, t2);
 }
 
-// Can this splat contribute to any pixel of the warp's 8x4 block (centre wcx, wcy)?  Bounding box of the
-// effective ellipse { q <= min(chi2, 2 ln(opacity / alpha_cutoff)) } (extents precomputed per splat,
-// conservative) against the block.  (An exact ellipse-vs-rectangle test was measured: it costs more than
-// the few extra visits it removes.)  One lane evaluates one splat.
-__device__ __forceinline__ bool splat_touches_block(float u, float v, float eu, float ev, float wcx, float wcy) {
-  return (fabsf(u - wcx) <= eu + 3.5f) && (fabsf(v - wcy) <= ev + 1.5f);
-}
-
-// Compacts the staged splats [0, lim) that can touch this warp's pixel block into the warp's list (shared
-// addresses of their s0 entries, in list order).  s_ext = (ext_u, ext_v) per staged splat.  Returns the count.
-__device__ __forceinline__ uint32_t compact_touching(uint32_t sa0, uint32_t sa_ext, uint32_t ext_stride,
-                                                     uint32_t sa_list, int lim, int lane, float wcx, float wcy) {
+// Compacts the staged splats [0, lim) of the buffer at `buf` that can touch this warp's 8x4 pixel block (centre
+// wcx, wcy) into the warp's list (shared addresses of their rec0 entries, in list order); one lane tests one
+// splat: bounding box of the effective ellipse { q <= min(chi2, 2 ln(opacity / alpha_cutoff)) } (half-extents
+// precomputed per splat, conservative) against the block.  (An exact ellipse-vs-rectangle test was measured:
+// it costs more than the few extra visits it removes.)  Returns the number of entries.
+__device__ __forceinline__ uint32_t compact_touching(uint32_t buf, uint32_t sa_list, int lim, int lane, float wcx,
+                                                     float wcy) {
   uint32_t nw = 0;
   const uint32_t lt = (1u << lane) - 1u;
-  for (int chunk = 0; chunk < lim; chunk += 32) {
-    const int jt = chunk + lane;
-    bool touch = false;
-    if (jt < lim) {
-      const float2 c = lds_f2(sa0 + (uint32_t)jt * 16u);
-      const float2 e = lds_f2(sa_ext + (uint32_t)jt * ext_stride);
-      touch = splat_touches_block(c.x, c.y, e.x, e.y, wcx, wcy);
-    }
+  uint32_t a = buf + (uint32_t)lane * 16u;
+  for (int jt = lane; jt - lane < lim; jt += 32, a += 512u) {
+    const float2 c = lds_f2(a);                                   // (u, v); slots >= lim hold stale data: masked below
+    const float2 e = lds_f2(a + 2 * kRecStride + 8u);             // (ext_u, ext_v)
+    const bool touch = (jt < lim) & (fabsf(c.x - wcx) <= e.x + 3.5f) & (fabsf(c.y - wcy) <= e.y + 1.5f);
     const unsigned m = __ballot_sync(0xffffffffu, touch);
-    if (touch) sts_u32(sa_list + (nw + __popc(m & lt)) * 4u, sa0 + (uint32_t)jt * 16u);
+    if (touch) sts_u32(sa_list + (nw + __popc(m & lt)) * 4u, a);
     nw += __popc(m);
   }
   __syncwarp();
@@ -131,7 +109,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
                                                                   float* __restrict__ image,
                                                                   float* __restrict__ final_T,
                                                                   uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 s_rec[3][kBlendThreads];      // staged s0, s1, s2 = (g, b, ext_u, ext_v)
+  __shared__ float4 s_rec[3][kBlendThreads];
   __shared__ uint32_t s_list[kBlendWarps][kBlendThreads];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sa0 = smem_addr(s_rec);
@@ -140,34 +118,32 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
-  const float amax = rp.alpha_max, chi2c = kExpScale * rp.chi2, cut_e = cutoff_exponent(rp);
-  // T is the true transmittance (stored for the backward); Tl is its "live" copy that drops to 0 once
-  // T <= 5e-5 (render.py:387: a splat contributes iff the transmittance BEFORE it is > 5e-5).
+  const float amax = rp.alpha_max;
   float T = 1.f, Tl = pc.inside ? 1.f : 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  uint32_t last16 = 0;     // 16 * (1-based list position of the last contributor)
-  // centre of this warp's 8x4 pixel block
+  uint32_t last16 = 0;
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
+  uint32_t idx = range.x + threadIdx.x;
+  uint32_t id_cur = (idx < range.y) ? vals[idx] : 0u;
   for (uint32_t base = range.x; base < range.y; base += kBlendThreads) {
     if (__syncthreads_count(Tl == 0.f) == kBlendThreads) break;
-    const uint32_t idx = base + threadIdx.x;
     if (idx < range.y) {
-      const uint32_t id = vals[idx];
-      const float4 a0 = rec0[id], a1 = rec1[id], a2 = rec2[id];
-      float4 t0, t1;
-      stage_splat(a0, a1, chi2c, cut_e, t0, t1);
-      s_rec[0][threadIdx.x] = t0;
-      s_rec[1][threadIdx.x] = t1;
-      s_rec[2][threadIdx.x] = make_float4(a1.w, a2.x, a2.y, a2.z);
+      const float4 a0 = rec0[id_cur], a1 = rec1[id_cur], a2 = rec2[id_cur];
+      s_rec[0][threadIdx.x] = a0;
+      s_rec[1][threadIdx.x] = a1;
+      s_rec[2][threadIdx.x] = a2;
     }
+    idx += kBlendThreads;
+    id_cur = (idx < range.y) ? vals[idx] : 0u;
     __syncthreads();
     const int cnt = (int)min((uint32_t)kBlendThreads, range.y - base);
-    if (__all_sync(0xffffffffu, Tl == 0.f)) continue;     // this warp is finished (the barrier above still counts it)
-    const uint32_t nw = compact_touching(sa0, sa0 + 2 * kRecStride + 8u, 16u, sa_list, cnt, lane, wcx, wcy);
+    if (__all_sync(0xffffffffu, Tl == 0.f)) continue;
+    const uint32_t nw = compact_touching(sa0, sa_list, cnt, lane, wcx, wcy);
     const uint32_t lastbase = (base - range.x + 1u) * 16u - sa0;
     for (uint32_t i = 0; i < nw;) {
       if (__all_sync(0xffffffffu, Tl == 0.f)) break;
-      const uint32_t iend = min(i + 8u, nw);
+      const uint32_t iend = min(i + 32u, nw);
+#pragma unroll 4
       for (; i < iend; ++i) {
         const uint32_t aj = lds_u32(sa_list + i * 4u);
         const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
@@ -231,19 +207,19 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
                                                                   const float* __restrict__ final_T,
                                                                   const uint32_t* __restrict__ n_contrib,
                                                                   float* __restrict__ grad_acc) {
-  __shared__ float4 s_rec[3][kBlendThreads];      // staged s0, s1, s2 = (g, b, -, Gaussian id bits)
-  __shared__ float2 s_ext[kBlendThreads];
+  __shared__ float4 s_rec[3][kBlendThreads];         // staged records
+  __shared__ uint32_t s_id[kBlendThreads];           // Gaussian ids of the staged splats
   __shared__ uint32_t s_list[kBlendWarps][kBlendThreads];
   __shared__ uint32_t s_max;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t sa0 = smem_addr(s_rec);
-  const uint32_t sa_ext = smem_addr(s_ext);
+  const uint32_t sa_id = smem_addr(s_id);
   const uint32_t sa_list = smem_addr(&s_list[warp][0]);
   const int tile_x = blockIdx.x, tile_y = rp.row_begin + blockIdx.y;
   const uint2 range = ranges[tile_y * rp.tiles_x + tile_x];
   const PixelCoord pc = pixel_of_thread(rp, tile_x, tile_y);
   const float pxf = (float)pc.px, pyf = (float)pc.py;
-  const float amax = rp.alpha_max, chi2c = kExpScale * rp.chi2, cut_e = cutoff_exponent(rp);
+  const float amax = rp.alpha_max;
   const float wcx = (float)(tile_x * kTile + ((warp & 1) << 3)) + 3.5f;
   const float wcy = (float)(tile_y * kTile + ((warp >> 1) << 2)) + 1.5f;
   // which of the nine totals this lane ends up holding after the halving reduction (-1: none)
@@ -282,95 +258,102 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(RenderParams r
   float rc0 = 0.f, rc1 = 0.f, rc2 = 0.f;   // colour accumulated behind the current splat, normalised by T_{i+1}
   float* const my_acc = grad_acc + (slot >= 0 ? slot : 0);
   const int nb = (int)((max_last + kBlendThreads - 1) / kBlendThreads);
+  // Batches back to front; the list entries (Gaussian ids) are fetched one batch ahead.
+  const uint32_t* const list = vals + range.x;
+  uint32_t pos = (uint32_t)(nb - 1) * kBlendThreads + threadIdx.x;       // list position this thread stages
+  uint32_t id_cur = (pos < max_last) ? list[pos] : 0u;
+  const uint32_t buf = sa0;
   for (int b = nb - 1; b >= 0; --b) {
     const uint32_t boff = (uint32_t)b * kBlendThreads;
     const int cnt = (int)min((uint32_t)kBlendThreads, max_last - boff);
     if (b != nb - 1) __syncthreads();      // every warp is done with the previous batch
     if ((int)threadIdx.x < cnt) {
-      const uint32_t id = vals[range.x + boff + threadIdx.x];
-      const float4 a0 = rec0[id], a1 = rec1[id], a2 = rec2[id];
-      float4 t0, t1;
-      stage_splat(a0, a1, chi2c, cut_e, t0, t1);
-      s_rec[0][threadIdx.x] = t0;
-      s_rec[1][threadIdx.x] = t1;
-      s_rec[2][threadIdx.x] = make_float4(a1.w, a2.x, 0.f, __uint_as_float(id));
-      s_ext[threadIdx.x] = make_float2(a2.y, a2.z);
+      const float4 a0 = rec0[id_cur], a1 = rec1[id_cur], a2 = rec2[id_cur];
+      s_rec[0][threadIdx.x] = a0;
+      s_rec[1][threadIdx.x] = a1;
+      s_rec[2][threadIdx.x] = a2;
+      s_id[threadIdx.x] = id_cur;
     }
+    if (b >= 1) id_cur = list[boff - kBlendThreads + threadIdx.x];
     __syncthreads();
-    if (wlast <= boff) continue;                                     // nobody in this warp consumed these splats
-    const int lim = (int)min((uint32_t)cnt, wlast - boff);
-    const uint32_t nw = compact_touching(sa0, sa_ext, 8u, sa_list, lim, lane, wcx, wcy);
-    // splat j of this batch was consumed by this pixel iff boff + j < last  <=>  its s0 address < last_addr
-    const int last_addr = (int)sa0 + ((int)last - (int)boff) * 16;
-    for (uint32_t i = nw; i-- > 0;) {
-      const uint32_t aj = lds_u32(sa_list + i * 4u);
-      const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
-      const float du = pxf - r0.x, dv = pyf - r0.y;
-      const float e = splat_exponent(r0, r1, du, dv);
-      const bool hit = ((int)aj < last_addr) && (e >= r1.z);
-      if (!__any_sync(0xffffffffu, hit)) continue;
-      const float4 r2 = lds_f4(aj + 2 * kRecStride);
-      float mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f, m0 = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
-      if (hit) {
-        const float araw = ex2_ftz(e);
-        const float a = fminf(araw, amax);
-        const float Ti = __fdividef(T, 1.f - a);
-        T = Ti;
-        const float w = a * Ti;
-        v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
-        const float d0c = r1.w - rc0, d1c = r2.x - rc1, d2c = r2.y - rc2;
-        const float dalpha = Ti * fmaf(g2, d2c, fmaf(g1, d1c, g0 * d0c));
-        rc0 = fmaf(a, d0c, rc0);
-        rc1 = fmaf(a, d1c, rc1);
-        rc2 = fmaf(a, d2c, rc2);
-        const float draw = (araw <= amax) ? dalpha : 0.f;            // clamp_max passes on <=
-        m0 = -0.5f * araw * draw;                                    // dL/dq: d/dq of op*exp(-q/2)
-        mx = m0 * du; my = m0 * dv;
-        mxx = mx * du; mxy = mx * dv; myy = my * dv;
+    if (wlast > boff) {                                                // else nobody in this warp consumed these splats
+      const int lim = (int)min((uint32_t)cnt, wlast - boff);
+      const uint32_t nw = compact_touching(buf, sa_list, lim, lane, wcx, wcy);
+      // splat j of this batch was consumed by this pixel iff boff + j < last  <=>  its rec0 address < last_addr
+      const int last_addr = (int)buf + ((int)last - (int)boff) * 16;
+      for (uint32_t i = nw; i-- > 0;) {
+        const uint32_t aj = lds_u32(sa_list + i * 4u);
+        const float4 r0 = lds_f4(aj), r1 = lds_f4(aj + kRecStride);
+        const float du = pxf - r0.x, dv = pyf - r0.y;
+        const float e = splat_exponent(r0, r1, du, dv);
+        const bool hit = ((int)aj < last_addr) && (e >= r1.z);
+        if (!__any_sync(0xffffffffu, hit)) continue;
+        const float2 gb = lds_f2(aj + 2 * kRecStride);
+        float mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f, m0 = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+        if (hit) {
+          const float araw = ex2_ftz(e);
+          const float a = fminf(araw, amax);
+          const float Ti = __fdividef(T, 1.f - a);
+          T = Ti;
+          const float w = a * Ti;
+          v_r = g0 * w; v_g = g1 * w; v_b = g2 * w;
+          const float d0c = r1.w - rc0, d1c = gb.x - rc1, d2c = gb.y - rc2;
+          const float dalpha = Ti * fmaf(g2, d2c, fmaf(g1, d1c, g0 * d0c));
+          rc0 = fmaf(a, d0c, rc0);
+          rc1 = fmaf(a, d1c, rc1);
+          rc2 = fmaf(a, d2c, rc2);
+          const float draw = (araw <= amax) ? dalpha : 0.f;            // clamp_max passes on <=
+          m0 = -0.5f * araw * draw;                                    // dL/dq: d/dq of op*exp(-q/2)
+          mx = m0 * du; my = m0 * dv;
+          mxx = mx * du; mxy = mx * dv; myy = my * dv;
+        }
+        // Reduce the 9 per-pixel values over the warp by recursive halving: at every step a lane keeps
+        // one half of its values and trades the other half with its partner, so 12 shuffles (instead of
+        // 45) leave each total in one lane pair; those lanes then issue one RED.
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+        float a0, a1, a2, a3, a4;
+        {
+          const float k0 = h16 ? m0 : mx,    t0 = h16 ? mx : m0;
+          const float k1 = h16 ? v_r : my,   t1 = h16 ? my : v_r;
+          const float k2 = h16 ? v_g : mxx,  t2 = h16 ? mxx : v_g;
+          const float k3 = h16 ? v_b : mxy,  t3 = h16 ? mxy : v_b;
+          const float k4 = h16 ? 0.f : myy,  t4 = h16 ? myy : 0.f;
+          a0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+          a1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
+          a2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
+          a3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
+          a4 = k4 + __shfl_xor_sync(0xffffffffu, t4, 16);
+        }
+        // low half-warp: (Mx, My, Mxx, Mxy, Myy)   high half-warp: (M0, r, g, b, 0)
+        float b0, b1, b2;
+        {
+          const float k0 = h8 ? a3 : a0, t0 = h8 ? a0 : a3;
+          const float k1 = h8 ? a4 : a1, t1 = h8 ? a1 : a4;
+          const float k2 = h8 ? 0.f : a2, t2 = h8 ? a2 : 0.f;
+          b0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
+          b1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
+          b2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 8);
+        }
+        // h8 = 0: (x0, x1, x2)   h8 = 1: (x3, x4, 0)   of the half-warp's five values
+        float c0, c1;
+        {
+          const float k0 = h4 ? b2 : b0, t0 = h4 ? b0 : b2;
+          const float k1 = h4 ? 0.f : b1, t1 = h4 ? b1 : 0.f;
+          c0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
+          c1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
+        }
+        // h4 = 0: (y0, y1)   h4 = 1: (y2, 0)
+        float d0;
+        {
+          const float k0 = h2 ? c1 : c0, t0 = h2 ? c0 : c1;
+          d0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2);
+        }
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+        if (slot >= 0) {
+          const uint32_t id = lds_u32(sa_id + ((aj - buf) >> 2));
+          atomicAdd(my_acc + (size_t)id * 12, d0);
+        }
       }
-      // Reduce the 9 per-pixel values over the warp by recursive halving: at every step a lane keeps
-      // one half of its values and trades the other half with its partner, so 12 shuffles (instead of
-      // 45) leave each total in one lane pair; those lanes then issue one RED.
-      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-      float a0, a1, a2, a3, a4;
-      {
-        const float k0 = h16 ? m0 : mx,    t0 = h16 ? mx : m0;
-        const float k1 = h16 ? v_r : my,   t1 = h16 ? my : v_r;
-        const float k2 = h16 ? v_g : mxx,  t2 = h16 ? mxx : v_g;
-        const float k3 = h16 ? v_b : mxy,  t3 = h16 ? mxy : v_b;
-        const float k4 = h16 ? 0.f : myy,  t4 = h16 ? myy : 0.f;
-        a0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
-        a1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
-        a2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
-        a3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
-        a4 = k4 + __shfl_xor_sync(0xffffffffu, t4, 16);
-      }
-      // low half-warp: (Mx, My, Mxx, Mxy, Myy)   high half-warp: (M0, r, g, b, 0)
-      float b0, b1, b2;
-      {
-        const float k0 = h8 ? a3 : a0, t0 = h8 ? a0 : a3;
-        const float k1 = h8 ? a4 : a1, t1 = h8 ? a1 : a4;
-        const float k2 = h8 ? 0.f : a2, t2 = h8 ? a2 : 0.f;
-        b0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
-        b1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
-        b2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 8);
-      }
-      // h8 = 0: (x0, x1, x2)   h8 = 1: (x3, x4, 0)   of the half-warp's five values
-      float c0, c1;
-      {
-        const float k0 = h4 ? b2 : b0, t0 = h4 ? b0 : b2;
-        const float k1 = h4 ? 0.f : b1, t1 = h4 ? b1 : 0.f;
-        c0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
-        c1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
-      }
-      // h4 = 0: (y0, y1)   h4 = 1: (y2, 0)
-      float d0;
-      {
-        const float k0 = h2 ? c1 : c0, t0 = h2 ? c0 : c1;
-        d0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2);
-      }
-      d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-      if (slot >= 0) atomicAdd(my_acc + (size_t)__float_as_uint(r2.w) * 12, d0);
     }
   }
 }

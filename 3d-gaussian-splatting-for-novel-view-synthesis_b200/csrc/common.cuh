@@ -33,10 +33,10 @@ __device__ __forceinline__ float ld_stream_f(const float* p) {
 // Frame workspace: header | per-Gaussian | per-tile | per-pixel.   Everything 256-byte aligned.
 struct FrameLayout {
   size_t header;          // b200gs_frame_stats (64 B) + scan/sort bookkeeping
-  size_t rec0, rec1, rec2;  // float4[n] each: (u,v,A11,2*A12) (A22,op,r,g) (b,ext_u,ext_v,radius)
+  size_t rec0, rec1, rec2;  // float4[n] each: (u,v,c*A11,c*2*A12) (c*A22,log2 op,gate,r) (g,b,ext_u,ext_v), see preprocess.cu
   size_t depth_key;       // u32[n]  float bits of z, 0xFFFFFFFF when culled
   size_t rect;            // uint2[n] packed u16 tile rect: x = tu0 | tu1<<16, y = tv0 | tv1<<16
-  size_t tiles_touched;   // u32[n]
+  size_t radius;          // u32[n]  ceil(2.5 sqrt(lambda_max)) (introspection only)
   size_t super_touched;   // u32[n]  number of supertiles the tile rect overlaps
   size_t sort_key_alt;    // u32[n]  depth-sort ping-pong buffers (depth_key itself stays intact)
   size_t sort_key_alt2;   // u32[n]
@@ -82,7 +82,7 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.rec0 = take(N * 16); L.rec1 = take(N * 16); L.rec2 = take(N * 16);
   L.depth_key = take(N * 4);
   L.rect = take(N * 8);
-  L.tiles_touched = take(N * 4);
+  L.radius = take(N * 4);
   L.super_touched = take(N * 4);
   L.sort_key_alt = take(N * 4);
   L.sort_key_alt2 = take(N * 4);

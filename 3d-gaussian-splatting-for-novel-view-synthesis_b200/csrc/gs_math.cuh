@@ -24,12 +24,16 @@ namespace gs {
 // ------------------------------------------------------------------------------------------------
 // Parameters
 // ------------------------------------------------------------------------------------------------
+// exp(-q/2) = 2^(kBlendExpScale * q)
+constexpr float kBlendExpScale = -0.72134752044448170368f;   // -log2(e)/2
+
 struct RenderParams {          // by-value kernel argument; built on the host from b200gs_camera
   float fx, fy, cx, cy;
   float ulo, uhi, vlo, vhi;    // (float)(-guard-cx), (float)(W+guard-cx), ... (utils.py:81-91)
   float near_plane, far_plane;
   float min_conis, alpha_pre;  // alpha_cutoff * 0.5 (render.py:107)
   float chi2, alpha_max, alpha_cutoff;
+  float chi2c, cut_e;          // blend gate terms: kBlendExpScale * chi2 and log2(alpha_cutoff) (see SplatRecord)
   int W, H, tiles_x, tiles_y;
   int row_begin, row_end;      // tile rows rendered by this rank [begin,end)
 };
@@ -50,6 +54,12 @@ inline void fill_render_params(RenderParams& rp, int H, int W, double fx, double
   rp.chi2 = (float)chi_square_clip;
   rp.alpha_max = (float)alpha_max;
   rp.alpha_cutoff = (float)alpha_cutoff;
+  rp.chi2c = kBlendExpScale * rp.chi2;
+  // lower bound of log2(alpha_raw): +inf when nothing can pass (alpha_cutoff > alpha_max), -inf when
+  // everything does (alpha_cutoff <= 0)
+  if (!(rp.alpha_cutoff <= rp.alpha_max)) rp.cut_e = INFINITY;
+  else if (!(rp.alpha_cutoff > 0.f)) rp.cut_e = -INFINITY;
+  else rp.cut_e = (float)log2((double)rp.alpha_cutoff);
   rp.W = W; rp.H = H;
   rp.tiles_x = (W + 15) / 16;
   rp.tiles_y = (H + 15) / 16;

@@ -55,11 +55,26 @@ struct FrameView {
   float4 *rec0, *rec1, *rec2;
   uint32_t* depth_key;
   uint2* rect;
-  uint32_t* tiles_touched;
+  uint32_t* radius;
   uint32_t* super_touched;
   float* grad_acc;
   b200gs_frame_stats* stats;
 };
+
+// The record the blend kernels consume, already in the form their per-(pixel, splat) visit wants, so that
+// staging a tile's splats into shared memory is a plain asynchronous copy:  with c = -log2(e)/2 the exponent of
+//     alpha_raw = op * exp(-q/2) = 2^e        is      e = c*A11*du^2 + c*2*A12*du*dv + c*A22*dv^2 + log2(op)
+// and both gates of render.py:362-374 (q <= chi2; min(alpha_raw, alpha_max) >= alpha_cutoff) are  e >= gate,
+// gate = max(c*chi2 + log2(op), log2(alpha_cutoff)).
+//   rec0 = (u, v, c*A11, c*2*A12)   rec1 = (c*A22, log2(op), gate, r)   rec2 = (g, b, ext_u, ext_v)
+__device__ __forceinline__ void write_splat_record(const FrameView& f, int i, const Projection& o, const float rgb[3],
+                                                   float eu, float ev, const RenderParams& rp) {
+  const float lop = log2f(o.op);
+  f.rec0[i] = make_float4(o.u, o.v, kBlendExpScale * o.A11, kBlendExpScale * (2.f * o.A12));
+  f.rec1[i] = make_float4(kBlendExpScale * o.A22, lop, fmaxf(rp.chi2c + lop, rp.cut_e), rgb[0]);
+  f.rec2[i] = make_float4(rgb[1], rgb[2], eu, ev);
+  f.radius[i] = (uint32_t)o.radius;
+}
 
 __device__ __forceinline__ void sh_color(const float* coef_dc, const float* coef_rest, const float Y[16],
                                          float rgb[3], float acc_out[3]) {
@@ -135,7 +150,6 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
     past_s7 = vis || o.offscreen;
     if (!vis) {
       f.depth_key[i] = kCulledKey;
-      f.tiles_touched[i] = 0;
       f.super_touched[i] = 0;
     } else {
       float rgb[3];
@@ -153,12 +167,9 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
       if (tiles == 0) { tv0 = 0; tv1 = 0; }
       float eu, ev;
       conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
-      f.rec0[i] = make_float4(o.u, o.v, o.A11, 2.f * o.A12);
-      f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
-      f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
+      write_splat_record(f, i, o, rgb, eu, ev, rp);
       f.depth_key[i] = __float_as_uint(o.z);
       f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
-      f.tiles_touched[i] = (uint32_t)tiles;
       my_tiles = (uint32_t)tiles;
       f.super_touched[i] = tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
     }
@@ -291,8 +302,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       }
       if (!vis) {
         f.depth_key[i] = kCulledKey;
-        f.tiles_touched[i] = 0;
-        f.super_touched[i] = 0;
+          f.super_touched[i] = 0;
       } else {
         ++vis_count;
         const ViewDir vd = view_dir(p, ps.cam);
@@ -304,13 +314,10 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
         if (tiles == 0) { tv0 = 0; tv1 = 0; }
         float eu, ev;
         conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
-        f.rec0[i] = make_float4(o.u, o.v, o.A11, 2.f * o.A12);
-        f.rec1[i] = make_float4(o.A22, o.op, rgb[0], rgb[1]);
-        f.rec2[i] = make_float4(rgb[2], eu, ev, (float)o.radius);
+        write_splat_record(f, i, o, rgb, eu, ev, rp);
         f.depth_key[i] = __float_as_uint(o.z);
         f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
-        f.tiles_touched[i] = (uint32_t)tiles;
-        tiles_sum += (uint32_t)tiles;
+          tiles_sum += (uint32_t)tiles;
         f.super_touched[i] =
             tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
       }
@@ -612,7 +619,7 @@ static FrameView make_view(void* ws, const FrameLayout& L) {
   f.rec0 = ws_ptr<float4>(ws, L.rec0); f.rec1 = ws_ptr<float4>(ws, L.rec1); f.rec2 = ws_ptr<float4>(ws, L.rec2);
   f.depth_key = ws_ptr<uint32_t>(ws, L.depth_key);
   f.rect = ws_ptr<uint2>(ws, L.rect);
-  f.tiles_touched = ws_ptr<uint32_t>(ws, L.tiles_touched);
+  f.radius = ws_ptr<uint32_t>(ws, L.radius);
   f.super_touched = ws_ptr<uint32_t>(ws, L.super_touched);
   f.grad_acc = ws_ptr<float>(ws, L.grad_acc);
   f.stats = ws_ptr<b200gs_frame_stats>(ws, L.header);
