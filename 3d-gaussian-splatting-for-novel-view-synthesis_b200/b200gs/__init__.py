@@ -1,13 +1,16 @@
 """b200gs - B200-native (sm_100a) differentiable Gaussian-splat rasterizer.
 
 Drop-in for the render path of ashu1069/3D-Gaussian-Splatting-for-Novel-View-Synthesis:
-`build_sigma_from_params`, `evaluate_sh`, `render` (same names/arguments as `gaussian_splatting`),
+`build_sigma_from_params`, `evaluate_sh`, `render`, and the loss that consumes the image (`compute_loss`,
+`l1_loss`, `ssim_loss`) - same names/arguments as `gaussian_splatting` -,
 `install()` to rebind them inside an imported reference package, `python -m b200gs.run <script>` to run
 a reference script unchanged on top of it.
 """
 from .api import build_sigma_from_params, evaluate_sh, render
+from .losses import compute_loss, compute_loss_tensors, l1_loss, ssim_loss
 from .install import install, uninstall
 from ._lib import B200GSError, LIB_PATH, load as load_library
 
-__all__ = ["build_sigma_from_params", "evaluate_sh", "render", "install", "uninstall", "B200GSError",
+__all__ = ["build_sigma_from_params", "evaluate_sh", "render", "compute_loss", "compute_loss_tensors", "l1_loss",
+           "ssim_loss", "install", "uninstall", "B200GSError",
            "LIB_PATH", "load_library"]

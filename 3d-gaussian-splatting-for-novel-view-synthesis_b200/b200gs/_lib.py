@@ -62,6 +62,11 @@ SYMBOLS = {
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200gs_render_backward": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, c_void_p, c_size_t,
                                        c_uint32, c_void_p, POINTER(Grads), c_void_p]),
+    "b200gs_loss_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "b200gs_l1_ssim_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_double, c_void_p,
+                                       c_size_t, c_int32, c_void_p, c_void_p]),
+    "b200gs_l1_ssim_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_double, c_void_p,
+                                        c_size_t, c_void_p, c_void_p, c_void_p]),
     "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
     "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,

@@ -1,4 +1,4 @@
-"""Rebind the reference's three render-path callables to the b200gs implementations.
+"""Rebind the reference's render-path callables (and the loss that consumes the image) to the b200gs implementations.
 
 The reference has no plugin mechanism: its scripts do `from gaussian_splatting.render import render`
 etc. at import time (scripts/train.py:41-45, scripts/render_trained.py:22-25, scripts/inference.py:33-36).
@@ -15,12 +15,17 @@ _PATCHES = (
     ("gaussian_splatting.render", "render"),
     ("gaussian_splatting.gaussian", "build_sigma_from_params"),
     ("gaussian_splatting.spherical_harmonics", "evaluate_sh"),
+    # the consumer of the image in every training iteration (scripts/train.py:44,511)
+    ("gaussian_splatting.losses", "compute_loss"),
+    ("gaussian_splatting.losses", "l1_loss"),
+    ("gaussian_splatting.losses", "ssim_loss"),
 )
 _saved = {}
 
 
 def install(package: str = "gaussian_splatting"):
-    from . import api
+    from . import api, losses
+    impl = {"compute_loss": losses.compute_loss, "l1_loss": losses.l1_loss, "ssim_loss": losses.ssim_loss}
     importlib.import_module(package)
     pkg = sys.modules[package]
     for mod_name, attr in _PATCHES:
@@ -30,10 +35,11 @@ def install(package: str = "gaussian_splatting"):
         importlib.import_module(mod_name)
         mod = sys.modules[mod_name]
         _saved.setdefault((mod_name, attr), getattr(mod, attr))
-        setattr(mod, attr, getattr(api, attr))
+        fn = impl.get(attr) or getattr(api, attr)
+        setattr(mod, attr, fn)
         if hasattr(pkg, attr):
             _saved.setdefault((package, attr), getattr(pkg, attr))
-            setattr(pkg, attr, getattr(api, attr))
+            setattr(pkg, attr, fn)
     return pkg
 
 

@@ -28,6 +28,7 @@ SOURCES = {
     "scan_sort.cu": [],
     "binning.cu": [],
     "blend.cu": [],
+    "loss.cu": [],
     "api.cu": [],
 }
 HEADERS = ["common.cuh", "gs_math.cuh", os.path.join(INCLUDE, "b200gs.h")]

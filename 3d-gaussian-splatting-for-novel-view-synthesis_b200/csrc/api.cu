@@ -29,10 +29,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -230,6 +230,37 @@ int b200gs_evaluate_sh_backward(int32_t n, const float* f_dc, const float* f_res
     return fail(B200GS_ERR_ARG, "evaluate_sh_backward: null");
   cudaStream_t s = (cudaStream_t)stream;
   PCU(R_EVAL_SH_BWD, 1, gs::launch_eval_sh_bwd(n, f_dc, f_rest, points, c2w, grad_color, grad_f_dc, grad_f_rest, grad_points, s));
+  return B200GS_OK;
+}
+
+size_t b200gs_loss_workspace_bytes(int32_t n_img, int32_t H, int32_t W, int32_t with_grad) {
+  if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+  return gs::loss_workspace_bytes(n_img, H, W, with_grad != 0);
+}
+
+int b200gs_l1_ssim_forward(const float* pred, const float* target, int32_t n_img, int32_t H, int32_t W,
+                           double lambda_l1, double lambda_ssim, void* workspace, size_t workspace_bytes,
+                           int32_t with_grad, float* out3, void* stream) {
+  if (!pred || !target || !workspace || !out3 || n_img <= 0 || H <= 0 || W <= 0)
+    return fail(B200GS_ERR_ARG, "l1_ssim_forward: null or empty argument");
+  if (workspace_bytes < gs::loss_workspace_bytes(n_img, H, W, with_grad != 0))
+    return fail(B200GS_ERR_WORKSPACE, "l1_ssim_forward: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_LOSS_FWD, 1, gs::launch_l1_ssim_fwd(pred, target, n_img, H, W, (float)lambda_l1, (float)lambda_ssim, workspace,
+                                            with_grad != 0, out3, s));
+  return B200GS_OK;
+}
+
+int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_img, int32_t H, int32_t W,
+                            double lambda_l1, double lambda_ssim, const void* workspace, size_t workspace_bytes,
+                            const float* grad_total, float* grad_pred, void* stream) {
+  if (!pred || !target || !workspace || !grad_pred || n_img <= 0 || H <= 0 || W <= 0)
+    return fail(B200GS_ERR_ARG, "l1_ssim_backward: null or empty argument");
+  if (workspace_bytes < gs::loss_workspace_bytes(n_img, H, W, true))
+    return fail(B200GS_ERR_WORKSPACE, "l1_ssim_backward: workspace too small (forward must run with with_grad)");
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_LOSS_BWD, 1, gs::launch_l1_ssim_bwd(pred, target, n_img, H, W, (float)lambda_l1, (float)lambda_ssim, workspace,
+                                            grad_total, grad_pred, s));
   return B200GS_OK;
 }
 

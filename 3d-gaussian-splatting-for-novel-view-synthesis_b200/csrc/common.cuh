@@ -174,6 +174,13 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
 cudaError_t launch_fill_list_tiles(const uint2* ranges, int n_tiles, uint32_t count, int32_t* list_tile,
                                    cudaStream_t s);
 
+size_t loss_workspace_bytes(int n_img, int H, int W, bool with_grad);
+cudaError_t launch_l1_ssim_fwd(const float* pred, const float* target, int n_img, int H, int W, float lambda_l1,
+                               float lambda_ssim, void* ws, bool with_grad, float* out3, cudaStream_t s);
+cudaError_t launch_l1_ssim_bwd(const float* pred, const float* target, int n_img, int H, int W, float lambda_l1,
+                               float lambda_ssim, const void* ws, const float* grad_total, float* grad_pred,
+                               cudaStream_t s);
+
 cudaError_t launch_blend_fwd(const RenderParams& rp, const void* frame_ws, const FrameLayout& L, const uint32_t* vals,
                              float* image, cudaStream_t s);
 cudaError_t launch_blend_bwd(const RenderParams& rp, void* frame_ws, const FrameLayout& L, const uint32_t* vals,

@@ -190,6 +190,8 @@ def algorithmic_bytes(N, V, I, P, tiles, S=0):
         "blend_bwd": 4 * I + 36 * I + 36 * I + 12 * P + 8 * P,
         "preprocess_bwd": 236 * N + 48 * N + 236 * N,
         "build_sigma": 28 * N + 36 * N,
+        "l1_ssim_fwd": 24 * P + 36 * P,           # pred + target in, three partial-derivative maps out
+        "l1_ssim_bwd": 36 * P + 24 * P + 12 * P,  # maps + pred + target in, dL/dpred out
     }
 
 
@@ -328,6 +330,24 @@ def run_b200gs(args):
         return loss
     ms_train, launches_train = timed(lambda i: train_step(i), K, Wm)
 
+    # the same step with the reference's own training loss (losses.py:158: 0.8 L1 + 0.2 (1 - SSIM) against a target
+    # image) through the fused loss kernels, loss values left on the device (scripts/train.py:511 reads them back)
+    target_dev = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(4321)).to(dev)
+
+    def train_step_loss(i):
+        for p in leaves.values():
+            p.grad = None
+        c2w = c2w_dev[view_of(i)]
+        sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        img = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sg, c2w, H, W, intr["fx"], intr["fy"],
+                            intr["cx"], intr["cy"])
+        loss, _ = b200gs.compute_loss_tensors(img, target_dev)
+        (loss / world).backward()
+        allreduce_gradients(leaves.values())
+        return loss
+    ms_train_loss, _ = timed(lambda i: train_step_loss(i), K, Wm)
+
     # e2e: every step's target image comes from pinned host memory (H2D inside the timed region) and the loss
     # is read back.  As a DataLoader with pin_memory would, the copy of step i+1's target runs on a copy stream
     # while step i computes (two device buffers).
@@ -367,13 +387,13 @@ def run_b200gs(args):
         for i in range(K):
             render_step(c2w_dev[view_of(i)])
     torch.cuda.synchronize()
-    nreg = 16
+    nreg = 24
     ms_buf, call_buf = (ctypes.c_float * nreg)(), (ctypes.c_int32 * nreg)()
     n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
     fwd_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
                    for r in range(n_regions) if call_buf[r]}
     for i in range(K):
-        train_step(i)
+        train_step_loss(i)
     torch.cuda.synchronize()
     n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
     train_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
@@ -459,6 +479,9 @@ def run_b200gs(args):
                   "ms_per_step": ms_train / K,
                   "step": "build_sigma + evaluate_sh + render + weighted-sum loss + backward" +
                           (" + NCCL sum all-reduce of 6 gradient tensors (236 MB)" if world > 1 else ""),
+                  "with_l1_ssim_loss": {"value": K / (ms_train_loss * 1e-3), "unit": "it/s", "ms_per_step": ms_train_loss / K,
+                                        "step": "the same with b200gs.compute_loss (fused L1 + SSIM, losses.py:158) "
+                                                "instead of the weighted sum"},
                   "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
                           "d2h_bytes_per_step": 4}},
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,

@@ -171,6 +171,22 @@ int b200gs_debug_export_lists(const void* frame_ws, size_t frame_bytes, const vo
                               int32_t* list_tile, int32_t* list_id, uint32_t count, int32_t* ranges,
                               void* stream);
 
+/* gaussian_splatting/losses.py:158-185  compute_loss(pred, target, lambda_l1, lambda_ssim) - the training loss
+ * that consumes the rendered image (scripts/train.py:511): mean |pred - target| and 1 - mean SSIM (11x11
+ * Gaussian window, sigma 1.5, zero padding, per channel; losses.py:27-155), fused into one kernel.
+ * pred / target: [n_img, H, W, 3] fp32.  out3 (device, 3 floats) = (l1, ssim_loss, lambda_l1 l1 + lambda_ssim
+ * ssim_loss).  with_grad != 0 also leaves the three partial-derivative maps in the workspace that
+ * b200gs_l1_ssim_backward convolves into grad_pred [n_img,H,W,3] = d(total)/d(pred) * (*grad_total)
+ * (grad_total: device scalar, NULL = 1).  The workspace (b200gs_loss_workspace_bytes) is caller-owned and
+ * must be the same buffer in both calls. */
+size_t b200gs_loss_workspace_bytes(int32_t n_img, int32_t H, int32_t W, int32_t with_grad);
+int b200gs_l1_ssim_forward(const float* pred, const float* target, int32_t n_img, int32_t H, int32_t W,
+                           double lambda_l1, double lambda_ssim, void* workspace, size_t workspace_bytes,
+                           int32_t with_grad, float* out3, void* stream);
+int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_img, int32_t H, int32_t W,
+                            double lambda_l1, double lambda_ssim, const void* workspace, size_t workspace_bytes,
+                            const float* grad_total, float* grad_pred, void* stream);
+
 /* Per-region CUDA-event profiling (bench.py's per-kernel table).  enable(1) starts recording an event
  * pair around every kernel group launched through this library; collect() synchronises the device,
  * sums the elapsed milliseconds and the number of calls per region, clears the records and returns the

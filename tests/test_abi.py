@@ -50,6 +50,8 @@ def test_no_cpu_fallback():
         b200gs.build_sigma_from_params(z, torch.zeros(4, 4))
     with pytest.raises(b200gs.B200GSError):
         b200gs.evaluate_sh(z, torch.zeros(4, 45), z, torch.eye(4))
+    with pytest.raises(b200gs.B200GSError):
+        b200gs.compute_loss(torch.zeros(8, 8, 3), torch.zeros(8, 8, 3))
 
 
 def test_product_never_imports_oracle():
@@ -66,19 +68,23 @@ def test_install_rebinds_reference_shaped_package(monkeypatch):
     pkg = types.ModuleType("fake_gs")
     pkg.__path__ = []
     mods = {}
-    for sub, attr in (("render", "render"), ("gaussian", "build_sigma_from_params"),
-                      ("spherical_harmonics", "evaluate_sh")):
+    for sub, attrs in (("render", ("render",)), ("gaussian", ("build_sigma_from_params",)),
+                       ("spherical_harmonics", ("evaluate_sh",)), ("losses", ("compute_loss", "l1_loss", "ssim_loss"))):
         m = types.ModuleType(f"fake_gs.{sub}")
-        setattr(m, attr, lambda *a, **k: "reference")
+        for attr in attrs:
+            setattr(m, attr, lambda *a, **k: "reference")
         mods[sub] = m
         monkeypatch.setitem(sys.modules, f"fake_gs.{sub}", m)
-        setattr(pkg, attr, getattr(m, attr))       # re-export, shadows the submodule name like the reference
+        if sub != "losses":                            # the reference re-exports the render-path names only
+            setattr(pkg, attrs[0], getattr(m, attrs[0]))   # re-export, shadows the submodule name like the reference
     monkeypatch.setitem(sys.modules, "fake_gs", pkg)
     b200gs.install("fake_gs")
     try:
         assert mods["render"].render is b200gs.render and pkg.render is b200gs.render
         assert mods["gaussian"].build_sigma_from_params is b200gs.build_sigma_from_params
         assert pkg.evaluate_sh is b200gs.evaluate_sh
+        assert mods["losses"].compute_loss is b200gs.compute_loss and mods["losses"].ssim_loss is b200gs.ssim_loss
+        assert mods["losses"].l1_loss is b200gs.l1_loss
     finally:
         b200gs.uninstall()
     assert mods["render"].render() == "reference"
