@@ -9,8 +9,9 @@ a reference script unchanged on top of it.
 from .api import build_sigma_from_params, evaluate_sh, render
 from .losses import compute_loss, compute_loss_tensors, l1_loss, ssim_loss
 from .install import install, uninstall
+from .optim import FusedAdam, clip_grad_norm_
 from ._lib import B200GSError, LIB_PATH, load as load_library
 
 __all__ = ["build_sigma_from_params", "evaluate_sh", "render", "compute_loss", "compute_loss_tensors", "l1_loss",
-           "ssim_loss", "install", "uninstall", "B200GSError",
+           "ssim_loss", "FusedAdam", "clip_grad_norm_", "install", "uninstall", "B200GSError",
            "LIB_PATH", "load_library"]

@@ -41,6 +41,11 @@ class Sizes(Structure):
     _fields_ = [("frame_bytes", c_size_t), ("isect_bytes", c_size_t)]
 
 
+class AdamTensor(Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("numel", ctypes.c_int64), ("lr", c_double), ("step", c_int32), ("reserved", c_int32)]
+
+
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
                 ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("reserved", c_uint32 * 11)]
@@ -67,6 +72,9 @@ SYMBOLS = {
                                        c_size_t, c_int32, c_void_p, c_void_p]),
     "b200gs_l1_ssim_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_double, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p]),
+    "b200gs_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_double, c_double, c_double, c_void_p]),
+    "b200gs_clip_workspace_bytes": (c_size_t, [ctypes.c_int64]),
+    "b200gs_clip_grad_norm": (c_int, [c_void_p, ctypes.c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
     "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,

@@ -23,8 +23,17 @@ _PATCHES = (
 _saved = {}
 
 
-def install(package: str = "gaussian_splatting"):
+def install(package: str = "gaussian_splatting", optimizer: bool = False):
+    """optimizer=True additionally rebinds torch.optim.Adam and torch.nn.utils.clip_grad_norm_ to the fused
+    versions (the reference script builds `optim.Adam(...)` itself, scripts/train.py:394-401,536)."""
     from . import api, losses
+    if optimizer:
+        import torch
+        from . import optim as _optim
+        _saved.setdefault(("torch.optim", "Adam"), torch.optim.Adam)
+        _saved.setdefault(("torch.nn.utils", "clip_grad_norm_"), torch.nn.utils.clip_grad_norm_)
+        torch.optim.Adam = _optim.FusedAdam
+        torch.nn.utils.clip_grad_norm_ = _optim.clip_grad_norm_
     impl = {"compute_loss": losses.compute_loss, "l1_loss": losses.l1_loss, "ssim_loss": losses.ssim_loss}
     importlib.import_module(package)
     pkg = sys.modules[package]

@@ -2,7 +2,8 @@
 
     python -m b200gs.run /path/to/reference/scripts/render_trained.py --checkpoint ... [args]
 
-Equivalent to `install()` followed by executing the script as __main__.  The reference checkout must
+Equivalent to `install()` followed by executing the script as __main__ (B200GS_PATCH_ADAM=1 also swaps
+torch.optim.Adam / clip_grad_norm_ for the fused versions).  The reference checkout must
 be importable: its root is derived from the script location (<root>/scripts/x.py) or taken from
 $B200GS_REFERENCE_ROOT.
 """
@@ -23,7 +24,7 @@ def main(argv=None):
     if root not in sys.path:
         sys.path.insert(0, root)
     from .install import install
-    install()
+    install(optimizer=os.environ.get("B200GS_PATCH_ADAM", "0") == "1")
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
     return 0

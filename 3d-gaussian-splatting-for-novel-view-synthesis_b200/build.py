@@ -29,6 +29,7 @@ SOURCES = {
     "binning.cu": [],
     "blend.cu": [],
     "loss.cu": [],
+    "optim.cu": [],
     "api.cu": [],
 }
 HEADERS = ["common.cuh", "gs_math.cuh", os.path.join(INCLUDE, "b200gs.h")]

@@ -29,10 +29,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -261,6 +261,30 @@ int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_im
   cudaStream_t s = (cudaStream_t)stream;
   PCU(R_LOSS_BWD, 1, gs::launch_l1_ssim_bwd(pred, target, n_img, H, W, (float)lambda_l1, (float)lambda_ssim, workspace,
                                             grad_total, grad_pred, s));
+  return B200GS_OK;
+}
+
+int b200gs_adam_step(const b200gs_adam_tensor* tensors, int32_t n_tensors, double beta1, double beta2, double eps,
+                     void* stream) {
+  if (n_tensors < 0 || (n_tensors > 0 && !tensors)) return fail(B200GS_ERR_ARG, "adam_step: null table");
+  for (int i = 0; i < n_tensors; ++i) {
+    const b200gs_adam_tensor& t = tensors[i];
+    if (t.numel < 0 || t.step < 1) return fail(B200GS_ERR_ARG, "adam_step: numel < 0 or step < 1");
+    if (t.numel > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq)) return fail(B200GS_ERR_ARG, "adam_step: null tensor");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_ADAM, 1, gs::launch_adam_step(tensors, n_tensors, beta1, beta2, eps, s));
+  return B200GS_OK;
+}
+
+size_t b200gs_clip_workspace_bytes(int64_t numel) { return gs::clip_workspace_bytes(numel > 0 ? numel : 0); }
+
+int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* workspace, size_t workspace_bytes,
+                          float* total_norm_out, void* stream) {
+  if (numel < 0 || (numel > 0 && (!grad || !workspace))) return fail(B200GS_ERR_ARG, "clip_grad_norm: null");
+  if (numel > 0 && workspace_bytes < gs::clip_workspace_bytes(numel)) return fail(B200GS_ERR_WORKSPACE, "clip_grad_norm: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_CLIP, 2, gs::launch_clip_grad_norm(grad, numel, max_norm, workspace, total_norm_out, s));
   return B200GS_OK;
 }
 

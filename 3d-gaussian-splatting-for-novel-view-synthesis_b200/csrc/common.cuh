@@ -174,6 +174,12 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
 cudaError_t launch_fill_list_tiles(const uint2* ranges, int n_tiles, uint32_t count, int32_t* list_tile,
                                    cudaStream_t s);
 
+cudaError_t launch_adam_step(const b200gs_adam_tensor* tensors, int n_tensors, double beta1, double beta2, double eps,
+                             cudaStream_t s);
+size_t clip_workspace_bytes(long long numel);
+cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
+                                  cudaStream_t s);
+
 size_t loss_workspace_bytes(int n_img, int H, int W, bool with_grad);
 cudaError_t launch_l1_ssim_fwd(const float* pred, const float* target, int n_img, int H, int W, float lambda_l1,
                                float lambda_ssim, void* ws, bool with_grad, float* out3, cudaStream_t s);

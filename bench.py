@@ -190,6 +190,8 @@ def algorithmic_bytes(N, V, I, P, tiles, S=0):
         "blend_bwd": 4 * I + 36 * I + 36 * I + 12 * P + 8 * P,
         "preprocess_bwd": 236 * N + 48 * N + 236 * N,
         "build_sigma": 28 * N + 36 * N,
+        "adam_step": 28 * 59 * N,                 # (param, grad, exp_avg, exp_avg_sq) in, (param, exp_avg, exp_avg_sq) out
+        "clip_grad_norm": 12 * N,                 # norm pass over pos.grad (the scale pass only runs when clipping)
         "l1_ssim_fwd": 24 * P + 36 * P,           # pred + target in, three partial-derivative maps out
         "l1_ssim_bwd": 36 * P + 24 * P + 12 * P,  # maps + pred + target in, dL/dpred out
     }
@@ -398,7 +400,40 @@ def run_b200gs(args):
     n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
     train_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
                      for r in range(n_regions) if call_buf[r]}
+    # ---- the whole training iteration of scripts/train.py:463-538 on the fused path: build_sigma + evaluate_sh + render
+    #      + L1/SSIM loss + backward (+ all-reduce) + clip_grad_norm_(pos, 1.0) + Adam over the six groups (the
+    #      reference's learning rates, eps 1e-15).  Runs last: it moves the parameters.
+    lr0 = {"pos": 1.6e-4 * 0.01, "opacity_raw": 0.05, "f_dc": 2.5e-3, "f_rest": 2.5e-3 / 20.0, "scale_raw": 5e-3, "q_raw": 1e-3}
+    opt = b200gs.FusedAdam([{"params": [leaves[k]], "lr": lr0[k], "name": k} for k in PARAMS], lr=1e-3, eps=1e-15)
+
+    def train_full(i):
+        opt.zero_grad(set_to_none=True)
+        train_step_loss_nograd_reset(i)
+        b200gs.clip_grad_norm_(leaves["pos"], max_norm=1.0)
+        opt.step()
+
+    def train_step_loss_nograd_reset(i):
+        c2w = c2w_dev[view_of(i)]
+        sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        img = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sg, c2w, H, W, intr["fx"], intr["fy"],
+                            intr["cx"], intr["cy"])
+        loss, _ = b200gs.compute_loss_tensors(img, target_dev)
+        (loss / world).backward()
+        allreduce_gradients(leaves.values())
+    for i in range(4):                      # first steps allocate the optimizer state: not representative
+        train_full(i)
+    torch.cuda.synchronize()
+    lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
+    for i in range(6):
+        train_full(4 + i)
+    torch.cuda.synchronize()
+    n_regions = lib.b200gs_profile_collect(ms_buf, call_buf, nreg)
+    opt_regions = {lib.b200gs_profile_region_name(r).decode(): (ms_buf[r] / max(1, call_buf[r]), call_buf[r])
+                   for r in range(n_regions) if call_buf[r] and lib.b200gs_profile_region_name(r).decode() in
+                   ("adam_step", "clip_grad_norm")}
     lib.b200gs_profile_enable(0)
+    ms_train_full, _ = timed(lambda i: train_full(i), K, Wm)
 
     # ---- frame statistics of view 0 (V, I) for the byte model ---------------------------------------------------
     with torch.no_grad():
@@ -449,7 +484,7 @@ def run_b200gs(args):
     hbm, peak_src, sm_max = peaks()
     bytes_model = algorithmic_bytes(N, V, I, P, tiles, S)
     table = {}
-    for name, (ms, calls) in {**train_regions, **fwd_regions}.items():
+    for name, (ms, calls) in {**opt_regions, **train_regions, **fwd_regions}.items():
         b = bytes_model.get(name)
         table[name] = {"ms": round(ms, 5), "calls": calls, "alg_bytes": b,
                        "gbs": None if b is None else round(b / (ms * 1e-3) / 1e9, 1),
@@ -482,6 +517,9 @@ def run_b200gs(args):
                   "with_l1_ssim_loss": {"value": K / (ms_train_loss * 1e-3), "unit": "it/s", "ms_per_step": ms_train_loss / K,
                                         "step": "the same with b200gs.compute_loss (fused L1 + SSIM, losses.py:158) "
                                                 "instead of the weighted sum"},
+                  "full_iteration": {"value": K / (ms_train_full * 1e-3), "unit": "it/s", "ms_per_step": ms_train_full / K,
+                                     "step": "train.py:463-538 on the fused path: render + L1/SSIM loss + backward + "
+                                             "clip_grad_norm_(pos) + fused Adam over the six parameter groups"},
                   "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
                           "d2h_bytes_per_step": 4}},
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,

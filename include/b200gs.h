@@ -187,6 +187,30 @@ int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_im
                             double lambda_l1, double lambda_ssim, const void* workspace, size_t workspace_bytes,
                             const float* grad_total, float* grad_pred, void* stream);
 
+/* scripts/train.py:394-401,538  torch.optim.Adam over the six parameter groups (per-group lr, eps = 1e-15):
+ * one launch updates every tensor of the table in place (param, exp_avg, exp_avg_sq), reading each array
+ * once.  Arithmetic of torch/optim/adam.py with weight_decay = 0, amsgrad = False; `step` is the 1-based
+ * step count of that tensor AFTER this update (bias corrections are evaluated on the host in double). */
+typedef struct b200gs_adam_tensor {
+  float* param;        /* [numel] updated in place */
+  const float* grad;   /* [numel] */
+  float* exp_avg;      /* [numel] first moment, updated in place */
+  float* exp_avg_sq;   /* [numel] second moment, updated in place */
+  int64_t numel;
+  double lr;
+  int32_t step;
+  int32_t reserved;
+} b200gs_adam_tensor;
+int b200gs_adam_step(const b200gs_adam_tensor* tensors, int32_t n_tensors, double beta1, double beta2, double eps,
+                     void* stream);
+
+/* scripts/train.py:536  torch.nn.utils.clip_grad_norm_(model.pos, max_norm): total_norm = ||grad||_2 (written to
+ * total_norm_out, device, may be NULL), grad *= min(1, max_norm / (total_norm + 1e-6)) in place - without a host
+ * sync.  workspace: b200gs_clip_workspace_bytes(numel) bytes, caller-owned. */
+size_t b200gs_clip_workspace_bytes(int64_t numel);
+int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* workspace, size_t workspace_bytes,
+                          float* total_norm_out, void* stream);
+
 /* Per-region CUDA-event profiling (bench.py's per-kernel table).  enable(1) starts recording an event
  * pair around every kernel group launched through this library; collect() synchronises the device,
  * sums the elapsed milliseconds and the number of calls per region, clears the records and returns the

@@ -1,0 +1,99 @@
+"""Fused Adam step + gradient-norm clipping (scripts/train.py:394-401,536-538) against torch's own
+implementations - the reference's optimizer IS torch.optim.Adam (third-party dependency of the reference,
+torch >= 1.9 per requirements.txt:1; pinned here by the torch build in the image), so torch is the oracle."""
+import pytest
+import torch
+
+
+def _groups(n, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = dict(pos=(n, 3), opacity_raw=(n,), f_dc=(n, 3), f_rest=(n, 45), scale_raw=(n, 3), q_raw=(n, 4))
+    lrs = dict(pos=1.6e-4, opacity_raw=0.05, f_dc=2.5e-3, f_rest=2.5e-3 / 20, scale_raw=5e-3, q_raw=1e-3)
+    params = {k: torch.randn(*s, generator=g).to(dev) for k, s in shapes.items()}
+    return params, lrs, g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 1023, 4097, 100_003])
+def test_fused_adam_matches_torch_adam(n):
+    import b200gs
+    dev = torch.device("cuda")
+    params, lrs, g = _groups(n, dev, seed=n)
+    mine = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    mk = lambda ps: [{"params": [ps[k]], "lr": lrs[k], "name": k} for k in ps]          # train.py:394-401
+    opt_m = b200gs.FusedAdam(mk(mine), lr=1e-3, eps=1e-15)
+    opt_r = torch.optim.Adam(mk(ref), lr=1e-3, eps=1e-15, foreach=False)
+    for it in range(6):
+        opt_m.param_groups[0]["lr"] = opt_r.param_groups[0]["lr"] = 1.6e-4 * 0.9 ** it      # the pos-LR schedule (:445-457)
+        for k in params:
+            gr = (torch.randn(params[k].shape, generator=g) * (10.0 ** (it - 3))).to(dev)    # wide dynamic range
+            if it == 4 and k == "f_rest":
+                gr.zero_()
+            mine[k].grad, ref[k].grad = gr.clone(), gr.clone()
+        if it == 2:
+            mine["q_raw"].grad = ref["q_raw"].grad = None                                 # a tensor without gradient is skipped
+        opt_m.step()
+        opt_r.step()
+    for k in params:
+        a, b = mine[k].detach(), ref[k].detach()
+        assert float((a - b).abs().max() / b.abs().max()) <= 2e-6, k
+        sm, sr = opt_m.state[mine[k]], opt_r.state[ref[k]]
+        assert float(sm["step"]) == float(sr["step"])
+        assert float((sm["exp_avg"] - sr["exp_avg"]).abs().max() / sr["exp_avg"].abs().max().clamp_min(1e-30)) <= 2e-6
+        assert float((sm["exp_avg_sq"] - sr["exp_avg_sq"]).abs().max() / sr["exp_avg_sq"].abs().max().clamp_min(1e-30)) <= 2e-6
+    # state dicts are interchangeable with torch.optim.Adam
+    opt_r2 = torch.optim.Adam(mk(ref), lr=1e-3, eps=1e-15)
+    opt_r2.load_state_dict(opt_m.state_dict())
+    with pytest.raises(NotImplementedError):
+        b200gs.FusedAdam(mk(mine), amsgrad=True)
+    cpu = torch.zeros(4, requires_grad=True)
+    cpu.grad = torch.ones(4)
+    with pytest.raises(b200gs.B200GSError):
+        b200gs.FusedAdam([cpu]).step()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,scale", [(1, 5.0), (4096, 1e-3), (4097, 1.0), (1_000_003, 0.01), (300_000, 3.0)])
+def test_clip_grad_norm_matches_torch(n, scale):
+    import b200gs
+    g = torch.Generator().manual_seed(n)
+    grad = (torch.randn(n, 3, generator=g) * scale).cuda()
+    a = torch.zeros(n, 3, device="cuda", requires_grad=True)
+    b = torch.zeros(n, 3, device="cuda", requires_grad=True)
+    a.grad, b.grad = grad.clone(), grad.clone()
+    tn_a = b200gs.clip_grad_norm_(a, max_norm=1.0)                       # train.py:536
+    tn_b = torch.nn.utils.clip_grad_norm_(b, max_norm=1.0)
+    assert tn_a.is_cuda and abs(float(tn_a) - float(tn_b)) <= 2e-6 * float(tn_b)
+    if float(tn_b) <= 1.0 - 1e-5:
+        assert torch.equal(a.grad, grad)                                  # below the threshold: untouched
+    assert float((a.grad - b.grad).abs().max()) <= 2e-6 * float(b.grad.abs().max())
+    # several tensors: joint norm
+    c = torch.zeros(7, device="cuda", requires_grad=True)
+    d = torch.zeros(7, device="cuda", requires_grad=True)
+    c.grad, d.grad = torch.full((7,), 2.0, device="cuda"), torch.full((7,), 2.0, device="cuda")
+    t1 = b200gs.clip_grad_norm_([a, c], 0.5)
+    t2 = torch.nn.utils.clip_grad_norm_([b, d], 0.5)
+    assert abs(float(t1) - float(t2)) <= 1e-5 * float(t2) and float((c.grad - d.grad).abs().max()) <= 1e-6
+
+
+def test_install_can_swap_the_optimizer(monkeypatch):
+    import sys
+    import types
+    import b200gs
+    pkg = types.ModuleType("fake_gs2")
+    pkg.__path__ = []
+    for sub, attrs in (("render", ("render",)), ("gaussian", ("build_sigma_from_params",)),
+                       ("spherical_harmonics", ("evaluate_sh",)), ("losses", ("compute_loss", "l1_loss", "ssim_loss"))):
+        m = types.ModuleType(f"fake_gs2.{sub}")
+        for attr in attrs:
+            setattr(m, attr, lambda *a, **k: "reference")
+        monkeypatch.setitem(sys.modules, f"fake_gs2.{sub}", m)
+    monkeypatch.setitem(sys.modules, "fake_gs2", pkg)
+    adam, clip = torch.optim.Adam, torch.nn.utils.clip_grad_norm_
+    b200gs.install("fake_gs2", optimizer=True)
+    try:
+        assert torch.optim.Adam is b200gs.FusedAdam and torch.nn.utils.clip_grad_norm_ is b200gs.clip_grad_norm_
+    finally:
+        b200gs.uninstall()
+    assert torch.optim.Adam is adam and torch.nn.utils.clip_grad_norm_ is clip
