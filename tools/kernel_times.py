@@ -30,8 +30,8 @@ def frame(i, p=sc):
 
 
 def collect():
-    ms, calls = (ctypes.c_float * 16)(), (ctypes.c_int32 * 16)()
-    nreg = lib.b200gs_profile_collect(ms, calls, 16)
+    ms, calls = (ctypes.c_float * 32)(), (ctypes.c_int32 * 32)()
+    nreg = lib.b200gs_profile_collect(ms, calls, 32)
     return {lib.b200gs_profile_region_name(r).decode(): round(ms[r] / calls[r] * 1e3, 1) for r in range(nreg) if calls[r]}
 
 

@@ -22,14 +22,21 @@ with torch.no_grad():
         col = b200gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
         img = b200gs.render(sc["pos"], col, sc["opacity_raw"], sigma, c2w, H, W, cams[i]["fx"], cams[i]["fy"], cams[i]["cx"],
                             cams[i]["cy"])
+# full training iterations (scripts/train.py:463-538): render + L1/SSIM loss + backward + clip + Adam
 leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
-w = torch.rand(H, W, 3, device="cuda")
+target = torch.rand(H, W, 3, device="cuda")
+lrs = {"pos": 1.6e-6, "opacity_raw": 0.05, "f_dc": 2.5e-3, "f_rest": 1.25e-4, "scale_raw": 5e-3, "q_raw": 1e-3}
+opt = b200gs.FusedAdam([{"params": [leaves[k]], "lr": lrs[k]} for k in leaves], lr=1e-3, eps=1e-15)
 for i in range(steps):
     c2w = cams[i]["c2w"].cuda()
+    opt.zero_grad(set_to_none=True)
     sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
     col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
     img = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sg, c2w, H, W, cams[i]["fx"], cams[i]["fy"], cams[i]["cx"],
                         cams[i]["cy"])
-    (img * w).sum().backward()
+    loss, _ = b200gs.compute_loss_tensors(img, target)
+    loss.backward()
+    b200gs.clip_grad_norm_(leaves["pos"], 1.0)
+    opt.step()
 torch.cuda.synchronize()
 print("ok", float(img.mean()))
