@@ -72,6 +72,7 @@ SYMBOLS = {
                                        c_size_t, c_int32, c_void_p, c_void_p]),
     "b200gs_l1_ssim_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_double, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p]),
+    "b200gs_image_to_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200gs_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_double, c_double, c_double, c_void_p]),
     "b200gs_clip_workspace_bytes": (c_size_t, [ctypes.c_int64]),
     "b200gs_clip_grad_norm": (c_int, [c_void_p, ctypes.c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -152,6 +152,20 @@ __global__ void export_kernel(int n, const float4* rec0, const float4* rec1, con
     tiles_out[i] = !vis ? -1 : (super_touched[i] ? (int32_t)(((r.x >> 16) - (r.x & 0xFFFF) + 1) * ((r.y >> 16) - (r.y & 0xFFFF) + 1)) : 0);
 }
 
+// fp32 [0,1] image -> uint8, exactly what the reference scripts do on the host after the download:
+// (img.cpu().numpy() * 255).astype(np.uint8)  (render_trained.py:357, inference.py:117) - multiply in fp32, truncate.
+__global__ void image_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n && (reinterpret_cast<uintptr_t>(img) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(img + i);
+    uchar4 o;
+    o.x = (uint8_t)(v.x * 255.f); o.y = (uint8_t)(v.y * 255.f); o.z = (uint8_t)(v.z * 255.f); o.w = (uint8_t)(v.w * 255.f);
+    *reinterpret_cast<uchar4*>(out + i) = o;
+  } else {
+    for (size_t k = i; k < n && k < i + 4; ++k) out[k] = (uint8_t)(img[k] * 255.f);
+  }
+}
+
 __global__ void copy_u32_kernel(const uint32_t* src, int32_t* dst, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (int32_t)src[i];
@@ -261,6 +275,17 @@ int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_im
   cudaStream_t s = (cudaStream_t)stream;
   PCU(R_LOSS_BWD, 1, gs::launch_l1_ssim_bwd(pred, target, n_img, H, W, (float)lambda_l1, (float)lambda_ssim, workspace,
                                             grad_total, grad_pred, s));
+  return B200GS_OK;
+}
+
+int b200gs_image_to_u8(const float* image, uint8_t* out, size_t numel, void* stream) {
+  if (numel > 0 && (!image || !out)) return fail(B200GS_ERR_ARG, "image_to_u8: null");
+  if (numel == 0) return B200GS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t threads = (numel + 3) / 4;
+  image_to_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(image, out, numel);
+  CU(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return B200GS_OK;
 }
 

@@ -311,6 +311,24 @@ def run_b200gs(args):
             e2e_step(Wm + i)
         barrier()
         s_e2e = max_over_ranks(time.perf_counter() - t0)
+        # the same loop delivering uint8 frames (b200gs.to_uint8: the conversion the reference scripts do on the
+        # host, render_trained.py:357, done on the device): 3 B/pixel over PCIe instead of 12
+        u8_pin = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(n_streams)]
+
+        def e2e_u8_step(i):
+            st = streams[i % n_streams]
+            st.synchronize()
+            with torch.cuda.stream(st):
+                c2w = c2w_pin[view_of(i)].to(dev, non_blocking=True)
+                u8_pin[i % n_streams].copy_(b200gs.to_uint8(render_step(c2w)), non_blocking=True)
+        for i in range(Wm):
+            e2e_u8_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_u8_step(Wm + i)
+        barrier()
+        s_e2e_u8 = max_over_ranks(time.perf_counter() - t0)
 
     # ---- train: fwd + bwd (+ all-reduce) --------------------------------------------------------------------
     leaves = {k: sc[k].clone().requires_grad_(True) for k in PARAMS}
@@ -525,6 +543,9 @@ def run_b200gs(args):
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,
                 "api": "b200gs.evaluate_sh + b200gs.render (pose from pinned host memory, image to pinned host memory; "
                        f"{n_streams} frames in flight)"},
+        "e2e_u8_frames": {"value": world * K / s_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": 64,
+                          "d2h_bytes_per_step": H * W * 3,
+                          "api": "the same, frames delivered as uint8 through b200gs.to_uint8 (device-side frame sink)"},
         "e2e_host_buffers": {"value": host_fps, "unit": "frames/s", "h2d_bytes_per_step": 236 * N + 64,
                              "d2h_bytes_per_step": H * W * 12,
                              "api": "b200gs_render_host (C ABI, every parameter array uploaded from host memory each call)"},

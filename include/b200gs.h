@@ -187,6 +187,11 @@ int b200gs_l1_ssim_backward(const float* pred, const float* target, int32_t n_im
                             double lambda_l1, double lambda_ssim, const void* workspace, size_t workspace_bytes,
                             const float* grad_total, float* grad_pred, void* stream);
 
+/* Frame sink (scripts/render_trained.py:357, scripts/inference.py:117): the reference downloads the fp32 image
+ * (12 B/pixel) and converts it on the host with (img * 255).astype(uint8); this does the same conversion (fp32
+ * multiply, truncation) on the device so that 3 B/pixel cross PCIe.  image: [numel] fp32 in [0,1]; out: [numel] u8. */
+int b200gs_image_to_u8(const float* image, uint8_t* out, size_t numel, void* stream);
+
 /* scripts/train.py:394-401,538  torch.optim.Adam over the six parameter groups (per-group lr, eps = 1e-15):
  * one launch updates every tensor of the table in place (param, exp_avg, exp_avg_sq), reading each array
  * once.  Arithmetic of torch/optim/adam.py with weight_decay = 0, amsgrad = False; `step` is the 1-based

@@ -377,3 +377,18 @@ def test_speculative_capacity_overflow_is_redone_with_exact_buffers(gs):
         assert torch.equal(img3, ref)
     finally:
         ops._high_water[dev] = max(saved, ops._high_water.get(dev, 0))
+
+
+def test_frame_sink_matches_the_reference_host_conversion(gs):
+    """render_trained.py:357 / inference.py:117: (img.cpu().numpy() * 255).astype(np.uint8)."""
+    g = torch.Generator().manual_seed(5)
+    for shape in [(1080, 1920, 3), (97, 71, 3), (5, 7, 3), (1, 1, 3)]:
+        img = torch.rand(*shape, generator=g)
+        img.view(-1)[:: 7] = 1.0
+        img.view(-1)[3:: 11] = 0.0
+        edges = (torch.arange(img.numel()) % 256).float().div(255.0)          # values sitting on the u8 grid
+        img.view(-1)[1:: 5] = edges[1:: 5]
+        want = (img.numpy() * 255).astype(np.uint8)
+        got = gs.to_uint8(img.cuda())
+        assert got.dtype == torch.uint8 and got.shape == img.shape
+        assert np.array_equal(got.cpu().numpy(), want)
