@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_step_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = k * kAdamThreads + threadIdx.x;
-      p[k] = p4[i]; g[k] = ld_stream_f4(g4 + i); m[k] = m4[i]; v[k] = v4[i];
+      p[k] = __ldcs(p4 + i); g[k] = __ldcs(g4 + i); m[k] = __ldcs(m4 + i); v[k] = __ldcs(v4 + i);   // touched once per step
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_step_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = k * kAdamThreads + threadIdx.x;
-      p4[i] = p[k]; m4[i] = m[k]; v4[i] = v[k];
+      __stcs(p4 + i, p[k]); __stcs(m4 + i, m[k]); __stcs(v4 + i, v[k]);
     }
   } else {
     for (long long i = base + threadIdx.x; i < end; i += kAdamThreads) {
