@@ -6,12 +6,12 @@ Drop-in for the render path of ashu1069/3D-Gaussian-Splatting-for-Novel-View-Syn
 `install()` to rebind them inside an imported reference package, `python -m b200gs.run <script>` to run
 a reference script unchanged on top of it.
 """
-from .api import build_sigma_from_params, evaluate_sh, render, to_uint8
+from .api import RenderPipeline, build_sigma_from_params, evaluate_sh, render, to_uint8
 from .losses import compute_loss, compute_loss_tensors, l1_loss, ssim_loss
 from .install import install, uninstall
 from .optim import FusedAdam, clip_grad_norm_
 from ._lib import B200GSError, LIB_PATH, load as load_library
 
 __all__ = ["build_sigma_from_params", "evaluate_sh", "render", "compute_loss", "compute_loss_tensors", "l1_loss",
-           "ssim_loss", "to_uint8", "FusedAdam", "clip_grad_norm_", "install", "uninstall", "B200GSError",
+           "ssim_loss", "to_uint8", "RenderPipeline", "FusedAdam", "clip_grad_norm_", "install", "uninstall", "B200GSError",
            "LIB_PATH", "load_library"]

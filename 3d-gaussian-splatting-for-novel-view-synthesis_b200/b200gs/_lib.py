@@ -65,6 +65,8 @@ SYMBOLS = {
                                         c_void_p, c_void_p, c_void_p]),
     "b200gs_render_rasterize_ev": (c_int, [POINTER(Camera), c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_uint32,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200gs_render_rasterize_split": (c_int, [POINTER(Camera), c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_uint32,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200gs_render_backward": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, c_void_p, c_size_t,
                                        c_uint32, c_void_p, POINTER(Grads), c_void_p]),
     "b200gs_loss_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),

@@ -153,6 +153,16 @@ def render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
 
     `tile_rows=(begin, end)` (keyword-only extension) renders only that band of 16-pixel tile rows; the
     rest of the image is zero (tile-row sharding of large frames across GPUs)."""
+    args, strict = _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, far, pix_guard, T, min_conis,
+                            chi_square_clip, alpha_max, alpha_cutoff, tile_rows)
+    image = ops._Rasterize.apply(*args, strict)
+    return image if image.dtype == pos.dtype else image.to(pos.dtype)
+
+
+def _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, far, pix_guard, T, min_conis,
+             chi_square_clip, alpha_max, alpha_cutoff, tile_rows):
+    """Arguments of render() -> (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg), strict:
+    the fused route (raw parameters) when the tags of `sigma` / `color` resolve, the tensors themselves otherwise."""
     ops._require_cuda(pos, "pos")
     H, W = int(H), int(W)           # callers pass Python ints, 0-dim tensors (train.py:499) or floats
     cfg = ops.RenderConfig(H=H, W=W, fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), near=float(near),
@@ -173,11 +183,8 @@ def render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
         if got is not None and got[2] is pos and (got[3] is c2w or torch.equal(got[3].to(c2w_d.device), c2w_d)):
             f_dc, f_rest = got[0], got[1]
     strict = os.environ.get("B200GS_STRICT_OFFSCREEN", "1") != "0"
-    image = ops._Rasterize.apply(pos, opacity_raw,
-                                 scale_raw, q_raw, None if scale_raw is not None else _real(sigma),
-                                 f_dc, f_rest, None if f_dc is not None else _real(color),
-                                 c2w_d, cfg, strict)
-    return image if image.dtype == pos.dtype else image.to(pos.dtype)
+    return (pos, opacity_raw, scale_raw, q_raw, None if scale_raw is not None else _real(sigma),
+            f_dc, f_rest, None if f_dc is not None else _real(color), c2w_d, cfg), strict
 
 
 def to_uint8(image: torch.Tensor) -> torch.Tensor:
@@ -192,3 +199,94 @@ def to_uint8(image: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.load().b200gs_image_to_u8(ops._ptr(img), ops._ptr(out), img.numel(), ops._stream(img.device)),
                    "image_to_u8")
     return out
+
+
+class RenderPipeline:
+    """Software pipelining of a SEQUENCE of independent frames (an orbit render: scripts/render_trained.py:333-358,
+    scripts/inference.py:100-119) on one GPU.
+
+    A frame is two halves with opposite bottlenecks: project + binning (one HBM-bound kernel and seven small,
+    latency-bound ones) and the blend (FP32-issue bound, nearly no HBM traffic).  Frames are queued with the first
+    half on a high-priority stream and the blend on a second stream, so the binning of frame i+1 runs while frame i
+    is being blended, and the host never waits for a frame it has just queued:
+
+        pipe = b200gs.RenderPipeline()
+        t = pipe.submit(pos, colors, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy)     # returns at once
+        ...                                                                              # submit the next frame(s)
+        img = pipe.result(t)        # waits for that frame's COUNTERS only (re-rasterizes if the lists overflowed)
+
+    `render()` = submit + result.  Same arguments and image as `b200gs.render` (forward only).  The image is valid
+    in `pipe.blend_stream` order: consume it under `torch.cuda.stream(pipe.blend_stream)` or after
+    `pipe.synchronize()`.  The Gaussian parameters must not be modified while frames are in flight."""
+
+    MAX_IN_FLIGHT = 4
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        _, high = torch.cuda.Stream.priority_range()
+        self.front_stream = torch.cuda.Stream(self.device, priority=high)
+        self.blend_stream = torch.cuda.Stream(self.device)
+        self._open = []                               # submitted, not yet checked (oldest first)
+        torch.cuda.synchronize(self.device)          # everything created so far is visible to both streams
+
+    def submit(self, pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near=0.01, far=100.0, pix_guard=32,
+               T=16, min_conis=1e-6, chi_square_clip=6.25, alpha_max=0.99, alpha_cutoff=1 / 128.):
+        while len(self._open) >= self.MAX_IN_FLIGHT:
+            self._check(self._open[0])
+        prev = ops._blend_stream.get(self.device.index)
+        ops._blend_stream[self.device.index] = self.blend_stream
+        try:
+            with torch.no_grad(), torch.cuda.stream(self.front_stream):
+                c2w_d = c2w.to(self.device, non_blocking=True)
+                args, strict = _resolve(pos, color, opacity_raw, sigma, c2w_d, H, W, fx, fy, cx, cy, near, far, pix_guard,
+                                        T, min_conis, chi_square_clip, alpha_max, alpha_cutoff, None)
+                image, frame = ops.launch_frame(*args)
+        finally:
+            if prev is None:
+                ops._blend_stream.pop(self.device.index, None)
+            else:
+                ops._blend_stream[self.device.index] = prev
+        done = torch.cuda.Event()
+        done.record(self.blend_stream)                # the frame's blend has been queued: completion marker
+        ticket = [image, frame, strict, pos.dtype, done]
+        self._open.append(ticket)
+        return ticket
+
+    def _check(self, ticket):
+        idx = next((i for i, t in enumerate(self._open) if t is ticket), None)
+        if idx is None:
+            return
+        del self._open[idx]
+        prev = ops._blend_stream.get(self.device.index)
+        ops._blend_stream[self.device.index] = self.blend_stream
+        try:
+            if ticket[1].finish():                    # rasterized again: the completion marker moves
+                ticket[4] = torch.cuda.Event()
+                ticket[4].record(self.blend_stream)
+        finally:
+            if prev is None:
+                ops._blend_stream.pop(self.device.index, None)
+            else:
+                ops._blend_stream[self.device.index] = prev
+
+    def done_event(self, ticket):
+        """CUDA event that completes when the frame's image is ready (call after `result`): lets a consumer on
+        another stream (e.g. a device-to-host copy) wait for exactly this frame, not for the blend stream's tail."""
+        self._check(ticket)
+        return ticket[4]
+
+    def result(self, ticket):
+        self._check(ticket)
+        image, frame, strict, dtype = ticket[:4]
+        if strict and frame.n_in_frustum > 0 and frame.n_visible == 0:
+            raise Exception("All projected points are off-screen")      # render.py:235-236
+        return image if image.dtype == dtype else image.to(dtype)
+
+    def render(self, *args, **kwargs):
+        return self.result(self.submit(*args, **kwargs))
+
+    def synchronize(self):
+        for t in list(self._open):
+            self._check(t)
+        self.front_stream.synchronize()
+        self.blend_stream.synchronize()

@@ -85,6 +85,28 @@ def _stats_buffer(device, stream_handle: int):
     return ent
 
 
+_stats_slots = {}
+_STATS_RING = 8          # frames whose statistics may be outstanding per (device, stream): RenderPipeline keeps <= 4
+
+
+def _stats_slot(device, stream):
+    """Next (numpy view, data pointer, torch event, raw cudaEvent_t) of this stream's ring of pinned statistics
+    buffers: a frame's counters stay readable until _STATS_RING - 1 later frames have been launched."""
+    key = (device.index, stream.cuda_stream)
+    ring = _stats_slots.get(key)
+    if ring is None:
+        bufs = torch.zeros(_STATS_RING, 16, dtype=torch.int32).pin_memory()
+        slots = []
+        for i in range(_STATS_RING):
+            ev = torch.cuda.Event()
+            ev.record(stream)                   # torch creates the CUDA event lazily, on first record
+            slots.append((bufs[i].numpy(), ctypes.c_void_p(bufs[i].data_ptr()), ev, ctypes.c_void_p(ev.cuda_event)))
+        ring = [bufs, slots, 0]
+        _stats_slots[key] = ring
+    ring[2] = (ring[2] + 1) % _STATS_RING
+    return ring[1][ring[2]]
+
+
 _stats_events = {}
 
 
@@ -121,6 +143,7 @@ def _sizes(lib, n: int, H: int, W: int, capacity: int):
 # and launch everything without a mid-frame sync; the overflow flag is checked when the frame's stats
 # are read (end of frame) and the frame is re-rasterized with exact buffers if it did not fit.
 _high_water = {}
+_blend_stream = {}       # device index -> torch stream the blend kernels go to (set by api.RenderPipeline)
 
 
 class Frame:
@@ -137,9 +160,18 @@ class Frame:
         self.n_in_frustum = 0
         self.n_super = 0
         self.overflow = False
+        self._unchecked = None
 
     # -- forward ----------------------------------------------------------------------------------------
     def render(self, mode: Optional[str] = None) -> torch.Tensor:
+        image = self.launch(mode)
+        self.finish()
+        return image
+
+    def launch(self, mode: Optional[str] = None) -> torch.Tensor:
+        """Queues the frame.  In speculative mode nothing is waited for: `finish()` must be called (before
+        _STATS_RING - 1 further frames are launched on this stream) to learn whether the frame fitted its buffers
+        and to redo it if it did not; the image is only trustworthy after that."""
         lib = _lib.load()
         dev = self.device
         n = int(self.g.n)
@@ -149,23 +181,17 @@ class Frame:
         st = ctypes.c_void_p(stream.cuda_stream)
         frame_bytes, _ = _sizes(lib, n, H, W, 0)
         self.frame_ws = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
-        _, stats_np, stats_ptr = _stats_buffer(dev, stream.cuda_stream)
+        stats_np, stats_ptr, ev, ev_ptr = _stats_slot(dev, stream)
         image = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
                                              frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
+        self._unchecked = None
         if spec_cap:
-            # the whole frame is queued; the host only waits until the counters are final (end of the binning
-            # scan), not for the sort / split / blend kernels behind it, so the next frame can be queued
-            # while this one is still running
-            ev, ev_ptr = _stats_event(dev, stream)
+            # the whole frame is queued; the host will only wait until the counters are final (end of the binning
+            # scan), not for the sort / split / blend kernels behind it
             self._rasterize(lib, n, H, W, spec_cap, image, stats_ptr, st, ev_ptr)
-            ev.synchronize()
-            self._read_stats(stats_np)
-            if self.n_isect > spec_cap or self.overflow:     # did not fit: redo with exact buffers
-                self._rasterize(lib, n, H, W, self._grow(self.n_isect), image, stats_ptr, st)
-                stream.synchronize()
-                self._read_stats(stats_np)
+            self._unchecked = (stream, st, stats_np, stats_ptr, ev, spec_cap, image)
         else:
             stream.synchronize()
             self._read_stats(stats_np)
@@ -173,6 +199,25 @@ class Frame:
                             image, stats_ptr, st)
             self._stats_pending = (stream, stats_np)     # n_super is only known after rasterize
         return image
+
+    def finish(self):
+        """Speculative frames: wait for the frame's counters (NOT for the frame) and rasterize again with exact
+        buffers if it did not fit (returns True in that case)."""
+        if self._unchecked is None:
+            return False
+        stream, st, stats_np, stats_ptr, ev, spec_cap, image = self._unchecked
+        self._unchecked = None
+        ev.synchronize()
+        self._read_stats(stats_np)
+        if self.n_isect > spec_cap or self.overflow:         # did not fit: redo with exact buffers
+            lib = _lib.load()
+            with torch.cuda.stream(stream):
+                self._rasterize(lib, int(self.g.n), int(self.cfg.H), int(self.cfg.W), self._grow(self.n_isect), image,
+                                stats_ptr, st)
+            stream.synchronize()
+            self._read_stats(stats_np)
+            return True
+        return False
 
     def refresh_stats(self):
         """Counters written by the rasterize phase (n_super); synchronises the stream."""
@@ -197,10 +242,21 @@ class Frame:
         frame_bytes, isect_bytes = _sizes(lib, n, H, W, capacity)
         self.capacity = capacity
         self.isect_ws = torch.empty(isect_bytes, dtype=torch.uint8, device=self.device)
-        _lib.check(lib.b200gs_render_rasterize_ev(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
-                                                  _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr,
-                                                  stats_event, st),
-                   "render_rasterize")
+        blend = _blend_stream.get(self.device.index)
+        if blend is None:
+            _lib.check(lib.b200gs_render_rasterize_ev(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
+                                                      _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr,
+                                                      stats_event, st),
+                       "render_rasterize")
+        else:
+            # frame pipelining (RenderPipeline): the blend runs on its own stream; the buffers were allocated in the
+            # binning stream's pool, so the allocator must know about their second user
+            for t in (self.frame_ws, self.isect_ws, image):
+                t.record_stream(blend)
+            _lib.check(lib.b200gs_render_rasterize_split(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
+                                                         _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image),
+                                                         stats_ptr, stats_event, st, ctypes.c_void_p(blend.cuda_stream)),
+                       "render_rasterize_split")
 
     # -- backward ---------------------------------------------------------------------------------------
     def backward(self, grad_image: torch.Tensor, grads: Grads):
@@ -250,6 +306,16 @@ def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
                   sigma=None if sg_ is None else sg_.data_ptr(), f_dc=None if dc_ is None else dc_.data_ptr(),
                   f_rest=None if fr_ is None else fr_.data_ptr(), color=None if col_ is None else col_.data_ptr())
     return g, keep
+
+
+def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg):
+    """Forward-only frame without autograd bookkeeping (RenderPipeline): returns (image, Frame); the caller must
+    call Frame.finish() before trusting the image."""
+    g, keep = _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)
+    with torch.cuda.device(pos.device):
+        frame = Frame(g, keep, cfg, c2w, pos.device)
+        image = frame.launch("speculative")
+    return image, frame
 
 
 class _Rasterize(torch.autograd.Function):

@@ -355,6 +355,14 @@ int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws,
 int b200gs_render_rasterize_ev(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
                                size_t isect_bytes, uint32_t isect_capacity, float* image_out,
                                b200gs_frame_stats* stats_host, void* stats_event, void* stream) {
+  return b200gs_render_rasterize_split(cam, n, frame_ws, frame_bytes, isect_ws, isect_bytes, isect_capacity, image_out,
+                                       stats_host, stats_event, stream, stream);
+}
+
+int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
+                                  size_t isect_bytes, uint32_t isect_capacity, float* image_out,
+                                  b200gs_frame_stats* stats_host, void* stats_event, void* stream,
+                                  void* blend_stream) {
   gs::RenderParams rp;
   int rc = make_params(cam, rp);
   if (rc) return rc;
@@ -398,6 +406,16 @@ int b200gs_render_rasterize_ev(const b200gs_camera* cam, int32_t n, void* frame_
   }
   // pixels of tiles outside this rank's band are not touched; the whole image is zeroed first so that
   // "pixels in empty tiles stay 0" (render.py:318) also holds for bands
+  // frame pipelining: the blend may run on another stream (ordered after the binning by an event), so that the
+  // binning of the NEXT frame - queued on `stream` right away - overlaps it
+  if (blend_stream != stream) {
+    cudaEvent_t binned;
+    CU(cudaEventCreateWithFlags(&binned, cudaEventDisableTiming));
+    CU(cudaEventRecord(binned, s));
+    CU(cudaStreamWaitEvent((cudaStream_t)blend_stream, binned, 0));
+    CU(cudaEventDestroy(binned));      // released once the recorded work completes
+    s = (cudaStream_t)blend_stream;
+  }
   if (rp.row_begin == 0 && rp.row_end == rp.tiles_y) {
     // every pixel is written by the blend kernel
   } else {

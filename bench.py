@@ -291,42 +291,118 @@ def run_b200gs(args):
         sigma = b200gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
         torch.cuda.synchronize()
         ms_render_1s, _ = timed(lambda i: render_step(c2w_dev[view_of(i)]), K, Wm)
-        ms_render, launches_render = timed_streams(lambda i: render_step(c2w_dev[view_of(i)]), K, Wm)
+        ms_render_2s, _ = timed_streams(lambda i: render_step(c2w_dev[view_of(i)]), K, Wm)
+        # ---- the headline: frames software-pipelined by b200gs.RenderPipeline - project + binning of frame i+1 on a
+        #      high-priority stream while frame i is blended on a second stream (an orbit render; frames independent)
+        pipe = b200gs.RenderPipeline(dev)
+
+        def pipe_submit(c2w):
+            colors = b200gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
+            return pipe.submit(sc["pos"], colors, sc["opacity_raw"], sigma, c2w, H, W, intr["fx"], intr["fy"],
+                               intr["cx"], intr["cy"])
+        pending = []
+
+        def pipe_step(c2w, deliver=None):
+            """Queues a frame and collects the one queued before it (one frame of lag keeps the host off the
+            critical path); `deliver(image, done_event)` consumes a finished frame."""
+            pending.append(pipe_submit(c2w))
+            if len(pending) > 1:
+                t = pending.pop(0)
+                img = pipe.result(t)
+                if deliver is not None:
+                    deliver(img, pipe.done_event(t))
+
+        def pipe_flush(deliver=None):
+            while pending:
+                t = pending.pop(0)
+                img = pipe.result(t)
+                if deliver is not None:
+                    deliver(img, pipe.done_event(t))
+            pipe.synchronize()
+
+        def timed_pipe(steps, warm):
+            for i in range(warm):
+                pipe_step(c2w_dev[view_of(i)])
+            pipe_flush()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = lib.b200gs_kernel_launch_count()
+            main = torch.cuda.current_stream(dev)
+            e0.record(main)
+            pipe.front_stream.wait_event(e0)
+            pipe.blend_stream.wait_event(e0)
+            for i in range(steps):
+                pipe_step(c2w_dev[view_of(warm + i)])
+            pipe_flush()
+            main.wait_stream(pipe.front_stream)
+            main.wait_stream(pipe.blend_stream)
+            e1.record(main)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)), lib.b200gs_kernel_launch_count() - l0
+        ms_render, launches_render = timed_pipe(K, Wm)
         # ---- render e2e: pose from pinned host memory in, image to pinned host memory out, every step; the
         #      D2H copy of a frame overlaps the next frame on the other stream (one pinned image per stream) ----
         img_pin = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(n_streams)]
 
-        def e2e_step(i):
-            st = streams[i % n_streams]
-            st.synchronize()                 # the frame that used this stream's pinned image has been delivered
-            with torch.cuda.stream(st):
+        # the D2H copy of a finished frame runs on a copy stream, waiting for exactly that frame (done_event); a ring
+        # of pinned images, each reused once its copy has completed
+        copy_stream = torch.cuda.Stream(dev)
+        n_ring = 3
+        img_pin = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(n_ring)]
+        copy_done = [torch.cuda.Event() for _ in range(n_ring)]
+        for e in copy_done:
+            e.record(copy_stream)
+        delivered = [0]
+
+        def deliver_f32(img, done):
+            k = delivered[0] % n_ring
+            delivered[0] += 1
+            copy_done[k].synchronize()                   # the frame that used this pinned image has been delivered
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                img.record_stream(copy_stream)
+                img_pin[k].copy_(img, non_blocking=True)
+                copy_done[k].record(copy_stream)
+
+        def e2e_step(i, deliver):
+            with torch.cuda.stream(pipe.front_stream):
                 c2w = c2w_pin[view_of(i)].to(dev, non_blocking=True)
-                img = render_step(c2w)
-                img_pin[i % n_streams].copy_(img, non_blocking=True)
+            pipe_step(c2w, deliver)
         for i in range(Wm):
-            e2e_step(i)
+            e2e_step(i, deliver_f32)
+        pipe_flush(deliver_f32)
+        copy_stream.synchronize()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            e2e_step(Wm + i)
+            e2e_step(Wm + i, deliver_f32)
+        pipe_flush(deliver_f32)
+        copy_stream.synchronize()
         barrier()
         s_e2e = max_over_ranks(time.perf_counter() - t0)
         # the same loop delivering uint8 frames (b200gs.to_uint8: the conversion the reference scripts do on the
         # host, render_trained.py:357, done on the device): 3 B/pixel over PCIe instead of 12
-        u8_pin = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(n_streams)]
+        u8_pin = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(n_ring)]
 
-        def e2e_u8_step(i):
-            st = streams[i % n_streams]
-            st.synchronize()
-            with torch.cuda.stream(st):
-                c2w = c2w_pin[view_of(i)].to(dev, non_blocking=True)
-                u8_pin[i % n_streams].copy_(b200gs.to_uint8(render_step(c2w)), non_blocking=True)
+        def deliver_u8(img, done):
+            k = delivered[0] % n_ring
+            delivered[0] += 1
+            copy_done[k].synchronize()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                img.record_stream(copy_stream)
+                u8_pin[k].copy_(b200gs.to_uint8(img), non_blocking=True)
+                copy_done[k].record(copy_stream)
         for i in range(Wm):
-            e2e_u8_step(i)
+            e2e_step(i, deliver_u8)
+        pipe_flush(deliver_u8)
+        copy_stream.synchronize()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            e2e_u8_step(Wm + i)
+            e2e_step(Wm + i, deliver_u8)
+        pipe_flush(deliver_u8)
+        copy_stream.synchronize()
         barrier()
         s_e2e_u8 = max_over_ranks(time.perf_counter() - t0)
 
@@ -522,12 +598,15 @@ def run_b200gs(args):
         "ms_per_step": ms_render / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I, "super_pairs_view0": S,
-                   "parallelism": f"frames/views sharded round-robin over {world} rank(s), {n_streams} frame(s) in flight "
-                                  f"per rank (one CUDA stream each); Gaussians replicated",
+                   "parallelism": f"frames/views sharded round-robin over {world} rank(s); per rank frames are software-"
+                                  "pipelined by b200gs.RenderPipeline (project + binning of frame i+1 on a high-priority "
+                                  "stream while frame i is blended on a second stream); Gaussians replicated",
                    "capacity_mode": os.environ.get("B200GS_CAPACITY_MODE"),
                    "l2_policy": "inputs larger than L2: every step streams 236 MB of parameters (L2 = 126 MB) and a different view"},
         "single_stream": {"value": world * K / (ms_render_1s * 1e-3), "unit": "frames/s", "ms_per_step": ms_render_1s / K,
                           "note": "one frame at a time on one stream (frame latency)"},
+        "two_streams": {"value": world * K / (ms_render_2s * 1e-3), "unit": "frames/s",
+                        "note": "whole frames alternating on two equal-priority streams"},
         "train": {"value": K / (ms_train * 1e-3), "unit": "it/s", "views_per_s": world * K / (ms_train * 1e-3),
                   "ms_per_step": ms_train / K,
                   "step": "build_sigma + evaluate_sh + render + weighted-sum loss + backward" +
@@ -541,8 +620,8 @@ def run_b200gs(args):
                   "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
                           "d2h_bytes_per_step": 4}},
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,
-                "api": "b200gs.evaluate_sh + b200gs.render (pose from pinned host memory, image to pinned host memory; "
-                       f"{n_streams} frames in flight)"},
+                "api": "b200gs.evaluate_sh + b200gs.RenderPipeline.render (pose from pinned host memory, image to "
+                       "pinned host memory, two pinned images in rotation)"},
         "e2e_u8_frames": {"value": world * K / s_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": 64,
                           "d2h_bytes_per_step": H * W * 3,
                           "api": "the same, frames delivered as uint8 through b200gs.to_uint8 (device-side frame sink)"},

@@ -145,6 +145,16 @@ int b200gs_render_rasterize_ev(const b200gs_camera* cam, int32_t n, void* frame_
                                float* image_out, b200gs_frame_stats* stats_host, void* stats_event,
                                void* stream);
 
+/* Same again with the blend on its own stream: binning runs on `stream`, the blend kernel on `blend_stream`, ordered
+ * by an event.  A host rendering a sequence of independent frames (an orbit: scripts/render_trained.py:333-358) queues
+ * the next frame's project + binning on `stream` (ideally a high-priority stream) while this frame's blend is still
+ * running on `blend_stream`; image_out is valid in `blend_stream` order.  The workspaces must stay untouched until
+ * the blend has finished. */
+int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes,
+                                  void* isect_ws, size_t isect_bytes, uint32_t isect_capacity,
+                                  float* image_out, b200gs_frame_stats* stats_host, void* stats_event,
+                                  void* stream, void* blend_stream);
+
 /* Backward of project+rasterize (scripts/train.py:530): grad_image [H,W,3] -> b200gs_grads.
  * Needs the frame/isect workspaces exactly as the forward left them. */
 int b200gs_render_backward(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws,
