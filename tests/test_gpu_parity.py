@@ -445,3 +445,36 @@ def test_render_pipeline_gives_the_same_frames(gs):
         assert torch.equal(redo, want[0])
     for i, g in enumerate(got):
         assert torch.equal(g, want[i % len(want)]), i
+
+
+@pytest.mark.parametrize("kw", [
+    dict(near=0.8, far=3.4, pix_guard=8, chi_square_clip=4.0, alpha_max=0.9, alpha_cutoff=1 / 64., min_conis=1e-4),
+    dict(near=0.01, far=100.0, pix_guard=64, chi_square_clip=9.21, alpha_max=0.999, alpha_cutoff=1 / 255.),   # README values
+    dict(chi_square_clip=1.5, alpha_cutoff=0.2),            # cutoff gate tighter than the chi-square gate for most splats
+    dict(alpha_cutoff=0.0),                                 # every alpha passes the cutoff
+])
+def test_non_default_render_arguments_against_live_oracle(gs, kw):
+    """The keyword arguments of render.py:62-64 other than T: forward image and all six gradients against the oracle
+    (the blend's single-compare gate, the frustum test and the pre-cull all depend on them)."""
+    from oracle import gs_oracle as O
+    sc = O.make_scene(9_000, seed=17, log_scale=-3.4, unique_depth=True)
+    cam = O.make_camera(200, 136, view=3, n_views=8)
+    w = torch.rand(136, 200, 3, generator=torch.Generator().manual_seed(2))
+    ref = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    img_ref = O.render_from_params(ref["pos"], ref["scale_raw"], ref["q_raw"], ref["opacity_raw"], ref["f_dc"],
+                                   ref["f_rest"], cam["c2w"], 136, 200, cam["fx"], cam["fy"], cam["cx"], cam["cy"], **kw)
+    (img_ref * w).sum().backward()
+    mine = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    c2w = cam["c2w"].cuda()
+    sigma = gs.build_sigma_from_params(mine["scale_raw"], mine["q_raw"])
+    color = gs.evaluate_sh(mine["f_dc"], mine["f_rest"], mine["pos"], c2w)
+    img = gs.render(mine["pos"], color, mine["opacity_raw"], sigma, c2w, 136, 200, cam["fx"], cam["fy"], cam["cx"],
+                    cam["cy"], **kw)
+    (img * w.cuda()).sum().backward()
+    d = (img.detach().cpu() - img_ref.detach()).abs()
+    n_bad = int((d > IMG_TOL).sum())
+    assert n_bad <= 3, (n_bad, float(d.max()))
+    assert float(img_ref.max()) > 0.05                       # the case renders something
+    for k in PARAMS:
+        err = grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy())
+        assert err <= 3 * GRAD_TOL if n_bad else err <= GRAD_TOL, (k, err, n_bad)
