@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_fwd_kernel(const float* 
                                                                    float lambda_ssim, double inv_count) {
   __shared__ float sx[kLossIn][kLossIn + 1];
   __shared__ float sy[kLossIn][kLossIn + 1];
-  __shared__ float sh[5][kLossIn][kLossTile];      // horizontally filtered x, y, xx, yy, xy
+  __shared__ float sh[5][kLossIn][kLossTile + 1];  // horizontally filtered x, y, xx, yy, xy (row stride 33 words:
+                                                   // conflict-free for row-per-lane writes and column-per-lane reads)
   __shared__ float s_red[2][kLossThreads / 32];
   __shared__ bool s_last;
   const int x0 = blockIdx.x * kLossTile, y0 = blockIdx.y * kLossTile, b = blockIdx.z;
@@ -95,32 +96,62 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_fwd_kernel(const float* 
     load_tile_hwc(pred + img_off, H, W, c, x0, y0, sx);
     load_tile_hwc(target + img_off, H, W, c, x0, y0, sy);
     __syncthreads();
-    for (int p = tid; p < kLossIn * kLossTile; p += kLossThreads) {
-      const int r = p >> 5, q = p & 31;
-      float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+    // horizontal pass: one work item = 4 consecutive outputs of one row, computed from a sliding window of 14
+    // inputs (each input is loaded once and feeds the up to 4 outputs it belongs to); lanes take consecutive rows
+    for (int item = tid; item < kLossIn * (kLossTile / 4); item += kLossThreads) {
+      const int r = item % kLossIn, q0 = (item / kLossIn) * 4;
+      float acc[4][5];
 #pragma unroll
-      for (int t = 0; t < 11; ++t) {
-        const float x = sx[r][q + t], y = sy[r][q + t];
-        const float wx = w[t] * x, wy = w[t] * y;
-        mx += wx; my += wy;
-        xx = fmaf(wx, x, xx); yy = fmaf(wy, y, yy); xy = fmaf(wx, y, xy);
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 14; ++t) {
+        const float x = sx[r][q0 + t], y = sy[r][q0 + t];
+        const float xx = x * x, yy = y * y, xy = x * y;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = t - j;
+          if (k >= 0 && k < 11) {
+            acc[j][0] = fmaf(w[k], x, acc[j][0]);
+            acc[j][1] = fmaf(w[k], y, acc[j][1]);
+            acc[j][2] = fmaf(w[k], xx, acc[j][2]);
+            acc[j][3] = fmaf(w[k], yy, acc[j][3]);
+            acc[j][4] = fmaf(w[k], xy, acc[j][4]);
+          }
+        }
       }
-      sh[0][r][q] = mx; sh[1][r][q] = my; sh[2][r][q] = xx; sh[3][r][q] = yy; sh[4][r][q] = xy;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) sh[m][r][q0 + j] = acc[j][m];
     }
     __syncthreads();
+    // vertical pass: a thread owns 4 vertically adjacent pixels of one column, same sliding window
+    float vacc[4][5];
 #pragma unroll
-    for (int k = 0; k < kLossTile / 8; ++k) {
-      const int py = warp + 8 * k, px = lane;
-      const int y = y0 + py, x = x0 + px;
-      float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < 11; ++t) {
-        mu1 = fmaf(w[t], sh[0][py + t][px], mu1);
-        mu2 = fmaf(w[t], sh[1][py + t][px], mu2);
-        exx = fmaf(w[t], sh[2][py + t][px], exx);
-        eyy = fmaf(w[t], sh[3][py + t][px], eyy);
-        exy = fmaf(w[t], sh[4][py + t][px], exy);
+      for (int m = 0; m < 5; ++m) vacc[j][m] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 14; ++t) {
+      float v[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) v[m] = sh[m][4 * warp + t][lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = t - j;
+        if (k >= 0 && k < 11) {
+#pragma unroll
+          for (int m = 0; m < 5; ++m) vacc[j][m] = fmaf(w[k], v[m], vacc[j][m]);
+        }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int py = 4 * warp + k, px = lane;
+      const int y = y0 + py, x = x0 + px;
+      const float mu1 = vacc[k][0], mu2 = vacc[k][1], exx = vacc[k][2], eyy = vacc[k][3], exy = vacc[k][4];
       if (y < H && x < W) {
         const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
         const float s1 = exx - mu1_sq, s2 = eyy - mu2_sq, s12 = exy - mu12;
@@ -192,7 +223,7 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_bwd_kernel(const float* 
                                                                    const float* __restrict__ grad_total,
                                                                    float* __restrict__ grad_pred) {
   __shared__ float sa[3][kLossIn][kLossIn + 1];
-  __shared__ float sh[3][kLossIn][kLossTile];
+  __shared__ float sh[3][kLossIn][kLossTile + 1];
   const int x0 = blockIdx.x * kLossTile, y0 = blockIdx.y * kLossTile, b = blockIdx.z;
   const size_t img_off = (size_t)b * H * W * 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -207,29 +238,55 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_bwd_kernel(const float* 
 #pragma unroll
     for (int m = 0; m < 3; ++m) load_tile_planar(maps + m * map_floats + plane, H, W, x0, y0, sa[m]);
     __syncthreads();
-    for (int p = tid; p < kLossIn * kLossTile; p += kLossThreads) {
-      const int r = p >> 5, q = p & 31;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int item = tid; item < kLossIn * (kLossTile / 4); item += kLossThreads) {
+      const int r = item % kLossIn, q0 = (item / kLossIn) * 4;
+      float acc[4][3];
 #pragma unroll
-      for (int t = 0; t < 11; ++t) {
-        a0 = fmaf(w[t], sa[0][r][q + t], a0);
-        a1 = fmaf(w[t], sa[1][r][q + t], a1);
-        a2 = fmaf(w[t], sa[2][r][q + t], a2);
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) acc[j][m] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 14; ++t) {
+        const float v0 = sa[0][r][q0 + t], v1 = sa[1][r][q0 + t], v2 = sa[2][r][q0 + t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = t - j;
+          if (k >= 0 && k < 11) {
+            acc[j][0] = fmaf(w[k], v0, acc[j][0]);
+            acc[j][1] = fmaf(w[k], v1, acc[j][1]);
+            acc[j][2] = fmaf(w[k], v2, acc[j][2]);
+          }
+        }
       }
-      sh[0][r][q] = a0; sh[1][r][q] = a1; sh[2][r][q] = a2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) sh[m][r][q0 + j] = acc[j][m];
     }
     __syncthreads();
+    float vacc[4][3];
 #pragma unroll
-    for (int k = 0; k < kLossTile / 8; ++k) {
-      const int py = warp + 8 * k, px = lane;
-      const int y = y0 + py, x = x0 + px;
-      float gA = 0.f, gB = 0.f, gC = 0.f;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < 11; ++t) {
-        gA = fmaf(w[t], sh[0][py + t][px], gA);
-        gB = fmaf(w[t], sh[1][py + t][px], gB);
-        gC = fmaf(w[t], sh[2][py + t][px], gC);
+      for (int m = 0; m < 3; ++m) vacc[j][m] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 14; ++t) {
+      const float v0 = sh[0][4 * warp + t][lane], v1 = sh[1][4 * warp + t][lane], v2 = sh[2][4 * warp + t][lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = t - j;
+        if (k >= 0 && k < 11) {
+          vacc[j][0] = fmaf(w[k], v0, vacc[j][0]);
+          vacc[j][1] = fmaf(w[k], v1, vacc[j][1]);
+          vacc[j][2] = fmaf(w[k], v2, vacc[j][2]);
+        }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int py = 4 * warp + k, px = lane;
+      const int y = y0 + py, x = x0 + px;
+      const float gA = vacc[k][0], gB = vacc[k][1], gC = vacc[k][2];
       if (y < H && x < W) {
         const size_t o = img_off + ((size_t)y * W + x) * 3 + c;
         const float xv = pred[o], yv = target[o];

@@ -41,7 +41,7 @@ def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 
 def ssim_map_single_channel(x: torch.Tensor, y: torch.Tensor, window_size: int = 11) -> torch.Tensor:
     """losses.py:91-130 for one [B,1,H,W] channel, returning the SSIM map (the reference returns its mean)."""
-    g = gaussian_window_1d(window_size, 1.5, x.dtype)
+    g = gaussian_window_1d(window_size, 1.5, x.dtype).to(x.device)
     win = (g.unsqueeze(1) * g.unsqueeze(0)).unsqueeze(0).unsqueeze(0)
     pad = window_size // 2
     mu1 = F.conv2d(x, win, padding=pad)
