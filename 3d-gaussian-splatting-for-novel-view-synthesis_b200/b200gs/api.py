@@ -227,6 +227,10 @@ class RenderPipeline:
         self.front_stream = torch.cuda.Stream(self.device, priority=high)
         self.blend_stream = torch.cuda.Stream(self.device)
         self._open = []                               # submitted, not yet checked (oldest first)
+        # ring of workspace sets ([frame_ws, isect_ws], completion event of their last user): the ~260 MB of a frame
+        # do not go through the caching allocator every frame (buffers used on two streams return to it slowly)
+        self._ring = [[[None, None], None] for _ in range(self.MAX_IN_FLIGHT + 1)]
+        self._next = 0
         torch.cuda.synchronize(self.device)          # everything created so far is visible to both streams
 
     def submit(self, pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near=0.01, far=100.0, pix_guard=32,
@@ -240,7 +244,11 @@ class RenderPipeline:
                 c2w_d = c2w.to(self.device, non_blocking=True)
                 args, strict = _resolve(pos, color, opacity_raw, sigma, c2w_d, H, W, fx, fy, cx, cy, near, far, pix_guard,
                                         T, min_conis, chi_square_clip, alpha_max, alpha_cutoff, None)
-                image, frame = ops.launch_frame(*args)
+                slot = self._ring[self._next % len(self._ring)]
+                self._next += 1
+                if slot[1] is not None:
+                    self.front_stream.wait_event(slot[1])      # the frame that last used these workspaces is blended
+                image, frame = ops.launch_frame(*args, buffers=slot[0])
         finally:
             if prev is None:
                 ops._blend_stream.pop(self.device.index, None)
@@ -248,7 +256,8 @@ class RenderPipeline:
                 ops._blend_stream[self.device.index] = prev
         done = torch.cuda.Event()
         done.record(self.blend_stream)                # the frame's blend has been queued: completion marker
-        ticket = [image, frame, strict, pos.dtype, done]
+        slot[1] = done
+        ticket = [image, frame, strict, pos.dtype, done, slot]
         self._open.append(ticket)
         return ticket
 
@@ -263,6 +272,7 @@ class RenderPipeline:
             if ticket[1].finish():                    # rasterized again: the completion marker moves
                 ticket[4] = torch.cuda.Event()
                 ticket[4].record(self.blend_stream)
+                ticket[5][1] = ticket[4]
         finally:
             if prev is None:
                 ops._blend_stream.pop(self.device.index, None)

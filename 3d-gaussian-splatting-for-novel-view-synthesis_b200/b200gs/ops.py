@@ -168,7 +168,7 @@ class Frame:
         self.finish()
         return image
 
-    def launch(self, mode: Optional[str] = None) -> torch.Tensor:
+    def launch(self, mode: Optional[str] = None, buffers=None) -> torch.Tensor:
         """Queues the frame.  In speculative mode nothing is waited for: `finish()` must be called (before
         _STATS_RING - 1 further frames are launched on this stream) to learn whether the frame fitted its buffers
         and to redo it if it did not; the image is only trustworthy after that."""
@@ -180,7 +180,15 @@ class Frame:
         stream = torch.cuda.current_stream(dev)
         st = ctypes.c_void_p(stream.cuda_stream)
         frame_bytes, _ = _sizes(lib, n, H, W, 0)
-        self.frame_ws = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+        # `buffers` = [frame_ws, isect_ws] owned by the caller (RenderPipeline keeps a ring of them instead of going
+        # through the allocator every frame); replaced in place when too small
+        self._buffers = buffers
+        if buffers is not None and buffers[0] is not None and buffers[0].numel() >= frame_bytes:
+            self.frame_ws = buffers[0]
+        else:
+            self.frame_ws = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+            if buffers is not None:
+                buffers[0] = self.frame_ws
         stats_np, stats_ptr, ev, ev_ptr = _stats_slot(dev, stream)
         image = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
@@ -241,7 +249,13 @@ class Frame:
     def _rasterize(self, lib, n, H, W, capacity, image, stats_ptr, st, stats_event=None):
         frame_bytes, isect_bytes = _sizes(lib, n, H, W, capacity)
         self.capacity = capacity
-        self.isect_ws = torch.empty(isect_bytes, dtype=torch.uint8, device=self.device)
+        buffers = getattr(self, "_buffers", None)
+        if buffers is not None and buffers[1] is not None and buffers[1].numel() >= isect_bytes:
+            self.isect_ws = buffers[1]
+        else:
+            self.isect_ws = torch.empty(isect_bytes, dtype=torch.uint8, device=self.device)
+            if buffers is not None:
+                buffers[1] = self.isect_ws
         blend = _blend_stream.get(self.device.index)
         if blend is None:
             _lib.check(lib.b200gs_render_rasterize_ev(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
@@ -308,13 +322,13 @@ def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
     return g, keep
 
 
-def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg):
+def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg, buffers=None):
     """Forward-only frame without autograd bookkeeping (RenderPipeline): returns (image, Frame); the caller must
     call Frame.finish() before trusting the image."""
     g, keep = _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)
     with torch.cuda.device(pos.device):
         frame = Frame(g, keep, cfg, c2w, pos.device)
-        image = frame.launch("speculative")
+        image = frame.launch("speculative", buffers)
     return image, frame
 
 
