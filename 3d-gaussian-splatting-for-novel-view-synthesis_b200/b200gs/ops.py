@@ -138,10 +138,10 @@ def _sizes(lib, n: int, H: int, W: int, capacity: int):
     return got
 
 
-# Intersection-capacity policy.  "sync" (default): read I back between project and rasterize (one
-# stream sync per frame, exact buffers).  "speculative": size the lists from a per-device high-water mark
-# and launch everything without a mid-frame sync; the overflow flag is checked when the frame's stats
-# are read (end of frame) and the frame is re-rasterized with exact buffers if it did not fit.
+# Intersection-capacity policy.  "speculative" (default): size the lists from a per-device high-water mark (the
+# first frame on a device is sized exactly), queue the whole frame without a mid-frame sync and wait only for the
+# event the library records once the frame's counters are final; a frame that did not fit is rasterized again with
+# exact buffers.  "sync": read I back between project and rasterize (one stream sync per frame, exact buffers).
 _high_water = {}
 _blend_stream = {}       # device index -> torch stream the blend kernels go to (set by api.RenderPipeline)
 
@@ -176,7 +176,7 @@ class Frame:
         dev = self.device
         n = int(self.g.n)
         H, W = int(self.cfg.H), int(self.cfg.W)
-        mode = mode or os.environ.get("B200GS_CAPACITY_MODE", "sync")
+        mode = mode or os.environ.get("B200GS_CAPACITY_MODE", "speculative")
         stream = torch.cuda.current_stream(dev)
         st = ctypes.c_void_p(stream.cuda_stream)
         frame_bytes, _ = _sizes(lib, n, H, W, 0)
