@@ -371,7 +371,8 @@ class _Rasterize(torch.autograd.Function):
                 res.append(None)
             else:
                 res.append(gten.reshape(meta[0]).to(meta[1]))
-        ctx.frame = None
+        # ctx.frame stays: backward(retain_graph=True) / a second autograd.grad on the same image must work as it does
+        # with the reference's autograd graph; the workspaces are released with the graph node
         return (*res, None, None, None)
 
 

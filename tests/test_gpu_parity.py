@@ -478,3 +478,29 @@ def test_non_default_render_arguments_against_live_oracle(gs, kw):
     for k in PARAMS:
         err = grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy())
         assert err <= 3 * GRAD_TOL if n_bad else err <= GRAD_TOL, (k, err, n_bad)
+
+
+def test_backward_is_linear_in_the_image_gradient_at_full_size(gs):
+    """No oracle at 1M Gaussians / 1080p: the backward of a fixed frame is a linear map of dL/dimage, so
+    bwd(a g1 + b g2) = a bwd(g1) + b bwd(g2) for all six parameter tensors (float atomics: 2e-4 of the max-norm)."""
+    from oracle import gs_oracle as O
+    sc = O.make_scene(1_000_000, seed=0, log_scale=-5.5)
+    cam = O.make_camera(1920, 1080, view=2, n_views=16)
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    c2w = cam["c2w"].cuda()
+    sigma = gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+    color = gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+    img = gs.render(leaves["pos"], color, leaves["opacity_raw"], sigma, c2w, 1080, 1920, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    g1 = torch.randn(img.shape, device="cuda", generator=g)
+    g2 = torch.rand(img.shape, device="cuda", generator=g)
+    params = [leaves[k] for k in PARAMS]
+    d1 = torch.autograd.grad(img, params, g1, retain_graph=True)
+    d2 = torch.autograd.grad(img, params, g2, retain_graph=True)
+    d3 = torch.autograd.grad(img, params, 0.75 * g1 - 2.0 * g2)
+    for k, a, b, c in zip(PARAMS, d1, d2, d3):
+        assert torch.isfinite(c).all(), k
+        want = 0.75 * a - 2.0 * b
+        scale = float(torch.maximum(a.abs().max(), b.abs().max()))
+        assert scale > 0, k
+        assert float((c - want).abs().max()) <= 2e-4 * scale, (k, float((c - want).abs().max()), scale)
