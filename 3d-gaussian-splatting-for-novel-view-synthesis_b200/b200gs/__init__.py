@@ -10,8 +10,9 @@ from .api import RenderPipeline, build_sigma_from_params, evaluate_sh, render, t
 from .losses import compute_loss, compute_loss_tensors, l1_loss, ssim_loss
 from .install import install, uninstall
 from .optim import FusedAdam, clip_grad_norm_
+from .peer import PeerAdam, peer_allreduce_gradients
 from ._lib import B200GSError, LIB_PATH, load as load_library
 
 __all__ = ["build_sigma_from_params", "evaluate_sh", "render", "compute_loss", "compute_loss_tensors", "l1_loss",
-           "ssim_loss", "to_uint8", "RenderPipeline", "FusedAdam", "clip_grad_norm_", "install", "uninstall", "B200GSError",
+           "ssim_loss", "to_uint8", "RenderPipeline", "FusedAdam", "clip_grad_norm_", "PeerAdam", "peer_allreduce_gradients", "install", "uninstall", "B200GSError",
            "LIB_PATH", "load_library"]

@@ -46,6 +46,25 @@ class AdamTensor(Structure):
                 ("numel", ctypes.c_int64), ("lr", c_double), ("step", c_int32), ("reserved", c_int32)]
 
 
+MAX_PEERS = 16
+PEER_MAX_TENSORS = 8
+PEER_CTRL_BYTES = 4096
+
+
+class PeerLayout(Structure):
+    _fields_ = [("offset", ctypes.c_int64 * PEER_MAX_TENSORS), ("per", ctypes.c_int64 * PEER_MAX_TENSORS),
+                ("shard_offset", ctypes.c_int64 * PEER_MAX_TENSORS), ("flat_total", ctypes.c_int64),
+                ("shard_total", ctypes.c_int64)]
+
+
+class PeerGroup(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("area", c_void_p * MAX_PEERS)]
+
+
+class PeerTensor(Structure):
+    _fields_ = [("grad", c_void_p), ("numel", ctypes.c_int64), ("lr", c_double), ("step", c_int32), ("clip", c_int32)]
+
+
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
                 ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("reserved", c_uint32 * 11)]
@@ -78,6 +97,14 @@ SYMBOLS = {
     "b200gs_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_double, c_double, c_double, c_void_p]),
     "b200gs_clip_workspace_bytes": (c_size_t, [ctypes.c_int64]),
     "b200gs_clip_grad_norm": (c_int, [c_void_p, ctypes.c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b200gs_peer_layout_compute": (c_int, [POINTER(ctypes.c_int64), c_int32, c_int32, POINTER(PeerLayout)]),
+    "b200gs_peer_area_bytes": (c_size_t, [POINTER(PeerLayout)]),
+    "b200gs_peer_barrier": (c_int, [POINTER(PeerGroup), POINTER(c_uint32), c_void_p]),
+    "b200gs_peer_adam_step": (c_int, [POINTER(PeerGroup), POINTER(PeerLayout), POINTER(PeerTensor), c_int32, c_void_p,
+                                      c_void_p, c_double, c_double, c_double, c_double, c_int32, POINTER(c_uint32),
+                                      c_void_p, c_void_p]),
+    "b200gs_peer_allreduce": (c_int, [POINTER(PeerGroup), POINTER(PeerLayout), POINTER(PeerTensor), c_int32,
+                                      POINTER(c_uint32), c_void_p]),
     "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
     "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,

@@ -30,6 +30,7 @@ SOURCES = {
     "blend.cu": [],
     "loss.cu": [],
     "optim.cu": [],
+    "peer.cu": [],
     "api.cu": [],
 }
 HEADERS = ["common.cuh", "gs_math.cuh", os.path.join(INCLUDE, "b200gs.h")]

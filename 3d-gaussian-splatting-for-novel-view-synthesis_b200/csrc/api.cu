@@ -17,6 +17,7 @@ int fail(int code, const char* what) {
   g_last_error = what;
   return code;
 }
+int fail(int code, const std::string& what) { return fail(code, what.c_str()); }
 int fail_cuda(cudaError_t e, const char* where) {
   g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
   return B200GS_ERR_CUDA;
@@ -29,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -336,6 +337,72 @@ int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* wor
   cudaStream_t s = (cudaStream_t)stream;
   PCU(R_CLIP, 2, gs::launch_clip_grad_norm(grad, numel, max_norm, workspace, total_norm_out, s));
   return B200GS_OK;
+}
+
+int b200gs_peer_layout_compute(const int64_t* numel, int32_t n_tensors, int32_t world, b200gs_peer_layout* out) {
+  if (gs::peer_layout_compute(numel, n_tensors, world, out) != 0)
+    return fail(B200GS_ERR_ARG, "peer_layout_compute: need 0 <= n_tensors <= 8, 1 <= world <= 16, numel >= 0");
+  return B200GS_OK;
+}
+
+size_t b200gs_peer_area_bytes(const b200gs_peer_layout* layout) {
+  return layout ? (size_t)B200GS_PEER_CTRL_BYTES + 8 * (size_t)layout->flat_total : 0;
+}
+
+static int check_peer_group(const b200gs_peer_group* g, const char* who) {
+  if (!g || g->world < 1 || g->world > B200GS_MAX_PEERS || g->rank < 0 || g->rank >= g->world)
+    return fail(B200GS_ERR_ARG, std::string(who) + ": bad peer group");
+  for (int q = 0; q < g->world; ++q)
+    if (!g->area[q]) return fail(B200GS_ERR_ARG, std::string(who) + ": unmapped peer area");
+  return B200GS_OK;
+}
+
+int b200gs_peer_barrier(const b200gs_peer_group* group, uint32_t* epoch, void* stream) {
+  if (int rc = check_peer_group(group, "peer_barrier")) return rc;
+  if (!epoch) return fail(B200GS_ERR_ARG, "peer_barrier: null epoch");
+  CU(gs::launch_peer_barrier(group, ++*epoch, (cudaStream_t)stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return B200GS_OK;
+}
+
+static int peer_step_common(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
+                            const b200gs_peer_tensor* tensors, int32_t n_tensors, bool adam, float* m, float* v,
+                            double beta1, double beta2, double eps, double max_norm, int32_t write_grads,
+                            uint32_t* epoch, float* total_norm_out, void* stream, const char* who) {
+  if (int rc = check_peer_group(group, who)) return rc;
+  if (!layout || !epoch || n_tensors < 0 || n_tensors > B200GS_PEER_MAX_TENSORS || (n_tensors > 0 && !tensors))
+    return fail(B200GS_ERR_ARG, std::string(who) + ": null argument or too many tensors");
+  for (int i = 0; i < n_tensors; ++i) {
+    const b200gs_peer_tensor& t = tensors[i];
+    if (t.numel < 0 || (adam && t.step < 1)) return fail(B200GS_ERR_ARG, std::string(who) + ": numel < 0 or step < 1");
+    if (layout->offset[i] + t.numel > layout->flat_total || (layout->offset[i] & 31))
+      return fail(B200GS_ERR_ARG, std::string(who) + ": tensor does not match the layout");
+    if (!adam && t.numel > 0 && !t.grad) return fail(B200GS_ERR_ARG, std::string(who) + ": null gradient");
+  }
+  if (adam && layout->shard_total > 0 && (!m || !v)) return fail(B200GS_ERR_ARG, std::string(who) + ": null moment shard");
+  cudaStream_t s = (cudaStream_t)stream;
+  int launches = 0;
+  {
+    ProfScope scope(adam ? R_PEER_STEP : R_PEER_ALLREDUCE, s, 0);
+    CU(gs::launch_peer_step(group, layout, tensors, n_tensors, adam, m, v, beta1, beta2, eps, max_norm, write_grads,
+                            epoch, total_norm_out, s, &launches));
+  }
+  g_launches.fetch_add((unsigned long long)launches, std::memory_order_relaxed);
+  return B200GS_OK;
+}
+
+int b200gs_peer_adam_step(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
+                          const b200gs_peer_tensor* tensors, int32_t n_tensors, float* exp_avg_shard,
+                          float* exp_avg_sq_shard, double beta1, double beta2, double eps, double max_norm,
+                          int32_t write_grads, uint32_t* epoch, float* total_norm_out, void* stream) {
+  return peer_step_common(group, layout, tensors, n_tensors, true, exp_avg_shard, exp_avg_sq_shard, beta1, beta2, eps,
+                          max_norm, write_grads, epoch, total_norm_out, stream, "peer_adam_step");
+}
+
+int b200gs_peer_allreduce(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
+                          const b200gs_peer_tensor* tensors, int32_t n_tensors, uint32_t* epoch, void* stream) {
+  return peer_step_common(group, layout, tensors, n_tensors, false, nullptr, nullptr, 0.9, 0.999, 1e-8, 0.0, 1, epoch,
+                          nullptr, stream, "peer_allreduce");
 }
 
 int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, void* frame_ws, size_t frame_bytes,

@@ -180,6 +180,14 @@ size_t clip_workspace_bytes(long long numel);
 cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
                                   cudaStream_t s);
 
+// peer.cu: data-parallel optimizer step over NVLink peer memory
+int peer_layout_compute(const int64_t* numel, int n_tensors, int world, b200gs_peer_layout* out);
+cudaError_t launch_peer_barrier(const b200gs_peer_group* g, uint32_t epoch, cudaStream_t s);
+cudaError_t launch_peer_step(const b200gs_peer_group* g, const b200gs_peer_layout* L, const b200gs_peer_tensor* tensors,
+                             int n_tensors, bool adam, float* m_shard, float* v_shard, double beta1, double beta2,
+                             double eps, double max_norm, int write_grads, uint32_t* epoch, float* total_norm_out,
+                             cudaStream_t s, int* launches);
+
 size_t loss_workspace_bytes(int n_img, int H, int W, bool with_grad);
 cudaError_t launch_l1_ssim_fwd(const float* pred, const float* target, int n_img, int H, int W, float lambda_l1,
                                float lambda_ssim, void* ws, bool with_grad, float* out3, cudaStream_t s);

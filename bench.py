@@ -507,7 +507,7 @@ def run_b200gs(args):
         b200gs.clip_grad_norm_(leaves["pos"], max_norm=1.0)
         opt.step()
 
-    def train_step_loss_nograd_reset(i):
+    def train_step_loss_nograd_reset(i, reduce=True):
         c2w = c2w_dev[view_of(i)]
         sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
         col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
@@ -515,7 +515,8 @@ def run_b200gs(args):
                             intr["cx"], intr["cy"])
         loss, _ = b200gs.compute_loss_tensors(img, target_dev)
         (loss / world).backward()
-        allreduce_gradients(leaves.values())
+        if reduce:
+            allreduce_gradients(leaves.values())
     for i in range(4):                      # first steps allocate the optimizer state: not representative
         train_full(i)
     torch.cuda.synchronize()
@@ -529,6 +530,20 @@ def run_b200gs(args):
                    ("adam_step", "clip_grad_norm")}
     lib.b200gs_profile_enable(0)
     ms_train_full, _ = timed(lambda i: train_full(i), K, Wm)
+    # N > 1: the same iteration with the optimizer half done over NVLink peer memory - gradient reduce-scatter +
+    # clip + Adam on the owned shard + parameter all-gather in one kernel (b200gs.PeerAdam, csrc/peer.cu) instead
+    # of NCCL all-reduce + clip + Adam.  Runs last: it re-homes the parameters into the peer-visible buffer.
+    ms_train_peer = peer_transport = None
+    if world > 1:
+        opt_p = b200gs.PeerAdam([{"params": [leaves[k]], "lr": lr0[k], "name": k} for k in PARAMS], lr=1e-3, eps=1e-15,
+                                clip_params=[leaves["pos"]], max_norm=1.0)
+        peer_transport = opt_p.area.transport
+
+        def train_full_peer(i):
+            opt_p.zero_grad(set_to_none=True)
+            train_step_loss_nograd_reset(i, reduce=False)
+            opt_p.step()
+        ms_train_peer, _ = timed(lambda i: train_full_peer(i), K, Wm)
 
     # ---- frame statistics of view 0 (V, I) for the byte model ---------------------------------------------------
     with torch.no_grad():
@@ -616,8 +631,16 @@ def run_b200gs(args):
                                         "step": "the same with b200gs.compute_loss (fused L1 + SSIM, losses.py:158) "
                                                 "instead of the weighted sum"},
                   "full_iteration": {"value": K / (ms_train_full * 1e-3), "unit": "it/s", "ms_per_step": ms_train_full / K,
-                                     "step": "train.py:463-538 on the fused path: render + L1/SSIM loss + backward + "
+                                     "views_per_s": world * K / (ms_train_full * 1e-3),
+                                     "step": "train.py:463-538 on the fused path: render + L1/SSIM loss + backward + " +
+                                             ("NCCL sum all-reduce of 6 gradient tensors + " if world > 1 else "") +
                                              "clip_grad_norm_(pos) + fused Adam over the six parameter groups"},
+                  **({"full_iteration_peer": {
+                      "value": K / (ms_train_peer * 1e-3), "unit": "it/s", "ms_per_step": ms_train_peer / K,
+                      "views_per_s": world * K / (ms_train_peer * 1e-3), "transport": peer_transport,
+                      "step": "the same iteration with b200gs.PeerAdam: gradient reduce-scatter + clip + Adam on the owned "
+                              "shard + parameter all-gather in ONE kernel over NVLink peer memory (no NCCL on the data path)"}}
+                     if ms_train_peer else {}),
                   "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
                           "d2h_bytes_per_step": 4}},
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,

@@ -226,6 +226,57 @@ size_t b200gs_clip_workspace_bytes(int64_t numel);
 int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* workspace, size_t workspace_bytes,
                           float* total_norm_out, void* stream);
 
+/* ---- Data-parallel optimizer step over NVLink peer memory (one process per GPU) --------------------------------
+ * The data-parallel form of scripts/train.py:530-538 (backward -> SUM of the six gradient tensors over the ranks ->
+ * clip_grad_norm_(model.pos, 1.0) -> optim.Adam.step()); the reference itself is single-GPU (scripts/train.py:285-291
+ * only prints the GPU count).  Every rank owns 1/world of every tensor: one kernel reads the owned gradient
+ * elements from every rank's staging buffer over NVLink (reduce-scatter), clips, updates its shard of the Adam
+ * moments and stores the new parameter values into every rank's parameter buffer (all-gather).
+ *
+ * Each rank allocates one peer-visible "area" of b200gs_peer_area_bytes() bytes (zero-filled before first use),
+ *     [ control block: B200GS_PEER_CTRL_BYTES ][ parameters: flat_total floats ][ gradient staging: flat_total floats ]
+ * and the host side maps every rank's area into every process (CUDA VMM / IPC) and passes the mapped base
+ * pointers in rank order.  Tensor t lives at float offset layout.offset[t] of the flat buffers; rank r owns its
+ * elements [min(numel, r*per[t]), min(numel, (r+1)*per[t])) and keeps their moments at shard_offset[t] of its two
+ * shard arrays (shard_total floats each).  All ranks must issue the same sequence of peer calls; *epoch is a
+ * host-side counter (start at 0) that the calls advance by the number of cross-GPU barriers they used. */
+#define B200GS_MAX_PEERS 16
+#define B200GS_PEER_MAX_TENSORS 8
+#define B200GS_PEER_CTRL_BYTES 4096
+typedef struct b200gs_peer_layout {
+  int64_t offset[B200GS_PEER_MAX_TENSORS];
+  int64_t per[B200GS_PEER_MAX_TENSORS];
+  int64_t shard_offset[B200GS_PEER_MAX_TENSORS];
+  int64_t flat_total, shard_total;
+} b200gs_peer_layout;
+typedef struct b200gs_peer_group {
+  int32_t world, rank;
+  void* area[B200GS_MAX_PEERS];   /* area[q]: rank q's area as mapped into THIS process (area[rank] is local) */
+} b200gs_peer_group;
+typedef struct b200gs_peer_tensor {
+  float* grad;      /* this rank's local gradient [numel] (NULL: contributes zeros); receives the reduced gradient
+                       when write_grads != 0 / from b200gs_peer_allreduce */
+  int64_t numel;
+  double lr;
+  int32_t step;     /* 1-based step count after this update */
+  int32_t clip;     /* != 0: member of the set whose joint L2 norm is clipped to max_norm */
+} b200gs_peer_tensor;
+/* Host arithmetic only (no device work). */
+int b200gs_peer_layout_compute(const int64_t* numel, int32_t n_tensors, int32_t world, b200gs_peer_layout* out);
+size_t b200gs_peer_area_bytes(const b200gs_peer_layout* layout);
+/* Cross-GPU barrier on `stream` (every rank must call it with the same epoch sequence). */
+int b200gs_peer_barrier(const b200gs_peer_group* group, uint32_t* epoch, void* stream);
+/* Fused reduce-scatter + clip + Adam + all-gather.  exp_avg_shard / exp_avg_sq_shard: [layout.shard_total] floats,
+ * local.  max_norm <= 0 disables clipping; total_norm_out (device, may be NULL) receives the joint norm. */
+int b200gs_peer_adam_step(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
+                          const b200gs_peer_tensor* tensors, int32_t n_tensors, float* exp_avg_shard,
+                          float* exp_avg_sq_shard, double beta1, double beta2, double eps, double max_norm,
+                          int32_t write_grads, uint32_t* epoch, float* total_norm_out, void* stream);
+/* SUM all-reduce of the gradient tensors over peer memory (reduce-scatter + all-gather in one kernel, no NCCL);
+ * every tensors[t].grad is replaced by the sum over the ranks. */
+int b200gs_peer_allreduce(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
+                          const b200gs_peer_tensor* tensors, int32_t n_tensors, uint32_t* epoch, void* stream);
+
 /* Per-region CUDA-event profiling (bench.py's per-kernel table).  enable(1) starts recording an event
  * pair around every kernel group launched through this library; collect() synchronises the device,
  * sums the elapsed milliseconds and the number of calls per region, clears the records and returns the
