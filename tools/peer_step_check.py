@@ -1,0 +1,77 @@
+"""Diagnostic: b200gs.PeerAdam against a local torch.optim.Adam replay on every rank, step by step, with per-tensor
+mismatch counts and the owners of the mismatching elements.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 \
+        tools/peer_step_check.py [N] [steps]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting-for-novel-view-synthesis_b200"))
+import torch
+import torch.distributed as dist
+import b200gs
+from b200gs import peer
+
+SHAPES = dict(pos=(3,), opacity_raw=(), f_dc=(3,), f_rest=(45,), scale_raw=(3,), q_raw=(4,))
+LRS = dict(pos=1.6e-4, opacity_raw=0.05, f_dc=2.5e-3, f_rest=1.25e-4, scale_raw=5e-3, q_raw=1e-3)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g0 = torch.Generator().manual_seed(1)
+    ref = {k: torch.nn.Parameter(torch.randn((n,) + s, generator=g0).to(dev)) for k, s in SHAPES.items()}
+    mine = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ref.items()}
+    opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15)
+    opt = b200gs.PeerAdam([{"params": [mine[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15,
+                          clip_params=[mine["pos"]], max_norm=1.0)
+    report = []
+    for step in range(1, steps + 1):
+        total = {k: None for k in SHAPES}
+        for r in range(world):                      # every rank can rebuild every rank's gradient
+            g = torch.Generator().manual_seed(1000 * step + r)
+            for k, s in SHAPES.items():
+                x = (torch.randn((n,) + s, generator=g) * 1e-3).to(dev)
+                if r == rank:
+                    mine[k].grad = x.clone()
+                total[k] = x if total[k] is None else total[k] + x      # rank order, like the plain peer path
+        for k in SHAPES:
+            ref[k].grad = total[k]
+        torch.nn.utils.clip_grad_norm_(ref["pos"], max_norm=1.0)
+        opt_ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        row = {"step": step}
+        for k in SHAPES:
+            a, b = mine[k].detach().flatten(), ref[k].detach().flatten()
+            bad = ((a - b).abs() > 2e-6 * b.abs().max()).nonzero().flatten()
+            if bad.numel():
+                per = peer.slice_bounds(a.numel(), world, 0)[1]
+                owners = torch.bincount(torch.clamp(bad // max(per, 1), max=world - 1), minlength=world).tolist()
+                row[k] = {"bad": int(bad.numel()), "owners": owners, "first": int(bad[0]), "last": int(bad[-1]),
+                          "max_abs": float((a - b).abs().max())}
+        report.append(row)
+    out = [None] * world
+    if world > 1:
+        dist.all_gather_object(out, report)
+    else:
+        out = [report]
+    if rank == 0:
+        print(json.dumps({"n": n, "world": world, "per_rank": out}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
