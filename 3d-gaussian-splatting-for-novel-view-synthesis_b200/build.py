@@ -25,7 +25,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 # per-file extra flags; preprocess.cu feeds floor()/ceil() decisions -> no implicit FMA contraction
 SOURCES = {
     "preprocess.cu": ["-fmad=false"],
-    "scan_sort.cu": [],
+    "scan_sort.cu": ([f"-DONESWEEP_MIN_BLOCKS={os.environ['B200GS_ONESWEEP_MIN_BLOCKS']}"]
+                     if os.environ.get("B200GS_ONESWEEP_MIN_BLOCKS") else []),
     "binning.cu": [],
     "blend.cu": [],
     "loss.cu": [],

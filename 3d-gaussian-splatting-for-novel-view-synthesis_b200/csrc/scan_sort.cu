@@ -219,13 +219,16 @@ __global__ void __launch_bounds__(kRadix) sort_scan_hist_kernel(uint32_t* __rest
 // the others do the expensive stable ranking and the shared-memory reorder, so the look-back latency -
 // which a synchronised wave of blocks pays in full, wave after wave - is off the critical path.
 constexpr int kSortBlock = kSortThreads + 32;
+#ifndef ONESWEEP_MIN_BLOCKS
+#define ONESWEEP_MIN_BLOCKS 3      // 72 registers (96 with 2): a smaller CTA finds room sooner next to the blend CTAs of the previous frame
+#endif
 constexpr int kLbBatch = 4;
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-__global__ void __launch_bounds__(kSortBlock, 2) onesweep_pass_kernel(
+__global__ void __launch_bounds__(kSortBlock, ONESWEEP_MIN_BLOCKS) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int shift, int bits,
     const uint32_t* __restrict__ ghist /*[256] digit counts of this pass*/, uint32_t* __restrict__ status, uint32_t* ticket) {
