@@ -221,10 +221,16 @@ class RenderPipeline:
 
     MAX_IN_FLIGHT = 4
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, front_streams=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         _, high = torch.cuda.Stream.priority_range()
-        self.front_stream = torch.cuda.Stream(self.device, priority=high)
+        if front_streams is None:
+            front_streams = int(os.environ.get("B200GS_FRONT_STREAMS", "2"))
+        # the binning chain is a dozen dependent, latency-bound kernels: with two front streams the chains of frames
+        # i+1 and i+2 interleave beside the blend of frame i (the caller must then keep `lag` frames queued)
+        self.front_streams = [torch.cuda.Stream(self.device, priority=high) for _ in range(max(1, int(front_streams)))]
+        self.front_stream = self.front_streams[0]
+        self.lag = len(self.front_streams)
         self.blend_stream = torch.cuda.Stream(self.device)
         self._open = []                               # submitted, not yet checked (oldest first)
         # ring of workspace sets ([frame_ws, isect_ws], completion event of their last user): the ~260 MB of a frame
@@ -239,15 +245,16 @@ class RenderPipeline:
             self._check(self._open[0])
         prev = ops._blend_stream.get(self.device.index)
         ops._blend_stream[self.device.index] = self.blend_stream
+        front = self.front_streams[self._next % len(self.front_streams)]
         try:
-            with torch.no_grad(), torch.cuda.stream(self.front_stream):
+            with torch.no_grad(), torch.cuda.stream(front):
                 c2w_d = c2w.to(self.device, non_blocking=True)
                 args, strict = _resolve(pos, color, opacity_raw, sigma, c2w_d, H, W, fx, fy, cx, cy, near, far, pix_guard,
                                         T, min_conis, chi_square_clip, alpha_max, alpha_cutoff, None)
                 slot = self._ring[self._next % len(self._ring)]
                 self._next += 1
                 if slot[1] is not None:
-                    self.front_stream.wait_event(slot[1])      # the frame that last used these workspaces is blended
+                    front.wait_event(slot[1])                  # the frame that last used these workspaces is blended
                 image, frame = ops.launch_frame(*args, buffers=slot[0])
         finally:
             if prev is None:
@@ -298,5 +305,24 @@ class RenderPipeline:
     def synchronize(self):
         for t in list(self._open):
             self._check(t)
-        self.front_stream.synchronize()
+        for st in self.front_streams:
+            st.synchronize()
         self.blend_stream.synchronize()
+
+    @property
+    def next_front_stream(self):
+        """The stream the NEXT `submit` queues its first half on: inputs of that frame that are produced
+        asynchronously (e.g. the pose uploaded from pinned memory) belong on this stream."""
+        return self.front_streams[self._next % len(self.front_streams)]
+
+    def wait_event(self, event):
+        """Every stream of the pipeline waits for `event` (e.g. the start marker of a timed region)."""
+        for st in self.front_streams:
+            st.wait_event(event)
+        self.blend_stream.wait_event(event)
+
+    def join(self, stream):
+        """`stream` waits for everything queued on the pipeline's streams so far."""
+        for st in self.front_streams:
+            stream.wait_stream(st)
+        stream.wait_stream(self.blend_stream)

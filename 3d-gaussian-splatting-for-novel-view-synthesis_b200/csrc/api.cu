@@ -513,7 +513,7 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
   } else {
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }
-  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s));
+  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s, blend_stream != stream));
   return B200GS_OK;
 }
 

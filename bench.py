@@ -329,13 +329,11 @@ def run_b200gs(args):
             l0 = lib.b200gs_kernel_launch_count()
             main = torch.cuda.current_stream(dev)
             e0.record(main)
-            pipe.front_stream.wait_event(e0)
-            pipe.blend_stream.wait_event(e0)
+            pipe.wait_event(e0)
             for i in range(steps):
                 pipe_step(c2w_dev[view_of(warm + i)])
             pipe_flush()
-            main.wait_stream(pipe.front_stream)
-            main.wait_stream(pipe.blend_stream)
+            pipe.join(main)
             e1.record(main)
             barrier()
             return max_over_ranks(e0.elapsed_time(e1)), lib.b200gs_kernel_launch_count() - l0
@@ -366,7 +364,7 @@ def run_b200gs(args):
                 copy_done[k].record(copy_stream)
 
         def e2e_step(i, deliver):
-            with torch.cuda.stream(pipe.front_stream):
+            with torch.cuda.stream(pipe.next_front_stream):
                 c2w = c2w_pin[view_of(i)].to(dev, non_blocking=True)
             pipe_step(c2w, deliver)
         for i in range(Wm):

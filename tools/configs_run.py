@@ -80,8 +80,7 @@ def run(name):
             pipe.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            pipe.front_stream.wait_event(e0)
-            pipe.blend_stream.wait_event(e0)
+            pipe.wait_event(e0)
             for i in range(120):
                 orbit(i)
             while pend:

@@ -17,11 +17,11 @@ with torch.no_grad():
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for i in range(60): single(i)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    pipe = b200gs.RenderPipeline(); pend = []
+    pipe = b200gs.RenderPipeline(); pend = []; LAG = int(os.environ.get('LAG', pipe.lag))
     def step(i):
         col = b200gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2ws[i % 16])
         pend.append(pipe.submit(sc["pos"], col, sc["opacity_raw"], sigma, c2ws[i % 16], H, W, K["fx"], K["fy"], K["cx"], K["cy"]))
-        if len(pend) > 1: pipe.result(pend.pop(0))
+        if len(pend) > LAG: pipe.result(pend.pop(0))
     for i in range(6): step(i)
     pipe.synchronize(); pend.clear()
     res = []
@@ -31,5 +31,5 @@ with torch.no_grad():
         while pend: pipe.result(pend.pop(0))
         pipe.synchronize(); t3 = time.perf_counter()
         res.append(round(60 / (t3 - t2)))
-    print(os.environ.get("B200GS_BLEND_EXTRA_SMEM"), "single", round(60 / (t1 - t0)), "fps  pipelined", res, "fps",
+    print("fronts", len(pipe.front_streams), "lag", LAG, "single", round(60 / (t1 - t0)), "fps  pipelined", res, "fps",
           "reserved GB", round(torch.cuda.memory_reserved() / 1e9, 2))
