@@ -35,10 +35,7 @@ struct AdamTable {
 };
 
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamTable& tb, const AdamTensor& t) {
-  m = m + (g - m) * tb.one_minus_beta1;
-  v = fmaf(tb.one_minus_beta2 * g, g, v * tb.beta2);
-  const float denom = sqrtf(v) / t.bc2_sqrt + tb.eps;
-  p = p - t.step_size * (m / denom);
+  adam_update_f32(p, g, m, v, tb.one_minus_beta1, tb.beta2, tb.one_minus_beta2, tb.eps, t.step_size, t.bc2_sqrt);
 }
 
 __global__ void __launch_bounds__(kAdamThreads) adam_step_kernel(const __grid_constant__ AdamTable tb) {

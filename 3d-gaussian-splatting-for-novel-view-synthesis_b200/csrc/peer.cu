@@ -161,10 +161,7 @@ __device__ __forceinline__ float clip_coefficient(const PeerPtrs& pp, const Peer
 }
 
 __device__ __forceinline__ void adam_update_peer(float& p, float g, float& m, float& v, const PeerTable& tb, const PeerTensor& t) {
-  m = m + (g - m) * tb.one_minus_beta1;                          // same arithmetic as optim.cu / torch.optim.Adam
-  v = fmaf(tb.one_minus_beta2 * g, g, v * tb.beta2);
-  const float denom = sqrtf(v) / t.bc2_sqrt + tb.eps;
-  p = p - t.step_size * (m / denom);
+  adam_update_f32(p, g, m, v, tb.one_minus_beta1, tb.beta2, tb.one_minus_beta2, tb.eps, t.step_size, t.bc2_sqrt);   // = optim.cu
 }
 
 // ADAM = true : reduce-scatter + clip + Adam on the owned slice + all-gather of the new parameters

@@ -54,6 +54,41 @@ def test_fused_adam_matches_torch_adam(n):
 
 
 @pytest.mark.gpu
+def test_fused_adam_zero_and_denormal_range_gradients_match_torch():
+    """Culled Gaussians have g = m = v = 0 and barely visible ones g*g in the denormal range: the kernel rescales
+    such operands around sqrt / division instead of taking the slow IEEE paths (csrc/common.cuh) - the results
+    must still be torch's."""
+    import b200gs
+    dev = torch.device("cuda")
+    n = 40_000
+    g = torch.Generator().manual_seed(7)
+    p0 = torch.randn(n, 3, generator=g)
+    mags = torch.tensor([0.0, 1e-30, 1e-24, 1e-21, 1e-19, 1e-12, 1e-6, 1.0]).repeat_interleave(n // 8)
+    mine = p0.clone().to(dev).requires_grad_(True)
+    ref = p0.clone().to(dev).requires_grad_(True)
+    opt_m = b200gs.FusedAdam([mine], lr=1e-2, eps=1e-15)
+    opt_r = torch.optim.Adam([ref], lr=1e-2, eps=1e-15, foreach=False)
+    for it in range(5):
+        gr = (torch.randn(n, 3, generator=g) * mags[:, None]).to(dev)
+        mine.grad, ref.grad = gr.clone(), gr.clone()
+        opt_m.step()
+        opt_r.step()
+    sm, sr = opt_m.state[mine], opt_r.state[ref]
+    k = n // 8
+    for gi in range(8):                                    # every magnitude group on its own scale
+        sl = slice(gi * k, (gi + 1) * k)
+        for name in ("exp_avg", "exp_avg_sq"):
+            a, b = sm[name][sl], sr[name][sl]
+            tol = 2e-6 * float(b.abs().max()) + 3e-45      # + two denormal steps where the moments underflow
+            assert float((a - b).abs().max()) <= tol, (gi, name, float((a - b).abs().max()), tol)
+        a, b = mine.detach()[sl], ref.detach()[sl]
+        # the UPDATE (not just the parameter) must agree: compare the displacement from the start
+        da, db = a - p0[sl].to(dev), b - p0[sl].to(dev)
+        assert float((da - db).abs().max()) <= 2e-6 * float(db.abs().max()) + 2.5e-7, (gi, float((da - db).abs().max()))
+    assert torch.equal(mine.detach()[:k], p0[:k].to(dev))            # zero gradient, zero moments: untouched
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,scale", [(1, 5.0), (4096, 1e-3), (4097, 1.0), (1_000_003, 0.01), (300_000, 3.0)])
 def test_clip_grad_norm_matches_torch(n, scale):
     import b200gs
