@@ -528,21 +528,6 @@ def run_b200gs(args):
                    ("adam_step", "clip_grad_norm")}
     lib.b200gs_profile_enable(0)
     ms_train_full, _ = timed(lambda i: train_full(i), K, Wm)
-    # N > 1: the same iteration with the optimizer half done over NVLink peer memory - gradient reduce-scatter +
-    # clip + Adam on the owned shard + parameter all-gather in one kernel (b200gs.PeerAdam, csrc/peer.cu) instead
-    # of NCCL all-reduce + clip + Adam.  Runs last: it re-homes the parameters into the peer-visible buffer.
-    ms_train_peer = peer_transport = None
-    if world > 1:
-        opt_p = b200gs.PeerAdam([{"params": [leaves[k]], "lr": lr0[k], "name": k} for k in PARAMS], lr=1e-3, eps=1e-15,
-                                clip_params=[leaves["pos"]], max_norm=1.0)
-        peer_transport = opt_p.area.transport
-
-        def train_full_peer(i):
-            opt_p.zero_grad(set_to_none=True)
-            train_step_loss_nograd_reset(i, reduce=False)
-            opt_p.step()
-        ms_train_peer, _ = timed(lambda i: train_full_peer(i), K, Wm)
-
     # ---- frame statistics of view 0 (V, I) for the byte model ---------------------------------------------------
     with torch.no_grad():
         g, keep = ops._gaussians(sc["pos"], sc["opacity_raw"], sc["scale_raw"], sc["q_raw"], None, sc["f_dc"],
@@ -584,9 +569,32 @@ def run_b200gs(args):
         cpu_base = {"value": 1.0 / est, "unit": "frames/s", "cores": cores, "torch_threads": torch.get_num_threads(),
                     "kind": "port", "sample": desc}
 
+    # ---- N > 1: the same iteration with the optimizer half done over NVLink peer memory - gradient reduce-scatter +
+    # clip + Adam on the owned shard + parameter all-gather in one kernel (b200gs.PeerAdam, csrc/peer.cu) instead of NCCL
+    # all-reduce + clip + Adam.  Runs after everything else (it re-homes the parameters into the peer-visible buffer)
+    # and may fail without taking the other numbers with it.
+    ms_train_peer = peer_transport = peer_error = None
+    if world > 1:
+        try:
+            opt_p = b200gs.PeerAdam([{"params": [leaves[k]], "lr": lr0[k], "name": k} for k in PARAMS], lr=1e-3, eps=1e-15,
+                                    clip_params=[leaves["pos"]], max_norm=1.0)
+            peer_transport = opt_p.area.transport
+
+            def train_full_peer(i):
+                opt_p.zero_grad(set_to_none=True)
+                train_step_loss_nograd_reset(i, reduce=False)
+                opt_p.step()
+            ms_train_peer, _ = timed(lambda i: train_full_peer(i), K, Wm)
+        except Exception as e:                    # noqa: BLE001 - reported in the JSON line
+            ms_train_peer = None
+            peer_error = f"{type(e).__name__}: {e}"[:300]
+
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            try:
+                dist.destroy_process_group()
+            except Exception:                     # noqa: BLE001 - nothing left to report from this rank
+                pass
         return 0
 
     hbm, peak_src, sm_max = peaks()
@@ -638,7 +646,7 @@ def run_b200gs(args):
                       "views_per_s": world * K / (ms_train_peer * 1e-3), "transport": peer_transport,
                       "step": "the same iteration with b200gs.PeerAdam: gradient reduce-scatter + clip + Adam on the owned "
                               "shard + parameter all-gather in ONE kernel over NVLink peer memory (no NCCL on the data path)"}}
-                     if ms_train_peer else {}),
+                     if ms_train_peer else ({"full_iteration_peer": {"error": peer_error}} if peer_error else {})),
                   "e2e": {"value": K / s_train_e2e, "unit": "it/s", "h2d_bytes_per_step": H * W * 12,
                           "d2h_bytes_per_step": 4}},
         "e2e": {"value": world * K / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 12,
@@ -667,7 +675,10 @@ def run_b200gs(args):
     }
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:                         # noqa: BLE001 - the line is out
+            pass
     return 0
 
 
