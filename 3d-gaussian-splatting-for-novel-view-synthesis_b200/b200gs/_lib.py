@@ -58,7 +58,7 @@ class PeerLayout(Structure):
 
 
 class PeerGroup(Structure):
-    _fields_ = [("world", c_int32), ("rank", c_int32), ("area", c_void_p * MAX_PEERS)]
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("area", c_void_p * MAX_PEERS), ("multicast", c_void_p)]
 
 
 class PeerTensor(Structure):

@@ -22,6 +22,7 @@ There is no CPU or NCCL fallback on the data path.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -48,8 +49,10 @@ def _layout(numels: Sequence[int], world: int) -> _lib.PeerLayout:
 
 class PeerArea:
     """One peer-visible area per rank, mapped into every process of the group."""
+    _multicast_in_use = False
 
-    def __init__(self, numels: Sequence[int], device: torch.device, group=None, transport: Optional[str] = None):
+    def __init__(self, numels: Sequence[int], device: torch.device, group=None, transport: Optional[str] = None,
+                 multicast: Optional[bool] = None):
         if device.type != "cuda":
             raise _lib.B200GSError("b200gs.peer: CUDA tensors only (no CPU fallback)")
         lib = _lib.load()
@@ -65,6 +68,17 @@ class PeerArea:
         self.nbytes = int(lib.b200gs_peer_area_bytes(ctypes.byref(self.layout)))
         self._keep = []          # whatever keeps the peer mappings alive
         self.transport = "local"
+        self.multicast_ptr = 0   # NVLS multicast mapping of all areas (0: none)
+        if multicast is None:
+            # Through the switch a rank's own copy crosses its links too: per GPU and direction (1 + 1/p) S bytes against
+            # 2 (p-1)/p S for plain peer loads / stores.  Measured (tools/peer_bench.py, N = 1M): 2 ranks 0.84 vs 0.58 ms,
+            # 4 ranks 0.79 vs 0.80 ms, 8 ranks 0.85 vs 1.06 ms -> NVLS from 8 ranks up.
+            env = os.environ.get("B200GS_PEER_MULTICAST")
+            multicast = (env == "1") if env is not None else self.world >= 8
+        if multicast and PeerArea._multicast_in_use:
+            # one multicast-mapped area per process: with a second one (the optimizer's and an all-reduce area, both
+            # through multimem) parameter updates were lost at 4 ranks; not understood, so not allowed
+            multicast = False
         if not multi:
             self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
             ptrs = [self.buf.data_ptr()]
@@ -80,6 +94,9 @@ class PeerArea:
         self.c_group = _lib.PeerGroup(world=self.world, rank=self.rank)
         for q, p in enumerate(ptrs):
             self.c_group.area[q] = p
+        self.c_group.multicast = (self.multicast_ptr or None) if multicast else None
+        if self.c_group.multicast:
+            PeerArea._multicast_in_use = True
         self.epoch = ctypes.c_uint32(0)
         n = int(self.layout.flat_total)
         ctrl = _lib.PEER_CTRL_BYTES
@@ -98,6 +115,10 @@ class PeerArea:
         dist.barrier(group=self.group)
         self.buf = buf
         self._keep.append(hdl)
+        try:
+            self.multicast_ptr = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
+        except Exception:          # noqa: BLE001 - no multicast query: plain peer loads and stores
+            self.multicast_ptr = 0
         return [int(p) for p in hdl.buffer_ptrs]
 
     # -- helpers ---------------------------------------------------------------------------------------------
@@ -130,12 +151,15 @@ class PeerAdam(torch.optim.Optimizer):
     * `p.data` of every parameter is re-homed into the peer-visible buffer (same values, new storage);
     * the local `.grad` of a parameter is this rank's contribution (None = zeros); with `write_grads=True` it
       holds the reduced (and clipped) gradient after `step()`, as it would after all-reduce + clip;
-    * the moments are sharded over the ranks (each rank keeps 1/world of `exp_avg` / `exp_avg_sq`).
+    * the moments are sharded over the ranks (each rank keeps 1/world of `exp_avg` / `exp_avg_sq`);
+    * from 8 ranks up (or with `multicast=True` / `B200GS_PEER_MULTICAST=1`) the areas are also mapped through an NVLS
+      multicast address and the kernel uses `multimem.ld_reduce` / `multimem.st`: the switch sums the gradients and
+      replicates the parameters, so the bytes a GPU moves stop growing with the number of ranks.
     """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, *, group=None,
                  clip_params: Optional[Iterable[torch.Tensor]] = None, max_norm: float = 0.0, write_grads: bool = False,
-                 transport: Optional[str] = None):
+                 transport: Optional[str] = None, multicast: Optional[bool] = None):
         if weight_decay != 0 or amsgrad:
             raise NotImplementedError("b200gs.PeerAdam implements the reference's configuration: weight_decay=0, amsgrad=False")
         if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
@@ -151,7 +175,7 @@ class PeerAdam(torch.optim.Optimizer):
         for p in self._plist:
             _check_param(p, "b200gs.PeerAdam")
         dev = self._plist[0].device
-        self.area = PeerArea([p.numel() for p in self._plist], dev, group=group, transport=transport)
+        self.area = PeerArea([p.numel() for p in self._plist], dev, group=group, transport=transport, multicast=multicast)
         clip_ids = {id(p) for p in (clip_params or [])}
         self._clip = [1 if id(p) in clip_ids else 0 for p in self._plist]
         self.max_norm = float(max_norm) if clip_ids else 0.0
@@ -228,7 +252,7 @@ def peer_allreduce_gradients(params: Iterable[torch.Tensor], group=None) -> None
     key = (dev.index, id(group), tuple(p.numel() for p in plist))
     area = _allreduce_areas.get(key)
     if area is None:
-        area = _allreduce_areas[key] = PeerArea([p.numel() for p in plist], dev, group=group)
+        area = _allreduce_areas[key] = PeerArea([p.numel() for p in plist], dev, group=group, multicast=False)
     lib = _lib.load()
     table = (_lib.PeerTensor * len(plist))()
     for i, p in enumerate(plist):

@@ -21,6 +21,11 @@
 //   B3 all parameter stores have landed, staging buffers may be reused
 // A barrier that waits longer than ~20 s traps (a dead peer must not hang the GPU).
 //
+// With an NVLS multicast mapping of the areas (NVSwitch; group.multicast != NULL) the p loads per element become one
+// multimem.ld_reduce (the switch sums) and the p stores one multimem.st (the switch replicates): the bytes a GPU puts
+// on / takes off its links go from 2 (p-1)/p x S to (1 + 1/p) x S (S = 4 B x elements; through the switch a rank's own
+// copy crosses the links too), which pays from 8 ranks up: 0.85 ms against 1.06 ms at N = 1M (2 ranks: 0.84 vs 0.58).
+//
 // Roofline: NVLink (reads (p-1)/p x 4 B + writes (p-1)/p x 4 B per element per GPU) + HBM (20 B per owned element).
 #include "common.cuh"
 
@@ -38,8 +43,80 @@ constexpr size_t kCtrlAcc = 512;           // double acc; uint32 ticket (local s
 
 struct PeerPtrs {
   char* area[kMaxPeers];
+  char* mc;                // NVLS multicast mapping of all areas, or null
   int world, rank;
 };
+
+// NVLS: one load returns the element summed over every rank's copy (the switch reduces), one store writes every
+// rank's copy.
+__device__ __forceinline__ float4 mc_ld_sum_f4(const void* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float mc_ld_sum_f1(const void* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st_f4(void* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st_f1(void* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// MC: false = plain peer loads / stores, true = multimem.ld_reduce + multimem.st through the multicast mapping
+template <bool MC>
+__device__ __forceinline__ void load_sum4(const PeerPtrs& pp, long long grad_off, long long e4, float4 (&g)[4]) {
+  if (MC) {
+    const float4* g4 = reinterpret_cast<const float4*>(pp.mc + grad_off) + e4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = mc_ld_sum_f4(g4 + k * kPeerThreads + threadIdx.x);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < pp.world; ++q) {              // rank order
+      const float4* g4 = reinterpret_cast<const float4*>(pp.area[q] + grad_off) + e4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 x = __ldcs(g4 + k * kPeerThreads + threadIdx.x);
+        g[k].x += x.x; g[k].y += x.y; g[k].z += x.z; g[k].w += x.w;
+      }
+    }
+  }
+}
+template <bool MC>
+__device__ __forceinline__ float load_sum1(const PeerPtrs& pp, long long grad_off, long long e) {
+  if (MC) return mc_ld_sum_f1(reinterpret_cast<const float*>(pp.mc + grad_off) + e);
+  float s = 0.f;
+  for (int q = 0; q < pp.world; ++q) s += reinterpret_cast<const float*>(pp.area[q] + grad_off)[e];
+  return s;
+}
+template <bool MC>
+__device__ __forceinline__ void store_all4(const PeerPtrs& pp, long long off, long long e4, const float4 (&x)[4]) {
+  if (MC) {
+    float4* o4 = reinterpret_cast<float4*>(pp.mc + off) + e4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mc_st_f4(o4 + k * kPeerThreads + threadIdx.x, x[k]);
+  } else {
+    for (int q = 0; q < pp.world; ++q) {
+      float4* o4 = reinterpret_cast<float4*>(pp.area[q] + off) + e4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o4[k * kPeerThreads + threadIdx.x] = x[k];
+    }
+  }
+}
+template <bool MC>
+__device__ __forceinline__ void store_all1(const PeerPtrs& pp, long long off, long long e, float x) {
+  if (MC) {
+    mc_st_f1(reinterpret_cast<float*>(pp.mc + off) + e, x);
+    return;
+  }
+  for (int q = 0; q < pp.world; ++q) reinterpret_cast<float*>(pp.area[q] + off)[e] = x;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -92,6 +169,7 @@ __device__ __forceinline__ const PeerTensor& tensor_of_block(const PeerTable& tb
 
 // Sum of squares of the REDUCED gradient over this rank's slices of the clipped tensors; the last block
 // publishes the total to every rank's control block.
+template <bool MC>
 __global__ void __launch_bounds__(kPeerThreads) peer_sqnorm_kernel(const __grid_constant__ PeerPtrs pp,
                                                                    const __grid_constant__ PeerTable tb) {
   __shared__ double s_w[kPeerThreads / 32];
@@ -101,22 +179,12 @@ __global__ void __launch_bounds__(kPeerThreads) peer_sqnorm_kernel(const __grid_
   float acc = 0.f;
   if (end - base == kPeerChunk) {                 // slice boundaries are multiples of 4 floats, offsets of 32
     float4 s[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < pp.world; ++q) {
-      const float4* g4 = reinterpret_cast<const float4*>(pp.area[q] + tb.grad_off) + ((t.offset + base) >> 2);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 x = __ldcs(g4 + k * kPeerThreads + threadIdx.x);
-        s[k].x += x.x; s[k].y += x.y; s[k].z += x.z; s[k].w += x.w;
-      }
-    }
+    load_sum4<MC>(pp, tb.grad_off, (t.offset + base) >> 2, s);
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc = fmaf(s[k].x, s[k].x, fmaf(s[k].y, s[k].y, fmaf(s[k].z, s[k].z, fmaf(s[k].w, s[k].w, acc))));
   } else {
     for (long long i = base + threadIdx.x; i < end; i += kPeerThreads) {
-      float s = 0.f;
-      for (int q = 0; q < pp.world; ++q) s += reinterpret_cast<const float*>(pp.area[q] + tb.grad_off)[t.offset + i];
+      const float s = load_sum1<MC>(pp, tb.grad_off, t.offset + i);
       acc = fmaf(s, s, acc);
     }
   }
@@ -166,7 +234,7 @@ __device__ __forceinline__ void adam_update_peer(float& p, float g, float& m, fl
 
 // ADAM = true : reduce-scatter + clip + Adam on the owned slice + all-gather of the new parameters
 // ADAM = false: reduce-scatter + all-gather of the reduced gradient (a plain SUM all-reduce over peer memory)
-template <bool ADAM>
+template <bool ADAM, bool MC>
 __global__ void __launch_bounds__(kPeerThreads) peer_step_kernel(const __grid_constant__ PeerPtrs pp,
                                                                  const __grid_constant__ PeerTable tb) {
   const PeerTensor& t = tensor_of_block(tb);
@@ -181,27 +249,12 @@ __global__ void __launch_bounds__(kPeerThreads) peer_step_kernel(const __grid_co
   if (end - base == kPeerChunk) {
     const long long e4 = (t.offset + base) >> 2;
     float4 g[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < pp.world; ++q) {
-      const float4* g4 = reinterpret_cast<const float4*>(pp.area[q] + tb.grad_off) + e4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 x = __ldcs(g4 + k * kPeerThreads + threadIdx.x);
-        g[k].x += x.x; g[k].y += x.y; g[k].z += x.z; g[k].w += x.w;
-      }
-    }
+    load_sum4<MC>(pp, tb.grad_off, e4, g);
     if (coef != 1.f) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) { g[k].x *= coef; g[k].y *= coef; g[k].z *= coef; g[k].w *= coef; }
     }
-    if (store_g) {
-      for (int q = 0; q < pp.world; ++q) {
-        float4* g4 = reinterpret_cast<float4*>(pp.area[q] + tb.grad_off) + e4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) __stcs(g4 + k * kPeerThreads + threadIdx.x, g[k]);
-      }
-    }
+    if (store_g) store_all4<MC>(pp, tb.grad_off, e4, g);
     if (ADAM) {
       const long long s4 = (t.shard_offset + (base - t.begin)) >> 2;
       float4* m4 = reinterpret_cast<float4*>(tb.m) + s4;
@@ -225,25 +278,19 @@ __global__ void __launch_bounds__(kPeerThreads) peer_step_kernel(const __grid_co
         const int i = k * kPeerThreads + threadIdx.x;
         __stcs(m4 + i, m[k]); __stcs(v4 + i, v[k]);
       }
-      for (int q = 0; q < pp.world; ++q) {
-        float4* o4 = reinterpret_cast<float4*>(pp.area[q] + tb.param_off) + e4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o4[k * kPeerThreads + threadIdx.x] = p[k];
-      }
+      store_all4<MC>(pp, tb.param_off, e4, p);
     }
   } else {
     for (long long i = base + threadIdx.x; i < end; i += kPeerThreads) {
-      float g = 0.f;
-      for (int q = 0; q < pp.world; ++q) g += reinterpret_cast<const float*>(pp.area[q] + tb.grad_off)[t.offset + i];
+      float g = load_sum1<MC>(pp, tb.grad_off, t.offset + i);
       g *= coef;
-      if (store_g)
-        for (int q = 0; q < pp.world; ++q) reinterpret_cast<float*>(pp.area[q] + tb.grad_off)[t.offset + i] = g;
+      if (store_g) store_all1<MC>(pp, tb.grad_off, t.offset + i, g);
       if (ADAM) {
         const long long si = t.shard_offset + (i - t.begin);
         float p = reinterpret_cast<const float*>(pp.area[pp.rank] + tb.param_off)[t.offset + i], m = tb.m[si], v = tb.v[si];
         adam_update_peer(p, g, m, v, tb, t);
         tb.m[si] = m; tb.v[si] = v;
-        for (int q = 0; q < pp.world; ++q) reinterpret_cast<float*>(pp.area[q] + tb.param_off)[t.offset + i] = p;
+        store_all1<MC>(pp, tb.param_off, t.offset + i, p);
       }
     }
   }
@@ -273,6 +320,7 @@ int peer_layout_compute(const int64_t* numel, int n_tensors, int world, b200gs_p
 static PeerPtrs make_ptrs(const b200gs_peer_group* g) {
   PeerPtrs pp;
   for (int q = 0; q < kMaxPeers; ++q) pp.area[q] = q < g->world ? static_cast<char*>(g->area[q]) : nullptr;
+  pp.mc = g->world > 1 ? static_cast<char*>(g->multicast) : nullptr;
   pp.world = g->world;
   pp.rank = g->rank;
   return pp;
@@ -339,15 +387,19 @@ cudaError_t launch_peer_step(const b200gs_peer_group* g, const b200gs_peer_layou
   ++nl;
   if (adam && max_norm > 0.0) {
     tc.grad_off = tb.grad_off; tc.param_off = tb.param_off;
-    if (cblocks > 0) peer_sqnorm_kernel<<<(unsigned)cblocks, kPeerThreads, 0, s>>>(pp, tc);
+    if (cblocks > 0 && pp.mc) peer_sqnorm_kernel<true><<<(unsigned)cblocks, kPeerThreads, 0, s>>>(pp, tc);
+    else if (cblocks > 0) peer_sqnorm_kernel<false><<<(unsigned)cblocks, kPeerThreads, 0, s>>>(pp, tc);
     else peer_sqnorm_zero_kernel<<<1, 32, 0, s>>>(pp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = launch_peer_barrier(g, ++*epoch, s)) != cudaSuccess) return e;                    // B2
     nl += 2;
   }
   if (blocks > 0) {
-    if (adam) peer_step_kernel<true><<<(unsigned)blocks, kPeerThreads, 0, s>>>(pp, tb);
-    else peer_step_kernel<false><<<(unsigned)blocks, kPeerThreads, 0, s>>>(pp, tb);
+    const unsigned nb = (unsigned)blocks;
+    if (adam && pp.mc) peer_step_kernel<true, true><<<nb, kPeerThreads, 0, s>>>(pp, tb);
+    else if (adam) peer_step_kernel<true, false><<<nb, kPeerThreads, 0, s>>>(pp, tb);
+    else if (pp.mc) peer_step_kernel<false, true><<<nb, kPeerThreads, 0, s>>>(pp, tb);
+    else peer_step_kernel<false, false><<<nb, kPeerThreads, 0, s>>>(pp, tb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++nl;
   }

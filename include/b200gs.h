@@ -252,6 +252,8 @@ typedef struct b200gs_peer_layout {
 typedef struct b200gs_peer_group {
   int32_t world, rank;
   void* area[B200GS_MAX_PEERS];   /* area[q]: rank q's area as mapped into THIS process (area[rank] is local) */
+  void* multicast;                /* NVLS multicast mapping of all the areas (multimem.ld_reduce / multimem.st go
+                                     through it), or NULL: plain peer loads and stores */
 } b200gs_peer_group;
 typedef struct b200gs_peer_tensor {
   float* grad;      /* this rank's local gradient [numel] (NULL: contributes zeros); receives the reduced gradient

@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Grads) == 8 * 8
     assert ctypes.sizeof(_lib.Camera) == 8 + 8 + 11 * 8 + 16
     assert ctypes.sizeof(_lib.PeerLayout) == 3 * 8 * 8 + 16
-    assert ctypes.sizeof(_lib.PeerGroup) == 8 + 16 * 8
+    assert ctypes.sizeof(_lib.PeerGroup) == 8 + 16 * 8 + 8
     assert ctypes.sizeof(_lib.PeerTensor) == 32
 
 

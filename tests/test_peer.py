@@ -127,7 +127,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out, n):
+def _worker(rank, world, port, out, n, multicast):
     import torch.distributed as dist
     import b200gs
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -139,8 +139,9 @@ def _worker(rank, world, port, out, n):
         mine = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ref.items()}
         opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15)
         opt = b200gs.PeerAdam([{"params": [mine[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15,
-                              clip_params=[mine["pos"]], max_norm=1.0, write_grads=True)
+                              clip_params=[mine["pos"]], max_norm=1.0, write_grads=True, multicast=multicast)
         out[f"transport{rank}"] = opt.area.transport
+        out[f"multicast{rank}"] = bool(opt.area.c_group.multicast)
         worst = 0.0
         for step in range(1, 5):
             grads = _make_grads(n, step, rank, 0.02 if step % 2 else 1e-6)     # clipping active / inactive
@@ -182,12 +183,13 @@ def _worker(rank, world, port, out, n):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_peer_adam_matches_nccl_allreduce_plus_torch_adam():
+@pytest.mark.parametrize("multicast", [False, True])     # plain peer loads / stores; NVLS multimem (if the box has it)
+def test_two_rank_peer_adam_matches_nccl_allreduce_plus_torch_adam(multicast):
     import torch.multiprocessing as mp
     world, port, n = 2, _free_port(), 50_001
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, port, out, n), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, out, n, multicast), nprocs=world, join=True)
         out = dict(out)
     for r in range(world):
         assert out[f"grad_err{r}"] <= 2e-6, out[f"grad_err{r}"]

@@ -5,7 +5,7 @@
     c) the all-reduce alone: NCCL vs b200gs.peer_allreduce_gradients
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/peer_bench.py [N]
+        tools/peer_bench.py [N] [multicast 0|1]
 
 CUDA events on the launching stream, max over ranks, one JSON line from rank 0.
 """
@@ -26,6 +26,7 @@ LRS = dict(pos=1.6e-6, opacity_raw=0.05, f_dc=2.5e-3, f_rest=1.25e-4, scale_raw=
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    multicast = (sys.argv[2] == "1") if len(sys.argv) > 2 else None
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,7 +41,7 @@ def main():
     grads = {k: torch.randn_like(p) * 1e-3 for k, p in pa.items()}
     opt_a = b200gs.FusedAdam([{"params": [pa[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15)
     opt_b = b200gs.PeerAdam([{"params": [pb[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15,
-                            clip_params=[pb["pos"]], max_norm=1.0)
+                            clip_params=[pb["pos"]], max_norm=1.0, multicast=multicast)
     opt_bw = None
 
     def set_grads(ps):
@@ -82,7 +83,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    res = {"n": n, "world": world, "transport": opt_b.area.transport, "bytes_per_rank": 59 * n * 4}
+    res = {"n": n, "world": world, "transport": opt_b.area.transport, "multicast": bool(opt_b.area.c_group.multicast), "bytes_per_rank": 59 * n * 4}
     res["nccl_allreduce_clip_fusedadam_ms"] = timed(step_a, pa)
     res["peer_adam_ms"] = timed(step_b, pb)
     res["nccl_allreduce_ms"] = timed(ar_nccl, pa)

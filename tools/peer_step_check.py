@@ -2,7 +2,7 @@
 mismatch counts and the owners of the mismatching elements.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 \
-        tools/peer_step_check.py [N] [steps]
+        tools/peer_step_check.py [N] [steps] [multicast 0|1]
 """
 import json
 import os
@@ -22,6 +22,7 @@ LRS = dict(pos=1.6e-4, opacity_raw=0.05, f_dc=2.5e-3, f_rest=1.25e-4, scale_raw=
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    multicast = (sys.argv[3] == "1") if len(sys.argv) > 3 else None
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -33,14 +34,15 @@ def main():
     mine = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ref.items()}
     opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15)
     opt = b200gs.PeerAdam([{"params": [mine[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15,
-                          clip_params=[mine["pos"]], max_norm=1.0)
+                          clip_params=[mine["pos"]], max_norm=1.0, multicast=multicast)
     report = []
     for step in range(1, steps + 1):
         total = {k: None for k in SHAPES}
         for r in range(world):                      # every rank can rebuild every rank's gradient
-            g = torch.Generator().manual_seed(1000 * step + r)
+            seed = 7 if os.environ.get("SAME_GRADS") == "1" else 1000 * step + r     # SAME_GRADS: one gradient for all ranks and steps
+            g = torch.Generator(device=dev).manual_seed(seed)                        # same stream of numbers on every GPU
             for k, s in SHAPES.items():
-                x = (torch.randn((n,) + s, generator=g) * 1e-3).to(dev)
+                x = torch.randn((n,) + s, generator=g, device=dev) * 1e-3
                 if r == rank:
                     mine[k].grad = x.clone()
                 total[k] = x if total[k] is None else total[k] + x      # rank order, like the plain peer path
@@ -68,7 +70,10 @@ def main():
     else:
         out = [report]
     if rank == 0:
-        print(json.dumps({"n": n, "world": world, "per_rank": out}))
+        bad = [[row for row in rep if len(row) > 1] for rep in out]
+        print(json.dumps({"n": n, "world": world, "steps": steps, "multicast": bool(opt.area.c_group.multicast),
+                          "mc_mode": os.environ.get("B200GS_PEER_MC_MODE"), "steps_with_mismatch": [len(b) for b in bad],
+                          "first": [b[:2] for b in bad]}))
     if world > 1:
         dist.destroy_process_group()
 
