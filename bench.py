@@ -578,7 +578,7 @@ def run_b200gs(args):
         try:
             opt_p = b200gs.PeerAdam([{"params": [leaves[k]], "lr": lr0[k], "name": k} for k in PARAMS], lr=1e-3, eps=1e-15,
                                     clip_params=[leaves["pos"]], max_norm=1.0)
-            peer_transport = opt_p.area.transport
+            peer_transport = opt_p.area.transport + ("+nvls" if opt_p.area.c_group.multicast else "")
 
             def train_full_peer(i):
                 opt_p.zero_grad(set_to_none=True)
