@@ -112,4 +112,22 @@ void hc_backward(int n, const float* pos, const float* scale_raw, const float* q
   }
 }
 
+// Optimizer arithmetic of csrc/optim.cu / csrc/peer.cu: the rescaled sqrt / division next to the plain IEEE operations,
+// and one Adam update per element.
+void hc_sqrt_div(int n, const float* a, const float* b, float* sqrt_resc, float* sqrt_plain, float* div_resc,
+                 float* div_plain) {
+  for (int i = 0; i < n; ++i) {
+    sqrt_resc[i] = gs::sqrt_no_slow_path(a[i] < 0.f ? -a[i] : a[i]);
+    sqrt_plain[i] = sqrtf(a[i] < 0.f ? -a[i] : a[i]);
+    div_resc[i] = gs::div_no_slow_path(a[i], b[i]);
+    div_plain[i] = a[i] / b[i];
+  }
+}
+void hc_adam(int n, float* p, const float* g, float* m, float* v, double beta1, double beta2, double eps, float step_size,
+             float bc2_sqrt) {
+  // the constants as launch_adam_step / launch_peer_step form them: in double on the host, then rounded to fp32
+  const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), e = (float)eps;
+  for (int i = 0; i < n; ++i) gs::adam_update_f32(p[i], g[i], m[i], v[i], omb1, b2, omb2, e, step_size, bc2_sqrt);
+}
+
 }  // extern "C"
