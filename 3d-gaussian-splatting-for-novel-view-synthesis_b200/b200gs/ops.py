@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -332,6 +333,46 @@ def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color,
     return image, frame
 
 
+# Gradient sinks: a caller that is going to hand the leaf gradients to other GPUs (b200gs.PeerAdam) registers, per leaf,
+# a view of its peer-visible staging buffer; the backward then writes that leaf's gradient THERE and autograd adopts the
+# tensor as `.grad` (it takes over a gradient it is handed instead of copying it), so the 236 MB staging copy of the
+# optimizer step disappears.  A sink is handed out at most once between two optimizer steps and only while the leaf
+# has no `.grad` yet (a second backward into the same leaf - several views per iteration - gets fresh tensors, which
+# autograd adds into the first one in place).
+_grad_sinks = {}      # data_ptr of the leaf -> [weakref(leaf), sink view, handed out]
+
+
+def register_grad_sink(leaf: torch.Tensor, view: torch.Tensor) -> None:
+    _grad_sinks[leaf.data_ptr()] = [weakref.ref(leaf), view, False]
+
+
+def release_grad_sinks(leaves) -> None:
+    """The optimizer has consumed the gradients: the sinks may be handed out again."""
+    for p in leaves:
+        e = _grad_sinks.get(p.data_ptr())
+        if e is not None:
+            e[2] = False
+
+
+def unregister_grad_sinks(leaves) -> None:
+    for p in leaves:
+        _grad_sinks.pop(p.data_ptr(), None)
+
+
+def _grad_sink_for(src: torch.Tensor, shape):
+    e = _grad_sinks.get(src.data_ptr())
+    if e is None or e[2]:
+        return None
+    leaf = e[0]()
+    if leaf is None:
+        _grad_sinks.pop(src.data_ptr(), None)
+        return None
+    if leaf.grad is not None or tuple(e[1].shape) != tuple(shape) or e[1].device != src.device:
+        return None
+    e[2] = True
+    return e[1]
+
+
 class _Rasterize(torch.autograd.Function):
     """render.py:62-410 (+ gaussian.py / spherical_harmonics.py when raw parameters are given)."""
 
@@ -360,7 +401,11 @@ class _Rasterize(torch.autograd.Function):
                     f_rest=(n, 45), color=(n, 3))
         out = {}
         for name, src in zip(names, frame.keep):
-            out[name] = None if src is None else torch.empty(dims[name], dtype=torch.float32, device=dev)
+            if src is None:
+                out[name] = None
+                continue
+            sink = _grad_sink_for(src, dims[name]) if _grad_sinks else None
+            out[name] = sink if sink is not None else torch.empty(dims[name], dtype=torch.float32, device=dev)
         grads = Grads(**{k: (None if v is None else v.data_ptr()) for k, v in out.items()})
         with torch.cuda.device(dev):
             frame.backward(gi, grads)

@@ -151,6 +151,8 @@ class PeerAdam(torch.optim.Optimizer):
     * `p.data` of every parameter is re-homed into the peer-visible buffer (same values, new storage);
     * the local `.grad` of a parameter is this rank's contribution (None = zeros); with `write_grads=True` it
       holds the reduced (and clipped) gradient after `step()`, as it would after all-reduce + clip;
+    * gradients that come out of `b200gs.render`'s backward are written straight into the peer-visible staging
+      buffer (`.grad` is then a view of it) - no staging copy; any other gradient tensor is copied there by `step()`;
     * the moments are sharded over the ranks (each rank keeps 1/world of `exp_avg` / `exp_avg_sq`);
     * from 8 ranks up (or with `multicast=True` / `B200GS_PEER_MULTICAST=1`) the areas are also mapped through an NVLS
       multicast address and the kernel uses `multimem.ld_reduce` / `multimem.st`: the switch sums the gradients and
@@ -191,6 +193,9 @@ class PeerAdam(torch.optim.Optimizer):
                                group=group)
                 torch.cuda.synchronize(dev)
                 dist.barrier(group=group)
+        # the render backward writes these leaves' gradients straight into the staging buffer (ops.register_grad_sink)
+        for i, p in enumerate(self._plist):
+            ops.register_grad_sink(p, self.area.view(self.area.flat_grads, i, p.shape))
         n_shard = max(1, int(self.area.layout.shard_total))
         self.exp_avg = torch.zeros(n_shard, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n_shard, dtype=torch.float32, device=dev)
@@ -231,7 +236,14 @@ class PeerAdam(torch.optim.Optimizer):
                                                  grp["betas"][0], grp["betas"][1], grp["eps"], self.max_norm,
                                                  1 if self.write_grads else 0, ctypes.byref(self.area.epoch),
                                                  ops._ptr(self.total_norm), ops._stream(dev)), "peer_adam_step")
+        ops.release_grad_sinks(self._plist)
         return loss
+
+    def __del__(self):
+        try:
+            ops.unregister_grad_sinks(self._plist)
+        except Exception:          # noqa: BLE001 - interpreter shutdown
+            pass
 
 
 _allreduce_areas = {}

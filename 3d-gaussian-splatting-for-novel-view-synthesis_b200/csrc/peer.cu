@@ -354,7 +354,9 @@ cudaError_t launch_peer_step(const b200gs_peer_group* g, const b200gs_peer_layou
     const b200gs_peer_tensor& a = tensors[k];
     if (a.numel <= 0) continue;
     // stage: local gradient -> this rank's peer-visible staging buffer
-    if (a.grad) e = cudaMemcpyAsync(stage + L->offset[k], a.grad, (size_t)a.numel * 4, cudaMemcpyDeviceToDevice, s);
+    // (a gradient that already lives in the staging buffer - the render backward wrote it there - is not copied)
+    if (a.grad == stage + L->offset[k]) e = cudaSuccess;
+    else if (a.grad) e = cudaMemcpyAsync(stage + L->offset[k], a.grad, (size_t)a.numel * 4, cudaMemcpyDeviceToDevice, s);
     else e = cudaMemsetAsync(stage + L->offset[k], 0, (size_t)a.numel * 4, s);
     if (e != cudaSuccess) return e;
     PeerTensor t;
@@ -408,7 +410,7 @@ cudaError_t launch_peer_step(const b200gs_peer_group* g, const b200gs_peer_layou
   if (!adam || write_grads) {          // hand the reduced gradients back to the caller's tensors
     for (int k = 0; k < n_tensors; ++k) {
       const b200gs_peer_tensor& a = tensors[k];
-      if (a.numel <= 0 || !a.grad) continue;
+      if (a.numel <= 0 || !a.grad || a.grad == stage + L->offset[k]) continue;
       if ((e = cudaMemcpyAsync(a.grad, stage + L->offset[k], (size_t)a.numel * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess)
         return e;
     }

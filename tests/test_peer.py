@@ -199,3 +199,74 @@ def test_two_rank_peer_adam_matches_nccl_allreduce_plus_torch_adam(multicast):
     for k in SHAPES:                          # the replicas stay bit-identical
         assert torch.equal(out["params0"][k], out["params1"][k]), k
         assert torch.equal(out["allreduce0"][k], out["allreduce1"][k]), k
+
+
+@pytest.mark.gpu
+def test_render_backward_writes_gradients_into_the_staging_buffer():
+    """Gradient sinks (b200gs/ops.py): with a PeerAdam constructed over the leaves, the backward of b200gs.render writes
+    the leaf gradients straight into the peer-visible staging buffer and autograd adopts those tensors as `.grad`
+    (no staging copy in step()); values, accumulation over several views and the optimizer step stay what they were."""
+    import b200gs
+    from oracle import gs_oracle as O
+    dev = torch.device("cuda", 0)
+    names = ("pos", "opacity_raw", "f_dc", "f_rest", "scale_raw", "q_raw")
+    sc = O.make_scene(6000, seed=8, log_scale=-3.4)
+    cams = [O.make_camera(200, 136, view=v, n_views=4) for v in range(2)]
+    w = [torch.rand(136, 200, 3, generator=torch.Generator().manual_seed(20 + v)).to(dev) for v in range(2)]
+
+    def loss_of(leaves, v):
+        cam = cams[v]
+        c2w = cam["c2w"].to(dev)
+        sg = b200gs.build_sigma_from_params(leaves["scale_raw"], leaves["q_raw"])
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        img = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sg, c2w, cam["H"], cam["W"], cam["fx"], cam["fy"],
+                            cam["cx"], cam["cy"])
+        return (img * w[v]).sum()
+
+    plain = {k: torch.nn.Parameter(sc[k].to(dev)) for k in names}
+    mine = {k: torch.nn.Parameter(sc[k].to(dev)) for k in names}
+    opt = b200gs.PeerAdam([{"params": [mine[k]], "lr": LRS[k]} for k in names], lr=1e-3, eps=1e-15,
+                          clip_params=[mine["pos"]], max_norm=1.0)
+    sinks = {k: opt.area.view(opt.area.flat_grads, i, mine[k].shape) for i, k in enumerate(names)}
+    # one view: every gradient lands in its sink
+    loss_of(plain, 0).backward()
+    loss_of(mine, 0).backward()
+    for k in names:
+        assert mine[k].grad.data_ptr() == sinks[k].data_ptr(), k
+        assert _rel(mine[k].grad, plain[k].grad) <= 1e-5, k
+    # the step on those gradients = clip + Adam on a copy of them
+    ref = {k: torch.nn.Parameter(sc[k].to(dev)) for k in names}
+    for k in names:
+        ref[k].grad = mine[k].grad.clone()
+    opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": LRS[k]} for k in names], lr=1e-3, eps=1e-15)
+    torch.nn.utils.clip_grad_norm_(ref["pos"], max_norm=1.0)
+    opt_ref.step()
+    opt.step()
+    for k in names:
+        assert _rel(mine[k].detach(), ref[k].detach()) <= 2e-6, k
+    # two views, one backward (scripts/train.py:471-530): the sum, whichever tensor autograd ends up keeping
+    for leaves in (plain, mine):
+        for p in leaves.values():
+            p.grad = None
+    with torch.no_grad():
+        for k in names:
+            plain[k].copy_(mine[k])
+    (loss_of(plain, 0) + loss_of(plain, 1)).backward()
+    (loss_of(mine, 0) + loss_of(mine, 1)).backward()
+    for k in names:
+        assert _rel(mine[k].grad, plain[k].grad) <= 1e-5, k
+    # two backward calls without a step in between: the second one accumulates into the first
+    for p in mine.values():
+        p.grad = None
+    opt.step()                                  # (consumes nothing: no gradients; frees the sinks)
+    with torch.no_grad():
+        for k in names:
+            plain[k].copy_(mine[k])
+    for p in plain.values():
+        p.grad = None
+    for v in (0, 1):
+        loss_of(plain, v).backward()
+        loss_of(mine, v).backward()
+    for k in names:
+        assert mine[k].grad.data_ptr() == sinks[k].data_ptr(), k
+        assert _rel(mine[k].grad, plain[k].grad) <= 1e-5, k
