@@ -1,3 +1,4 @@
+"""adam_step stand-alone at N = 1M: b200gs.FusedAdam next to torch.optim.Adam (foreach) and torch's fused=True (CUDA events)."""
 import sys, os
 sys.path.insert(0, "3d-gaussian-splatting-for-novel-view-synthesis_b200")
 import torch, b200gs

@@ -1,3 +1,4 @@
+"""Host-side cost of clip + optimizer step at a small N (5 000 Gaussians): torch vs b200gs, with and without empty_cache()."""
 import sys, time
 sys.path.insert(0, "3d-gaussian-splatting-for-novel-view-synthesis_b200")
 import torch, b200gs

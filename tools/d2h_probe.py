@@ -1,3 +1,4 @@
+"""Device-to-host copy rate of one 1080p frame (fp32 and uint8) into pinned memory."""
 import torch, time
 H, W = 1080, 1920
 img = torch.rand(H, W, 3, device="cuda")

@@ -1,3 +1,4 @@
+"""Headline workload: frames/s one frame at a time against the software-pipelined RenderPipeline (B200GS_FRONT_STREAMS, LAG)."""
 import os, sys, time
 ROOT = os.getcwd()
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting-for-novel-view-synthesis_b200"))

@@ -1,3 +1,4 @@
+"""Quick wall-clock timing of forward and forward + backward on the headline workload."""
 import sys, time, torch
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/3d-gaussian-splatting-for-novel-view-synthesis_b200')
 import b200gs
