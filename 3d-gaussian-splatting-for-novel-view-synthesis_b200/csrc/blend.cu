@@ -26,7 +26,7 @@ namespace gs {
 constexpr int kBlendThreads = 256;
 constexpr int kBlendWarps = kBlendThreads / 32;
 constexpr uint32_t kCountMask = 0x1FFFFFFFu;
-constexpr float kExpScale = -0.72134752044448170368f;   // -log2(e)/2 : exp(-q/2) = 2^(kExpScale*q)
+// (the records arrive pre-scaled by c = -log2(e)/2 = -0.7213475: exp(-q/2) = 2^(c q); see write_splat_record in preprocess.cu)
 constexpr uint32_t kRecStride = kBlendThreads * 16;      // bytes between the staged float4 planes
 
 struct PixelCoord { int px, py; bool inside; };
