@@ -12,8 +12,9 @@ from .install import install, uninstall
 from .optim import FusedAdam, clip_grad_norm_
 from .peer import PeerAdam, peer_allreduce_gradients
 from .io import load_cameras, load_gaussians, save_gaussians
+from .densify import densify_and_prune, densify_tensors
 from ._lib import B200GSError, LIB_PATH, load as load_library
 
 __all__ = ["build_sigma_from_params", "evaluate_sh", "render", "compute_loss", "compute_loss_tensors", "l1_loss",
-           "ssim_loss", "to_uint8", "RenderPipeline", "FusedAdam", "clip_grad_norm_", "PeerAdam", "peer_allreduce_gradients", "load_gaussians", "save_gaussians", "load_cameras", "install", "uninstall", "B200GSError",
+           "ssim_loss", "to_uint8", "RenderPipeline", "FusedAdam", "clip_grad_norm_", "PeerAdam", "peer_allreduce_gradients", "load_gaussians", "save_gaussians", "load_cameras", "densify_and_prune", "densify_tensors", "install", "uninstall", "B200GSError",
            "LIB_PATH", "load_library"]

@@ -97,6 +97,10 @@ SYMBOLS = {
     "b200gs_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_double, c_double, c_double, c_void_p]),
     "b200gs_clip_workspace_bytes": (c_size_t, [ctypes.c_int64]),
     "b200gs_clip_grad_norm": (c_int, [c_void_p, ctypes.c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b200gs_densify_workspace_bytes": (c_size_t, [c_int32]),
+    "b200gs_densify_plan": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p, c_size_t,
+                                    c_void_p, c_void_p]),
+    "b200gs_densify_apply": (c_int, [c_int32, c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]),
     "b200gs_peer_layout_compute": (c_int, [POINTER(ctypes.c_int64), c_int32, c_int32, POINTER(PeerLayout)]),
     "b200gs_peer_area_bytes": (c_size_t, [POINTER(PeerLayout)]),
     "b200gs_peer_barrier": (c_int, [POINTER(PeerGroup), POINTER(c_uint32), c_void_p]),

@@ -32,6 +32,7 @@ SOURCES = {
     "loss.cu": [],
     "optim.cu": [],
     "peer.cu": [],
+    "densify.cu": [],
     "api.cu": [],
 }
 HEADERS = ["common.cuh", "gs_math.cuh", os.path.join(INCLUDE, "b200gs.h")]

@@ -339,6 +339,31 @@ int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* wor
   return B200GS_OK;
 }
 
+size_t b200gs_densify_workspace_bytes(int32_t n) { return gs::densify_workspace_bytes(n); }
+
+int b200gs_densify_plan(int32_t n, const float* opacity_raw, const float* scale_raw, const float* pos_grad,
+                        double opacity_threshold, double max_grad, double scale_threshold, void* workspace,
+                        size_t workspace_bytes, uint32_t* counts_host, void* stream) {
+  if (n < 0 || !workspace || (n > 0 && (!opacity_raw || !scale_raw))) return fail(B200GS_ERR_ARG, "densify_plan: null argument");
+  if (workspace_bytes < gs::densify_workspace_bytes(n)) return fail(B200GS_ERR_WORKSPACE, "densify_plan: workspace too small");
+  CU(gs::launch_densify_plan(n, opacity_raw, scale_raw, pos_grad, opacity_threshold, max_grad, scale_threshold, workspace,
+                             counts_host, (cudaStream_t)stream));
+  g_launches.fetch_add(n > 0 ? 4 : 0, std::memory_order_relaxed);
+  return B200GS_OK;
+}
+
+int b200gs_densify_apply(int32_t n, const void* workspace, size_t workspace_bytes, const float* const* in6,
+                         float* const* out6, const float* noise, void* stream) {
+  if (n < 0 || !workspace || !in6 || !out6) return fail(B200GS_ERR_ARG, "densify_apply: null argument");
+  if (workspace_bytes < gs::densify_workspace_bytes(n)) return fail(B200GS_ERR_WORKSPACE, "densify_apply: workspace too small");
+  if (n > 0)
+    for (int t = 0; t < 6; ++t)
+      if (!in6[t] || !out6[t]) return fail(B200GS_ERR_ARG, "densify_apply: null tensor");
+  CU(gs::launch_densify_apply(n, workspace, in6, out6, noise, (cudaStream_t)stream));
+  g_launches.fetch_add(n > 0 ? 6 : 0, std::memory_order_relaxed);
+  return B200GS_OK;
+}
+
 int b200gs_peer_layout_compute(const int64_t* numel, int32_t n_tensors, int32_t world, b200gs_peer_layout* out) {
   if (gs::peer_layout_compute(numel, n_tensors, world, out) != 0)
     return fail(B200GS_ERR_ARG, "peer_layout_compute: need 0 <= n_tensors <= 8, 1 <= world <= 16, numel >= 0");

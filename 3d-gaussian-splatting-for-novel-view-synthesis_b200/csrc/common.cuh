@@ -180,6 +180,14 @@ size_t clip_workspace_bytes(long long numel);
 cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
                                   cudaStream_t s);
 
+// densify.cu: prune / split / clone as stream compaction
+size_t densify_workspace_bytes(int n);
+cudaError_t launch_densify_plan(int n, const float* opacity_raw, const float* scale_raw, const float* pos_grad,
+                                double thr_op, double max_grad, double thr_scale, void* ws, uint32_t* counts_host,
+                                cudaStream_t s);
+cudaError_t launch_densify_apply(int n, const void* ws, const float* const in[6], float* const out[6], const float* noise,
+                                 cudaStream_t s);
+
 // peer.cu: data-parallel optimizer step over NVLink peer memory
 int peer_layout_compute(const int64_t* numel, int n_tensors, int world, b200gs_peer_layout* out);
 cudaError_t launch_peer_barrier(const b200gs_peer_group* g, uint32_t epoch, cudaStream_t s);

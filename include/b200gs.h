@@ -226,6 +226,22 @@ size_t b200gs_clip_workspace_bytes(int64_t numel);
 int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* workspace, size_t workspace_bytes,
                           float* total_norm_out, void* stream);
 
+/* scripts/train.py:89-195  GaussianModel.densify_and_prune (+ _prune_points / _split_points / _clone_points), called
+ * every 100 iterations (train.py:544-557): prune rows with sigmoid(opacity_raw) < opacity_threshold; of the kept rows
+ * with ||pos_grad||_2 > max_grad, append a displaced, shrunk copy of the large ones (max exp(scale_raw) >
+ * scale_threshold: pos + (noise * exp(scale_raw)) * 0.1, scale_raw - 0.5) and an identical copy of the small ones.
+ * plan():  flags + three scans into `workspace` (b200gs_densify_workspace_bytes(n) bytes, caller-owned); the counts
+ *          {n_keep, n_split, n_clone} are copied to counts_host (3 x uint32, pinned or pageable) on `stream`.
+ * apply(): in[t] -> out[t] for the six tensors in the order pos[3] opacity_raw[1] f_dc[3] f_rest[45] scale_raw[3] q_raw[4];
+ *          out[t] has n_keep + n_split + n_clone rows (kept rows, then split copies, then clones, each in order);
+ *          noise: [n_split,3] standard-normal samples (the reference draws them with torch.randn_like). */
+size_t b200gs_densify_workspace_bytes(int32_t n);
+int b200gs_densify_plan(int32_t n, const float* opacity_raw, const float* scale_raw, const float* pos_grad,
+                        double opacity_threshold, double max_grad, double scale_threshold, void* workspace,
+                        size_t workspace_bytes, uint32_t* counts_host, void* stream);
+int b200gs_densify_apply(int32_t n, const void* workspace, size_t workspace_bytes, const float* const* in6,
+                         float* const* out6, const float* noise, void* stream);
+
 /* ---- Data-parallel optimizer step over NVLink peer memory (one process per GPU) --------------------------------
  * The data-parallel form of scripts/train.py:530-538 (backward -> SUM of the six gradient tensors over the ranks ->
  * clip_grad_norm_(model.pos, 1.0) -> optim.Adam.step()); the reference itself is single-GPU (scripts/train.py:285-291
