@@ -1,6 +1,6 @@
 """Run a reference script unchanged on the b200gs render path:
 
-    python -m b200gs.run /path/to/reference/scripts/render_trained.py --checkpoint ... [args]
+    python -m b200gs.run /path/to/reference/scripts/render_trained.py --checkpoint_dir ... --data_dir ... [args]
 
 Equivalent to `install()` followed by executing the script as __main__ (B200GS_PATCH_ADAM=1 also swaps
 torch.optim.Adam / clip_grad_norm_ for the fused versions).  The reference checkout must
