@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libb200gs.so")
 OK = 0
 ERR_CAPACITY = -5
 TILE = 16
+CAM_KEEP_OUTSIDE_BAND = 1
 
 
 class Gaussians(Structure):
@@ -29,7 +30,7 @@ class Camera(Structure):
                 ("cx", c_double), ("cy", c_double), ("near_plane", c_double), ("far_plane", c_double),
                 ("pix_guard", c_double), ("min_conis", c_double), ("chi_square_clip", c_double),
                 ("alpha_max", c_double), ("alpha_cutoff", c_double), ("tile", c_int32),
-                ("tile_row_begin", c_int32), ("tile_row_end", c_int32)]
+                ("tile_row_begin", c_int32), ("tile_row_end", c_int32), ("flags", c_int32)]
 
 
 class Grads(Structure):
@@ -67,7 +68,7 @@ class PeerTensor(Structure):
 
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
-                ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("reserved", c_uint32 * 11)]
+                ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("n_sorted", c_uint32), ("reserved", c_uint32 * 10)]
 
 
 # every symbol include/b200gs.h declares: name -> (restype, argtypes)

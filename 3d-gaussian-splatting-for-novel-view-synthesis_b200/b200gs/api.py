@@ -120,6 +120,8 @@ class _Source:
 def build_sigma_from_params(scale_raw: torch.Tensor, q_raw: torch.Tensor) -> torch.Tensor:
     """Sigma = R S S^T R^T with s = max(exp(scale_raw), 1e-6), q normalised (gaussian.py:71-127)."""
     ops._require_cuda(scale_raw, "scale_raw")
+    ops._require_f32("scale_raw", scale_raw)
+    ops._require_f32("q_raw", q_raw)
     if _lazy_enabled() and _fusion_enabled():
         n = scale_raw.shape[0]
         needs = torch.is_grad_enabled() and (scale_raw.requires_grad or q_raw.requires_grad)
@@ -134,6 +136,8 @@ def build_sigma_from_params(scale_raw: torch.Tensor, q_raw: torch.Tensor) -> tor
 def evaluate_sh(f_dc: torch.Tensor, f_rest: torch.Tensor, points: torch.Tensor, c2w: torch.Tensor) -> torch.Tensor:
     """sigmoid(sum_k sh_k Y_k(dir)), degree-3 real SH with the reference's signs (spherical_harmonics.py:70-166)."""
     ops._require_cuda(points, "points")
+    for name, t in (("f_dc", f_dc), ("f_rest", f_rest), ("points", points)):
+        ops._require_f32(name, t)
     if f_rest.dim() != 2 or f_rest.shape[1] != 45:
         raise RuntimeError(f"evaluate_sh expects f_rest of shape [N,45], got {tuple(f_rest.shape)}")
     if _lazy_enabled() and _fusion_enabled():
@@ -148,13 +152,16 @@ def evaluate_sh(f_dc: torch.Tensor, f_rest: torch.Tensor, points: torch.Tensor, 
 
 def render(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy,
            near=0.01, far=100.0, pix_guard=32, T=16, min_conis=1e-6,
-           chi_square_clip=6.25, alpha_max=0.99, alpha_cutoff=1 / 128., *, tile_rows=None):
+           chi_square_clip=6.25, alpha_max=0.99, alpha_cutoff=1 / 128., *, tile_rows=None, out=None):
     """Drop-in for render.py:62-410.  Returns [H,W,3] in [0,1], same dtype/device as `pos`.
 
     `tile_rows=(begin, end)` (keyword-only extension) renders only that band of 16-pixel tile rows; the
-    rest of the image is zero (tile-row sharding of large frames across GPUs)."""
+    rest of the image is zero (tile-row sharding of large frames across GPUs).  `out` (keyword-only): a
+    contiguous [H,W,3] float32 CUDA tensor to render into."""
     args, strict = _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, far, pix_guard, T, min_conis,
                             chi_square_clip, alpha_max, alpha_cutoff, tile_rows)
+    if out is not None:
+        args[-1].out = out
     image = ops._Rasterize.apply(*args, strict)
     return image if image.dtype == pos.dtype else image.to(pos.dtype)
 
@@ -164,6 +171,8 @@ def _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, fa
     """Arguments of render() -> (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg), strict:
     the fused route (raw parameters) when the tags of `sigma` / `color` resolve, the tensors themselves otherwise."""
     ops._require_cuda(pos, "pos")
+    for name, t in (("pos", pos), ("color", color), ("opacity_raw", opacity_raw), ("sigma", sigma)):
+        ops._require_f32(name, t)
     H, W = int(H), int(W)           # callers pass Python ints, 0-dim tensors (train.py:499) or floats
     cfg = ops.RenderConfig(H=H, W=W, fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), near=float(near),
                            far=float(far), pix_guard=float(pix_guard), T=int(T), min_conis=float(min_conis),

@@ -63,7 +63,9 @@ def shard_tile_rows(n_rows: int, world: int, weights: Sequence[float] | None = N
 def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: bool = False) -> None:
     """SUM all-reduce of `.grad` of every parameter (in place).  Ranks that have no gradient for a
     parameter contribute zeros, so densify/prune decisions taken from the reduced gradients stay
-    identical on every rank (scripts/train.py:544-557)."""
+    identical on every rank (scripts/train.py:544-557).  `params` may be any iterable (a generator is
+    consumed once)."""
+    params = list(params)
     if not dist.is_available() or not dist.is_initialized():
         return
     world = dist.get_world_size(group)
@@ -73,6 +75,8 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: boo
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
+        elif not p.grad.is_contiguous():
+            p.grad = p.grad.contiguous()
         handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group, async_op=True))
     for h in handles:
         h.wait()
@@ -81,17 +85,162 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: boo
             p.grad.div_(world)
 
 
+class GradBucket:
+    """One flat gradient buffer for a parameter set, reduced with ONE collective per iteration.
+
+    Six `all_reduce` calls (f_rest 180 MB + five tensors of <= 16 MB) cost a launch and a ring/tree set-up each; here
+    the gradients of `b200gs.render`'s backward are written straight into views of one flat fp32 buffer
+    (`ops.register_grad_sink`: autograd adopts the view as `.grad`, no copy), and `allreduce()` sums that buffer over
+    the ranks in one call.  Gradients that did not come through a sink (another producer, a second backward into the
+    same leaf) are copied into their slot first.  After `allreduce()` every `p.grad` is a view of the reduced buffer.
+    Backend-agnostic (NCCL on GPUs; the CPU tests run it over gloo, where the sinks are simply never handed out)."""
+
+    def __init__(self, params: Iterable[torch.Tensor], group=None):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GradBucket: no parameters")
+        self.group = group
+        dev, dt = self.params[0].device, self.params[0].dtype
+        offs, total = [], 0
+        for p in self.params:
+            if p.device != dev or p.dtype != dt:
+                raise ValueError("GradBucket: all parameters must share a device and a dtype")
+            offs.append(total)
+            total += (p.numel() + 31) // 32 * 32          # 128-byte aligned slots
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        if dev.type == "cuda":
+            from . import ops
+            for p, v in zip(self.params, self.views):
+                ops.register_grad_sink(p, v)
+
+    def allreduce(self, average: bool = False) -> None:
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+            p.grad = v
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if average:
+                self.flat.div_(dist.get_world_size(self.group))
+        if self.flat.is_cuda:
+            from . import ops
+            ops.release_grad_sinks(self.params)
+
+    def zero_grad(self) -> None:
+        """`optimizer.zero_grad(set_to_none=True)` for the bucket's parameters (the sinks are handed out again)."""
+        for p in self.params:
+            p.grad = None
+
+
 def render_tile_row_sharded(render_fn, n_tile_rows: int, group=None, weights=None) -> torch.Tensor:
     """Every rank renders its band of tile rows with `render_fn(tile_rows=(begin, end))` (pixels outside
-    the band are zero), then the bands are combined with a SUM all-reduce: bands are disjoint, so the sum
-    is the full frame on every rank."""
+    the band are zero) and the bands are gathered into the full frame on every rank.
+
+    Bands are contiguous row ranges of the [H,W,3] image, so the exchange is an all-gather of the band slices
+    (each rank sends only its own pixels), not a reduction of whole frames.  Backend-agnostic (gloo in the CPU
+    tests).  On an NVLink box `TileRowRenderer` skips the collective altogether."""
     if not dist.is_available() or not dist.is_initialized():
         return render_fn(tile_rows=(0, n_tile_rows))
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    begin, end = shard_tile_rows(n_tile_rows, world, weights)[rank]
+    bands = shard_tile_rows(n_tile_rows, world, weights)
+    begin, end = bands[rank]
     if end <= begin:            # more ranks than rows: an empty band is (n_rows, n_rows); (0, 0) means "all rows"
-        begin = end = n_tile_rows
-    image = render_fn(tile_rows=(begin, end))
-    if world > 1:
-        dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
+        image = render_fn(tile_rows=(n_tile_rows, n_tile_rows))
+    else:
+        image = render_fn(tile_rows=(begin, end))
+    if world == 1:
+        return image
+    H = image.shape[0]
+    rows_of = [(min(b * 16, H), min(e * 16, H)) for b, e in bands]
+    pad = max(r1 - r0 for r0, r1 in rows_of)
+    if pad == 0:
+        return image
+    mine = image.new_zeros((pad,) + tuple(image.shape[1:]))
+    r0, r1 = rows_of[rank]
+    mine[:r1 - r0] = image[r0:r1]
+    gathered = image.new_empty((world * pad,) + tuple(image.shape[1:]))
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    for q, (q0, q1) in enumerate(rows_of):
+        if q != rank and q1 > q0:
+            image[q0:q1] = gathered[q * pad:q * pad + (q1 - q0)]
     return image
+
+
+class TileRowRenderer:
+    """A large single frame split into bands of 16-pixel tile rows, one band per GPU of an NVLink box, with NO
+    collective on the data path (BASELINE.json configs[4]; tiles are independent in the reference's loop,
+    render.py:325-399).
+
+    Every rank holds the whole Gaussian set, culls it to its band BEFORE evaluating colours (the band variant of the
+    preprocess kernel), depth-sorts only the band's survivors and blends its tile rows; the blend kernel stores the
+    band's pixels straight into the frame buffer of the `root` rank over peer-mapped memory (plain st.global over
+    NVLink), so when the closing flag barrier completes the full frame sits in root's buffer:
+
+        tr = b200gs.dist.TileRowRenderer(H, W, device)
+        img = tr.render(pos, color, opacity_raw, sigma, c2w, fx, fy, cx, cy)    # complete on root, in stream order
+
+    `weights` (one number per tile row, e.g. intersections per row of an earlier frame - `row_weights()`) balances the
+    bands.  One process (no process group) renders the whole frame locally.  Forward only."""
+
+    def __init__(self, H: int, W: int, device, group=None, root: int = 0, weights=None):
+        from . import peer
+        self.H, self.W, self.device, self.group, self.root = int(H), int(W), torch.device(device), group, int(root)
+        self.n_rows = (self.H + 15) // 16
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        self.set_weights(weights)
+        # the frame lives in the parameter half of a peer area (the control block carries the barrier flags)
+        self.area = peer.PeerArea([self.H * self.W * 3], self.device, group=group, multicast=False)
+        self.image = self.area.view(self.area.flat_params, 0, (self.H, self.W, 3))
+        off = self.image.data_ptr() - self.area.buf.data_ptr()
+        self.root_ptr = int(self.area.c_group.area[self.root]) + off
+        self._buffers = [None, None]      # frame / intersection workspaces, reused from frame to frame
+
+    def set_weights(self, weights=None):
+        self.bands = shard_tile_rows(self.n_rows, self.world, weights)
+
+    def render(self, pos, color, opacity_raw, sigma, c2w, fx, fy, cx, cy, **kw):
+        from . import api, ops
+        begin, end = self.bands[self.rank]
+        if end <= begin:
+            begin = end = self.n_rows
+        with torch.no_grad():
+            args, _ = api._resolve(pos, color, opacity_raw, sigma, c2w, self.H, self.W, fx, fy, cx, cy,
+                                   kw.get("near", 0.01), kw.get("far", 100.0), kw.get("pix_guard", 32), kw.get("T", 16),
+                                   kw.get("min_conis", 1e-6), kw.get("chi_square_clip", 6.25), kw.get("alpha_max", 0.99),
+                                   kw.get("alpha_cutoff", 1 / 128.), (begin, end) if self.world > 1 else None)
+            cfg = args[-1]
+            cfg.out = self.image
+            if self.world > 1:
+                cfg.keep_outside_band = True
+                cfg.out_ptr = self.root_ptr
+                self.area.barrier()            # root has consumed the previous frame: its buffer may be overwritten
+            image, frame = ops.launch_frame(*args, buffers=self._buffers)
+            frame.finish()
+            if self.world > 1:
+                self.area.barrier()            # every band has landed in root's buffer
+        self.last_frame = frame
+        return image
+
+    def row_weights(self, pos, color, opacity_raw, sigma, c2w, fx, fy, cx, cy, **kw):
+        """Intersections per tile row of this view, measured by rendering the whole frame once on this GPU; feed the
+        result to `set_weights` (every rank computes the same numbers from the same scene)."""
+        from . import api, ops
+        with torch.no_grad():
+            args, _ = api._resolve(pos, color, opacity_raw, sigma, c2w, self.H, self.W, fx, fy, cx, cy,
+                                   kw.get("near", 0.01), kw.get("far", 100.0), kw.get("pix_guard", 32), kw.get("T", 16),
+                                   kw.get("min_conis", 1e-6), kw.get("chi_square_clip", 6.25), kw.get("alpha_max", 0.99),
+                                   kw.get("alpha_cutoff", 1 / 128.), None)
+            g, keep = ops._gaussians(*args[:8])
+            with torch.cuda.device(self.device):
+                frame = ops.Frame(g, keep, args[-1], args[-2], self.device)
+                frame.render("sync")
+                ranges = frame.export()["ranges"].to(torch.int64)
+        tiles_x = (self.W + 15) // 16
+        per_tile = (ranges[:, 1] - ranges[:, 0]).view(self.n_rows, tiles_x)
+        return (per_tile.sum(dim=1) + per_tile.sum() // (8 * self.n_rows) + 1).tolist()

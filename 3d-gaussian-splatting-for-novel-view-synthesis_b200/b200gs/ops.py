@@ -24,6 +24,13 @@ def _require_cuda(t: torch.Tensor, name: str):
             "fallback.")
 
 
+def _require_f32(name: str, t: Optional[torch.Tensor]):
+    """The reference is dtype-generic (its image follows pos.dtype, render.py:318); this path computes in fp32 only
+    and refuses anything else rather than rounding it silently."""
+    if t is not None and t.is_floating_point() and t.dtype != torch.float32:
+        raise TypeError(f"b200gs: `{name}` is {t.dtype}; the CUDA path computes in float32 only (pass .float() tensors)")
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
@@ -59,6 +66,10 @@ class RenderConfig:
     alpha_cutoff: float = 1 / 128.
     tile_row_begin: int = 0
     tile_row_end: int = 0
+    keep_outside_band: bool = False     # a band writes its own pixels only (the image belongs to a tile-row sharded frame)
+    out: Optional[torch.Tensor] = None  # caller-owned [H,W,3] fp32 image to render into (returned as the result)
+    out_ptr: int = 0                    # raw device address the kernels write instead of out.data_ptr(): the same frame
+                                        # buffer on another GPU, peer-mapped (b200gs.dist.TileRowRenderer)
 
     def to_c(self, c2w: torch.Tensor) -> Camera:
         if int(self.T) != _lib.TILE:
@@ -69,7 +80,8 @@ class RenderConfig:
                       pix_guard=float(self.pix_guard), min_conis=float(self.min_conis),
                       chi_square_clip=float(self.chi_square_clip), alpha_max=float(self.alpha_max),
                       alpha_cutoff=float(self.alpha_cutoff), tile=int(self.T),
-                      tile_row_begin=int(self.tile_row_begin), tile_row_end=int(self.tile_row_end))
+                      tile_row_begin=int(self.tile_row_begin), tile_row_end=int(self.tile_row_end),
+                      flags=_lib.CAM_KEEP_OUTSIDE_BAND if self.keep_outside_band else 0)
 
 
 _pinned_stats = {}
@@ -152,6 +164,7 @@ class Frame:
 
     def __init__(self, g: Gaussians, keep, cam_cfg: RenderConfig, c2w: torch.Tensor, device):
         self.g, self.keep, self.cfg, self.c2w, self.device = g, keep, cam_cfg, c2w, device
+        self.out, self.out_ptr = cam_cfg.out, cam_cfg.out_ptr
         self.cam = cam_cfg.to_c(c2w)
         self.frame_ws = None
         self.isect_ws = None
@@ -191,7 +204,10 @@ class Frame:
             if buffers is not None:
                 buffers[0] = self.frame_ws
         stats_np, stats_ptr, ev, ev_ptr = _stats_slot(dev, stream)
-        image = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+        image = self.out if self.out is not None else torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+        if self.out is not None and (tuple(image.shape) != (H, W, 3) or image.dtype != torch.float32 or
+                                     not image.is_contiguous() or image.device != dev):
+            raise ValueError("out must be a contiguous [H,W,3] float32 tensor on the device of the Gaussians")
         spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
                                              frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
@@ -260,7 +276,7 @@ class Frame:
         blend = _blend_stream.get(self.device.index)
         if blend is None:
             _lib.check(lib.b200gs_render_rasterize_ev(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
-                                                      _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image), stats_ptr,
+                                                      _ptr(self.isect_ws), isect_bytes, capacity, self._image_ptr(image), stats_ptr,
                                                       stats_event, st),
                        "render_rasterize")
         else:
@@ -269,9 +285,12 @@ class Frame:
             for t in (self.frame_ws, self.isect_ws, image):
                 t.record_stream(blend)
             _lib.check(lib.b200gs_render_rasterize_split(ctypes.byref(self.cam), n, _ptr(self.frame_ws), frame_bytes,
-                                                         _ptr(self.isect_ws), isect_bytes, capacity, _ptr(image),
+                                                         _ptr(self.isect_ws), isect_bytes, capacity, self._image_ptr(image),
                                                          stats_ptr, stats_event, st, ctypes.c_void_p(blend.cuda_stream)),
                        "render_rasterize_split")
+
+    def _image_ptr(self, image):
+        return ctypes.c_void_p(int(self.out_ptr)) if self.out_ptr else _ptr(image)
 
     # -- backward ---------------------------------------------------------------------------------------
     def backward(self, grad_image: torch.Tensor, grads: Grads):
@@ -312,10 +331,20 @@ def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
     keep = [_f32c(t) for t in (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)]
     pos_, op_, sr_, q_, sg_, dc_, fr_, col_ = keep
     n = pos_.shape[0]
+    if pos_.dim() != 2 or pos_.shape[1] != 3:
+        raise ValueError(f"pos must be [N,3], got {tuple(pos_.shape)}")
     if op_.numel() != n:
         raise ValueError("opacity_raw must have one entry per Gaussian")
     if fr_ is not None and (fr_.dim() != 2 or fr_.shape[1] != 45):
         raise ValueError("f_rest must be [N,45] (spherical_harmonics.py:125-127)")
+    # the kernels index every array with the same Gaussian id: a row-count mismatch (e.g. tags of a model that has
+    # been densified since) would read out of bounds where the reference raises a shape error
+    for name, t, tail in (("scale_raw", sr_, (3,)), ("q_raw", q_, (4,)), ("sigma", sg_, (3, 3)), ("f_dc", dc_, (3,)),
+                          ("f_rest", fr_, (45,)), ("color", col_, (3,))):
+        if t is not None and tuple(t.shape) != (n,) + tail:
+            raise ValueError(f"{name} must be {(n,) + tail} to match pos [N={n},3], got {tuple(t.shape)}")
+    if q_ is not None and q_.data_ptr() % 16:
+        raise ValueError("q_raw must be 16-byte aligned (a contiguous [N,4] float32 tensor is)")
     g = Gaussians(n=n, pos=pos_.data_ptr(), opacity_raw=op_.data_ptr(),
                   scale_raw=None if sr_ is None else sr_.data_ptr(), q_raw=None if q_ is None else q_.data_ptr(),
                   sigma=None if sg_ is None else sg_.data_ptr(), f_dc=None if dc_ is None else dc_.data_ptr(),

@@ -72,9 +72,11 @@ class PeerArea:
         if multicast is None:
             # Through the switch a rank's own copy crosses its links too: per GPU and direction (1 + 1/p) S bytes against
             # 2 (p-1)/p S for plain peer loads / stores.  Measured (tools/peer_bench.py, N = 1M): 2 ranks 0.84 vs 0.58 ms,
-            # 4 ranks 0.79 vs 0.80 ms, 8 ranks 0.85 vs 1.06 ms -> NVLS from 8 ranks up.
-            env = os.environ.get("B200GS_PEER_MULTICAST")
-            multicast = (env == "1") if env is not None else self.world >= 8
+            # 4 ranks 0.79 vs 0.80 ms, 8 ranks 0.85 vs 1.06 ms.  OPT-IN at every world size all the same: with two
+            # multimem-mapped areas in one process parameter updates were lost at 4 ranks and the
+            # cause is not established, so the default is the path whose ordering argument is complete - plain peer
+            # loads / stores, ordered by release/acquire flag barriers.
+            multicast = os.environ.get("B200GS_PEER_MULTICAST") == "1"
         if multicast and PeerArea._multicast_in_use:
             # one multicast-mapped area per process: with a second one (the optimizer's and an all-reduce area, both
             # through multimem) parameter updates were lost at 4 ranks; not understood, so not allowed
@@ -154,9 +156,10 @@ class PeerAdam(torch.optim.Optimizer):
     * gradients that come out of `b200gs.render`'s backward are written straight into the peer-visible staging
       buffer (`.grad` is then a view of it) - no staging copy; any other gradient tensor is copied there by `step()`;
     * the moments are sharded over the ranks (each rank keeps 1/world of `exp_avg` / `exp_avg_sq`);
-    * from 8 ranks up (or with `multicast=True` / `B200GS_PEER_MULTICAST=1`) the areas are also mapped through an NVLS
-      multicast address and the kernel uses `multimem.ld_reduce` / `multimem.st`: the switch sums the gradients and
-      replicates the parameters, so the bytes a GPU moves stop growing with the number of ranks.
+    * opt-in (`multicast=True` / `B200GS_PEER_MULTICAST=1`): the areas are also mapped through an NVLS multicast
+      address and the kernel uses `multimem.ld_reduce` / `multimem.st` - the switch sums the gradients and replicates
+      the parameters, so the bytes a GPU moves stop growing with the number of ranks (0.85 vs 1.06 ms at 8 ranks).
+      Off by default at every world size until the lost updates seen with two multicast areas are explained.
     """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, *, group=None,

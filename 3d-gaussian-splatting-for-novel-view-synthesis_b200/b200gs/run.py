@@ -6,6 +6,28 @@ Equivalent to `install()` followed by executing the script as __main__ (B200GS_P
 torch.optim.Adam / clip_grad_norm_ for the fused versions).  The reference checkout must
 be importable: its root is derived from the script location (<root>/scripts/x.py) or taken from
 $B200GS_REFERENCE_ROOT.
+
+Data-parallel training, script still byte-for-byte unchanged (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \\
+        -m b200gs.run --dp /path/to/reference/scripts/train.py --data_dir ... --batch_size 1 [args]
+
+`--dp` turns the single-GPU loop of scripts/train.py into data parallelism over the training views without touching it
+(the reference itself only prints the GPU count, scripts/train.py:285-291):
+  * every rank sees ONE GPU as cuda:0 (the script hard-codes `cuda:0`, train.py:372) and joins an NCCL group;
+  * all ranks are seeded identically (B200GS_DP_SEED, default 0), so the model initialisation (data_loader.py:327,346)
+    and the split noise of densification (train.py:164) are the same everywhere - the replicas never diverge;
+  * `DataLoader(shuffle=True)` (train.py:318-324) is given a sampler that draws ONE permutation of the views per epoch
+    from a generator shared by all ranks and hands rank r the entries r, r + world, ... - so an iteration of the job
+    processes world x batch_size distinct views, and a run with p processes x batch b visits the same views per
+    iteration as 1 process x batch p*b;
+  * the script averages a batch's losses over ITS batch size (train.py:514-521); the launcher completes the average over
+    the global batch: the first of `clip_grad_norm_` (train.py:536) / `optimizer.step()` (train.py:538) after a backward
+    sums the six gradient tensors over the ranks (one flat bucket, one NCCL all-reduce - b200gs.dist.GradBucket) and
+    divides by the world size; clipping, Adam and the densification statistics (train.py:544-557) then see the same
+    reduced gradient on every rank;
+  * only rank 0 writes checkpoints and prints progress.
+Without torchrun (`python -m b200gs.run --dp ...`) the same code runs as a world of one.
 """
 from __future__ import annotations
 
@@ -14,8 +36,107 @@ import runpy
 import sys
 
 
+def _setup_dp():
+    """Everything `--dp` changes, applied BEFORE the script is imported.  Returns (rank, world)."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("B200GS_DP_KEEP_VISIBLE") != "1":
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        ids = [v for v in vis.split(",") if v] if vis else None
+        os.environ["CUDA_VISIBLE_DEVICES"] = ids[local] if ids and local < len(ids) else str(local)
+    import random
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import torch.utils.data as tud
+    seed = int(os.environ.get("B200GS_DP_SEED", "0"))
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)                       # CPU and every CUDA generator
+    if world > 1:
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", 0))
+
+    # ---- views: one shared permutation per epoch, rank r takes entries r, r + world, ... ----------------------------
+    class ShardedRandomSampler(tud.Sampler):
+        def __init__(self, data_source):
+            self.n = len(data_source)
+            self.gen = torch.Generator().manual_seed(seed + 7919)      # same stream on every rank
+
+        def __iter__(self):
+            perm = torch.randperm(self.n, generator=self.gen).tolist()
+            total = -(-self.n // world) * world            # padded by wrapping around, like DistributedSampler:
+            perm = (perm * (total // max(self.n, 1) + 1))[:total]   # every rank gets the same number of views per epoch
+            return iter(perm[rank::world])
+
+        def __len__(self):
+            return -(-self.n // world)
+
+    orig_init = tud.DataLoader.__init__
+
+    def dl_init(self, dataset, *a, **kw):
+        if kw.get("shuffle") and kw.get("sampler") is None and kw.get("batch_sampler") is None:
+            kw["shuffle"] = False
+            kw["sampler"] = ShardedRandomSampler(dataset)
+        orig_init(self, dataset, *a, **kw)
+    tud.DataLoader.__init__ = dl_init
+
+    # ---- gradients: reduced once per iteration by whichever of clip_grad_norm_ / optimizer.step comes first ---------
+    from .dist import GradBucket
+    from . import ops
+    state = {"bucket": None, "params": None, "reduced": False}
+
+    def ensure_reduced():
+        if state["reduced"] or state["params"] is None:
+            return
+        if state["bucket"] is None:
+            state["bucket"] = GradBucket(state["params"])
+        state["bucket"].allreduce(average=True)
+        state["reduced"] = True
+
+    def wrap_optimizer(cls):
+        class DataParallel(cls):
+            def __init__(self, params, *a, **kw):
+                super().__init__(params, *a, **kw)
+                plist = [p for g in self.param_groups for p in g["params"]]
+                if state["params"] is not None:
+                    ops.unregister_grad_sinks(state["params"])         # the script re-creates the optimizer after densify
+                state.update(bucket=None, params=plist, reduced=False)
+
+            def step(self, closure=None):
+                ensure_reduced()
+                out = super().step(closure)
+                state["reduced"] = False
+                return out
+
+            def zero_grad(self, set_to_none=True):
+                state["reduced"] = False
+                return super().zero_grad(set_to_none)
+        DataParallel.__name__ = cls.__name__
+        return DataParallel
+
+    torch.optim.Adam = wrap_optimizer(torch.optim.Adam)
+    inner_clip = torch.nn.utils.clip_grad_norm_
+
+    def clip_grad_norm_(parameters, *a, **kw):
+        ensure_reduced()
+        return inner_clip(parameters, *a, **kw)
+    torch.nn.utils.clip_grad_norm_ = clip_grad_norm_
+
+    # ---- side effects: rank 0 only ---------------------------------------------------------------------------------------
+    if rank != 0:
+        torch.save = lambda *a, **kw: None
+        devnull = open(os.devnull, "w")
+        sys.stdout = devnull
+        os.environ.setdefault("TQDM_DISABLE", "1")
+    return rank, world
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    dp = bool(argv) and argv[0] == "--dp"
+    if dp:
+        argv = argv[1:]
     if not argv:
         print(__doc__)
         return 2
@@ -24,9 +145,18 @@ def main(argv=None):
     if root not in sys.path:
         sys.path.insert(0, root)
     from .install import install
-    install(optimizer=os.environ.get("B200GS_PATCH_ADAM", "0") == "1")
+    install(optimizer=os.environ.get("B200GS_PATCH_ADAM", "0") == "1")     # first: --dp wraps whatever Adam is installed
+    world = 1
+    if dp:
+        _, world = _setup_dp()
     sys.argv = [script] + argv[1:]
-    runpy.run_path(script, run_name="__main__")
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        if dp and world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
     return 0
 
 

@@ -30,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -108,6 +108,8 @@ int make_gauss(const b200gs_gaussians* g, gs::GaussIn& o) {
   o.color = raw_sh ? nullptr : g->color;
   return B200GS_OK;
 }
+
+bool is_band(const gs::RenderParams& rp) { return rp.row_begin > 0 || rp.row_end < rp.tiles_y; }
 
 int super_dims(const gs::RenderParams& rp, int& super_x, int& super_y) {
   super_x = gs::ceil_div(rp.tiles_x, gs::kSuperX);
@@ -451,11 +453,23 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
                                                        gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch)), &hist_done));
     // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
     int in_a = 0;
-    PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
-                             gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2), gs::ws_ptr<uint32_t>(frame_ws, L.order),
-                             gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
-                             (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
-                             &in_a, s, hist_done));
+    uint32_t* keys_a = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2);
+    uint32_t* order = gs::ws_ptr<uint32_t>(frame_ws, L.order);
+    if (is_band(rp)) {
+      // a band keeps a fraction of the Gaussians: compact the live keys (stable) and sort those only
+      PCU(R_COMPACT, 1, gs::launch_compact_keys(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), (uint32_t)gi.n, keys_a, order,
+                                                &stats->n_sorted, gs::ws_ptr<void>(frame_ws, L.offsets), (size_t)gi.n * 4, s));
+      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(keys_a, order, keys_a, order,
+                               gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
+                               (uint32_t)gi.n, &stats->n_sorted, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch),
+                               L.scratch_bytes, &in_a, s, hist_done));
+    } else {
+      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
+                               keys_a, order,
+                               gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
+                               (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
+                               &in_a, s, hist_done));
+    }
     if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
   }
   if (stats_host) CU(publish_stats(stats, stats_host, s));
@@ -497,7 +511,7 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
   uint32_t* lists = gs::ws_ptr<uint32_t>(isect_ws, IL.lists);
   // a frame that overflowed a speculative capacity is rasterized again with exact buffers: start clean
   CU(cudaMemsetAsync(&stats->overflow, 0, sizeof(uint32_t), s));
-  PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
+  PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, is_band(rp) ? &stats->n_sorted : nullptr, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
                                             gs::ws_ptr<uint2>(frame_ws, L.rect), super_x, isect_capacity, keys, vals, stats,
                                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes,
                                             gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));
@@ -533,8 +547,8 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
     CU(cudaEventDestroy(binned));      // released once the recorded work completes
     s = (cudaStream_t)blend_stream;
   }
-  if (rp.row_begin == 0 && rp.row_end == rp.tiles_y) {
-    // every pixel is written by the blend kernel
+  if (!is_band(rp) || (cam->flags & B200GS_CAM_KEEP_OUTSIDE_BAND)) {
+    // every pixel is written by the blend kernel / the pixels outside the band belong to somebody else
   } else {
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }

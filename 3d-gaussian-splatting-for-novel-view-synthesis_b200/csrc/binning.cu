@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
                                                                     const b200gs_frame_stats* __restrict__ stats,
                                                                     int super_x, int tiles_x, int tiles_y,
                                                                     uint32_t* __restrict__ tile_count,
+                                                                    uint32_t* __restrict__ part_total,
                                                                     uint2* __restrict__ ranges,
                                                                     uint32_t* __restrict__ lists) {
   __shared__ uint32_t s_wc[kSplitRows][kSuperTiles];    // per-warp-chunk tile counts, then exclusive offsets
@@ -130,9 +131,11 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
   if (tid < 2) s_seg[tid] = lower_bound_u32(keys, count, (uint32_t)s + tid);
   if (tid < kSuperTiles) s_run[tid] = 0;
   if (WRITE) {
-    // start of this supertile's region = number of intersections of all earlier supertiles
+    // start of this supertile's region = number of intersections of all earlier supertiles = sum of the per-CTA
+    // totals the counting pass left behind (one word per CTA: summing the per-tile counts here instead made every
+    // CTA read up to 128 words per earlier supertile - 67 M loads per headline frame)
     uint32_t acc = 0;
-    for (int i = tid; i < s * kSplitParts * kSuperTiles; i += kSplitThreads) acc += tile_count[i];
+    for (int i = tid; i < s * kSplitParts; i += kSplitThreads) acc += part_total[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s_red[warp] = acc;
@@ -220,7 +223,12 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
     __syncthreads();
     if (my_total) atomicAdd(&s_run[lane], my_total);
     __syncthreads();
-    if (tid < kSuperTiles) tile_count[(s * kSplitParts + part) * kSuperTiles + tid] = s_run[tid];
+    if (tid < kSuperTiles) {
+      const uint32_t c = s_run[tid];
+      tile_count[(s * kSplitParts + part) * kSuperTiles + tid] = c;
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, c);      // warp 0 = the 32 tiles
+      if (tid == 0) part_total[s * kSplitParts + part] = tot;
+    }
   }
 }
 
@@ -230,12 +238,13 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
                                cudaStream_t s) {
   const int grid = super_x * super_y * kSplitParts;
   if (grid <= 0) return cudaSuccess;
+  uint32_t* part_total = tile_count + (size_t)grid * kSuperTiles;     // one word per CTA, behind the per-tile counts
   if (write) {
     split_super_kernel<true><<<grid, kSplitThreads, 0, s>>>(keys, vals, rect, capacity, stats, super_x, tiles_x,
-                                                           tiles_y, tile_count, ranges, lists);
+                                                           tiles_y, tile_count, part_total, ranges, lists);
   } else {
     split_super_kernel<false><<<grid, kSplitThreads, 0, s>>>(keys, vals, rect, capacity, stats, super_x, tiles_x,
-                                                            tiles_y, tile_count, ranges, lists);
+                                                            tiles_y, tile_count, part_total, ranges, lists);
   }
   return cudaGetLastError();
 }

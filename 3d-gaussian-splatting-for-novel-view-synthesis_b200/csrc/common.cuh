@@ -45,7 +45,7 @@ struct FrameLayout {
   size_t offsets;         // u32[n]  exclusive scan of super_touched in depth order
   size_t grad_acc;        // float[n*12] blend-backward accumulators (Mx,My,Mxx,Mxy,Myy,M0,r,g,b,+pad): moments of dL/dq
   size_t ranges;          // uint2[tiles] (start,end) per tile
-  size_t tile_count;      // u32[supertiles*4*32] entries per tile and list quarter, supertile-major
+  size_t tile_count;      // u32[supertiles*4*32] entries per tile and list quarter, supertile-major; + u32[supertiles*4] totals
   size_t final_T;         // float[P]
   size_t n_contrib;       // u32[P]  (#list entries consumed) | channel-overflow bits 29..31
   size_t scratch;         // scan + sort scratch (sized for max(n, isect) users at call time)
@@ -91,7 +91,8 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.offsets = take(N * 4);
   L.grad_acc = take(N * 12 * 4);
   L.ranges = take(tiles * 8);
-  L.tile_count = take((size_t)ceil_div(ceil_div(W, kTile), kSuperX) * ceil_div(ceil_div(H, kTile), kSuperY) * 32 * 4 * 4 /* kSplitParts */);
+  // per supertile and list quarter (kSplitParts = 4): 32 per-tile counts, then one total per (supertile, quarter)
+  L.tile_count = take((size_t)ceil_div(ceil_div(W, kTile), kSuperX) * ceil_div(ceil_div(H, kTile), kSuperY) * (32 + 1) * 4 * 4);
   L.final_T = take(P * 4);
   L.n_contrib = take(P * 4);
   size_t a = scan_scratch_bytes((uint32_t)N);
@@ -158,11 +159,16 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
                               uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
                               const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
                               size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready = false);
-cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t* super_touched, const uint2* rect,
-                                   int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+// n_dev (optional): device-side count of live entries at the front of `order` (band frames compact their keys)
+cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t* order, const uint32_t* super_touched,
+                                   const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
                                    b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
                                    size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
                                    cudaStream_t s);
+// (key, id) of every key != kCulledKey in index order -> out_keys / out_ids, their number -> *count_out (device)
+size_t compact_scratch_bytes(uint32_t n);
+cudaError_t launch_compact_keys(const uint32_t* keys, uint32_t n, uint32_t* out_keys, uint32_t* out_ids,
+                                uint32_t* count_out, void* scratch, size_t scratch_bytes, cudaStream_t s);
 
 cudaError_t launch_emit_super(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* super_touched,
                               const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,

@@ -141,6 +141,27 @@ __global__ void peer_barrier_kernel(PeerPtrs pp, uint32_t epoch) {
   }
 }
 
+// The same barrier signalled THROUGH the multicast mapping: after a kernel that replicated data with multimem.st, the
+// arrival flag must not overtake that data on its way through the switch, so it takes the same path - one
+// multimem.st.release per rank writes arrive_mc[rank] in every rank's control block.
+constexpr size_t kCtrlArriveMc = 1024;     // uint32 arrive_mc[kMaxPeers]
+__global__ void peer_barrier_mc_kernel(PeerPtrs pp, uint32_t epoch) {
+  const int q = threadIdx.x;
+  if (q >= pp.world) return;
+  if (q == 0) {
+    __threadfence_system();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    uint32_t* flag = reinterpret_cast<uint32_t*>(pp.mc + kCtrlArriveMc) + pp.rank;
+    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(epoch) : "memory");
+  }
+  const uint32_t* mine = reinterpret_cast<const uint32_t*>(pp.area[pp.rank] + kCtrlArriveMc) + q;
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    if (clock64() - t0 > 40000000000LL) __trap();
+    __nanosleep(200);
+  }
+}
+
 struct PeerTensor {
   long long offset;        // floats from the start of the flat buffers
   long long begin, end;    // this rank's slice [begin, end) of the tensor
@@ -405,7 +426,10 @@ cudaError_t launch_peer_step(const b200gs_peer_group* g, const b200gs_peer_layou
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++nl;
   }
-  if ((e = launch_peer_barrier(g, ++*epoch, s)) != cudaSuccess) return e;                      // B3
+  if (pp.mc) {                                                                                 // B3
+    peer_barrier_mc_kernel<<<1, 32, 0, s>>>(pp, ++*epoch);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  } else if ((e = launch_peer_barrier(g, ++*epoch, s)) != cudaSuccess) return e;
   ++nl;
   if (!adam || write_grads) {          // hand the reduced gradients back to the caller's tensors
     for (int k = 0; k < n_tensors; ++k) {

@@ -148,7 +148,14 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
     Projection o;
     vis = project_gaussian(p, S, ld_stream_f(g.opacity_raw + i), ps, rp, o);
     past_s7 = vis || o.offscreen;
-    if (!vis) {
+    // tile-row sharding: this rank only bins tile rows [row_begin, row_end); a survivor whose rect misses the band
+    // is dropped here (culled key, no record, no SH evaluation) but still counts as visible
+    int tv0 = 0, tv1 = 0, tiles = 0;
+    if (vis) {
+      tv0 = max(o.tv0, rp.row_begin); tv1 = min(o.tv1, rp.row_end - 1);
+      tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
+    }
+    if (!vis || tiles == 0) {
       f.depth_key[i] = kCulledKey;
       f.super_touched[i] = 0;
     } else {
@@ -161,17 +168,13 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(GaussIn g, co
       } else {
         rgb[0] = s_col[3 * tid]; rgb[1] = s_col[3 * tid + 1]; rgb[2] = s_col[3 * tid + 2];
       }
-      // tile-row sharding: this rank only bins tile rows [row_begin, row_end)
-      int tv0 = max(o.tv0, rp.row_begin), tv1 = min(o.tv1, rp.row_end - 1);
-      const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
-      if (tiles == 0) { tv0 = 0; tv1 = 0; }
       float eu, ev;
       conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
       write_splat_record(f, i, o, rgb, eu, ev, rp);
       f.depth_key[i] = __float_as_uint(o.z);
       f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
       my_tiles = (uint32_t)tiles;
-      f.super_touched[i] = tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
+      f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -224,11 +227,37 @@ struct __align__(128) PreStage {
 };
 constexpr uint32_t kPreStageBytes = kPreBlock * (45 + 4 + 3 + 3 + 3 + 1) * 4;
 
+// Tile-row bands (a large frame sharded over GPUs): most Gaussians miss the band, so only the 44 B the projection
+// needs go through the copy pipeline; the 192 B of SH coefficients are fetched - straight from global memory, one
+// row per thread - for the band's survivors only.
+struct __align__(128) PreStageBand {
+  float quat[kPreBlock * 4];
+  float pos[kPreBlock * 3];
+  float scale[kPreBlock * 3];
+  float opac[kPreBlock];
+};
+constexpr uint32_t kPreStageBandBytes = kPreBlock * (4 + 3 + 3 + 1) * 4;
+template <bool BAND> struct PreStageOf { using type = PreStage; };
+template <> struct PreStageOf<true> { using type = PreStageBand; };
+
+__device__ __forceinline__ void sh_color_global(const float* __restrict__ dc, const float* __restrict__ rest,
+                                                const float Y[16], float rgb[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = __ldg(dc + c) * Y[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) acc = fmaf(__ldg(rest + 15 * c + k - 1), Y[k], acc);
+    rgb[c] = sigmoidf_(acc);
+  }
+}
+
+template <bool BAND>
 __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
                                                                        RenderParams rp, FrameView f, int n_chunks,
                                                                        uint32_t* __restrict__ depth_hist) {
+  using Stage = typename PreStageOf<BAND>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PreStage* stage = reinterpret_cast<PreStage*>(smem_raw);       // [2]
+  Stage* stage = reinterpret_cast<Stage*>(smem_raw);             // [2]
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
@@ -248,14 +277,14 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
   // full chunks go through the bulk-copy engine; a ragged last chunk is staged by the threads
   auto issue = [&](int chunk, int buf) {
     const size_t n0 = (size_t)chunk * kPreBlock;
-    PreStage& st = stage[buf];
+    Stage& st = stage[buf];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
-    mbar_expect_tx(&s_bar[buf], kPreStageBytes);
-    bulk_g2s(st.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
+    mbar_expect_tx(&s_bar[buf], BAND ? kPreStageBandBytes : kPreStageBytes);
+    if constexpr (!BAND) bulk_g2s(st.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
     bulk_g2s(st.quat, g.q_raw + n0 * 4, kPreBlock * 4 * 4, &s_bar[buf]);
     bulk_g2s(st.pos, g.pos + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
     bulk_g2s(st.scale, g.scale_raw + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
-    bulk_g2s(st.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    if constexpr (!BAND) bulk_g2s(st.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
     bulk_g2s(st.opac, g.opacity_raw + n0, kPreBlock * 4, &s_bar[buf]);
   };
   auto is_full = [&](int chunk) { return (chunk + 1) * kPreBlock <= g.n; };
@@ -267,17 +296,17 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
     const int buf = it & 1;
     const int next = chunk + gridDim.x;
     if (next < n_chunks && is_full(next) && tid == 0) issue(next, buf ^ 1);
-    PreStage& st = stage[buf];
+    Stage& st = stage[buf];
     const int n0 = chunk * kPreBlock;
     const int count = min(kPreBlock, g.n - n0);
     if (is_full(chunk)) {
       mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
     } else {
-      stage_rows<45>(g.f_rest, st.rest, n0, count);
+      if constexpr (!BAND) stage_rows<45>(g.f_rest, st.rest, n0, count);
       stage_rows<4>(g.q_raw, st.quat, n0, count);
       stage_rows<3>(g.pos, st.pos, n0, count);
       stage_rows<3>(g.scale_raw, st.scale, n0, count);
-      stage_rows<3>(g.f_dc, st.dc, n0, count);
+      if constexpr (!BAND) stage_rows<3>(g.f_dc, st.dc, n0, count);
       stage_rows<1>(g.opacity_raw, st.opac, n0, count);
       __syncthreads();
     }
@@ -295,31 +324,40 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       Projection o;
       const bool vis = project_gaussian(p, S, st.opac[tid], ps, rp, o);
       s7_count += (vis || o.offscreen) ? 1u : 0u;
-      if (depth_hist) {
-        const uint32_t dk = vis ? __float_as_uint(o.z) : kCulledKey;
+      vis_count += vis ? 1u : 0u;
+      // a survivor whose tile rect misses this rank's band [row_begin, row_end) is dropped from the frame
+      int tv0 = 0, tv1 = 0, tiles = 0;
+      if (vis) {
+        tv0 = max(o.tv0, rp.row_begin); tv1 = min(o.tv1, rp.row_end - 1);
+        tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
+      }
+      const bool in_frame = tiles > 0;
+      // BAND: the keys are compacted before the sort, so the histograms cover the band's survivors only
+      if (depth_hist && (!BAND || in_frame)) {
+        const uint32_t dk = in_frame ? __float_as_uint(o.z) : kCulledKey;
         atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
         atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
       }
-      if (!vis) {
+      if (!in_frame) {
         f.depth_key[i] = kCulledKey;
-          f.super_touched[i] = 0;
+        f.super_touched[i] = 0;
       } else {
-        ++vis_count;
         const ViewDir vd = view_dir(p, ps.cam);
-        float Y[16], acc[3], rgb[3];
+        float Y[16], rgb[3];
         sh_basis(vd.d, Y);
-        sh_color(&st.dc[3 * tid], &st.rest[45 * tid], Y, rgb, acc);
-        int tv0 = max(o.tv0, rp.row_begin), tv1 = min(o.tv1, rp.row_end - 1);
-        const int tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
-        if (tiles == 0) { tv0 = 0; tv1 = 0; }
+        if constexpr (BAND) {
+          sh_color_global(g.f_dc + (size_t)i * 3, g.f_rest + (size_t)i * 45, Y, rgb);
+        } else {
+          float acc[3];
+          sh_color(&st.dc[3 * tid], &st.rest[45 * tid], Y, rgb, acc);
+        }
         float eu, ev;
         conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
         write_splat_record(f, i, o, rgb, eu, ev, rp);
         f.depth_key[i] = __float_as_uint(o.z);
         f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
-          tiles_sum += (uint32_t)tiles;
-        f.super_touched[i] =
-            tiles ? (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1)) : 0u;
+        tiles_sum += (uint32_t)tiles;
+        f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
       }
     }
     __syncthreads();   // everyone is done with stage[buf] before it is refilled (two iterations from now)
@@ -642,10 +680,17 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
+      cudaFuncSetAttribute(preprocess_fwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
     }
-    const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
-    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
+    if (rp.row_begin > 0 || rp.row_end < rp.tiles_y) {
+      // a band: 11 KB of stages per CTA, latency-bound on the per-survivor SH gathers; 90 registers x 128 threads
+      // -> 5 resident CTAs per SM
+      const int bgrid = grid < 5 * sm_count ? grid : 5 * sm_count;
+      preprocess_fwd_tma_kernel<true><<<bgrid, kPreBlock, 2 * sizeof(PreStageBand), s>>>(g, c2w, rp, f, grid, depth_hist);
+    } else {
+      const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
+      preprocess_fwd_tma_kernel<false><<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
+    }
     if (hist_done) *hist_done = depth_hist != nullptr;
     return cudaGetLastError();
   }

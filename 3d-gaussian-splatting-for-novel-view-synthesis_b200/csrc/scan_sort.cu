@@ -148,6 +148,89 @@ cudaError_t launch_exclusive_scan(const uint32_t* in, const uint32_t* gather_idx
 }
 
 // =================================================================================================
+// Stable compaction of the live depth keys (tile-row bands: most Gaussians miss the band, so the depth sort
+// should not carry them): (key, id) of every key != culled, in index order, and their number.
+// One pass, decoupled look-back on the per-block counts.
+// =================================================================================================
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 16;
+constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 4096 keys per block
+
+size_t compact_scratch_bytes(uint32_t n) { return 256 + ((size_t)(n + kCompactTile - 1) / kCompactTile + 1) * 8; }
+
+__global__ void __launch_bounds__(kCompactThreads) compact_keys_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                                       uint32_t* __restrict__ out_keys,
+                                                                       uint32_t* __restrict__ out_ids,
+                                                                       uint32_t* __restrict__ count_out,
+                                                                       uint32_t* ticket, unsigned long long* status) {
+  __shared__ uint32_t s_warp[kCompactThreads / 32];
+  __shared__ uint32_t s_tile, s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kCompactTile + tid * kCompactItems;     // thread-contiguous: index order is kept
+  uint32_t k[kCompactItems];
+  if (base + kCompactItems <= n) {
+#pragma unroll
+    for (int q = 0; q < kCompactItems / 4; ++q) {
+      const uint4 v = reinterpret_cast<const uint4*>(keys + base)[q];
+      k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kCompactItems; ++i) k[i] = (base + i < n) ? keys[base + i] : kCulledKey;
+  }
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int i = 0; i < kCompactItems; ++i) cnt += (k[i] != kCulledKey) ? 1u : 0u;
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kCompactThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) warp_off += t;
+    tile_sum += t;
+  }
+  if (warp == 0) {
+    const uint32_t prefix = scan_lookback(status, tile, tile_sum, lane);
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (tile == (n - 1) / kCompactTile) *count_out = prefix + tile_sum;
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_prefix + warp_off + (inc - cnt);
+#pragma unroll
+  for (int i = 0; i < kCompactItems; ++i)
+    if (k[i] != kCulledKey) {
+      out_keys[off] = k[i];
+      out_ids[off] = base + i;
+      ++off;
+    }
+}
+
+cudaError_t launch_compact_keys(const uint32_t* keys, uint32_t n, uint32_t* out_keys, uint32_t* out_ids,
+                                uint32_t* count_out, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  if (n == 0) return cudaMemsetAsync(count_out, 0, 4, s);
+  if (scratch_bytes < compact_scratch_bytes(n)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);
+  if (e != cudaSuccess) return e;
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(scratch);
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + 256);
+  compact_keys_kernel<<<(n + kCompactTile - 1) / kCompactTile, kCompactThreads, 0, s>>>(keys, n, out_keys, out_ids,
+                                                                                      count_out, ticket, status);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
 // Onesweep radix sort (8-bit digits)
 // =================================================================================================
 constexpr int kSortThreads = 256;
@@ -434,7 +517,8 @@ constexpr int kSeItems = 4;
 constexpr int kSeTile = kSeThreads * kSeItems;   // 1024 depth ranks per block
 
 __global__ void __launch_bounds__(kSeThreads) scan_emit_super_kernel(
-    int n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ super_touched,
+    int n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ order,
+    const uint32_t* __restrict__ super_touched,
     const uint2* __restrict__ rect, int super_x, uint32_t capacity, uint32_t* __restrict__ keys,
     uint32_t* __restrict__ vals, b200gs_frame_stats* __restrict__ stats, uint32_t* ticket,
     unsigned long long* status, SortPasses sp, uint32_t* __restrict__ ghist) {
@@ -447,6 +531,8 @@ __global__ void __launch_bounds__(kSeThreads) scan_emit_super_kernel(
   __syncthreads();
   const uint32_t tile = s_tile;
   if (tile == 0 && tid == 0 && stats->n_isect > capacity) stats->overflow = 1u;   // per-tile lists would not fit
+  const int n = (int)eff_count((uint32_t)n_host, n_dev);   // band frames: only the compacted prefix of `order` is live
+  if (tile * (uint32_t)kSeTile >= (uint32_t)n) return;      // uniform; no earlier tile ever waits on a later one
   const uint32_t r0 = tile * kSeTile + tid * kSeItems;
   uint32_t id[kSeItems], cnt[kSeItems], excl[kSeItems];
   uint32_t sum = 0;
@@ -515,8 +601,8 @@ size_t scan_emit_scratch_bytes(uint32_t n) { return 256 + ((size_t)(n + kSeTile 
 
 // Zeroes `sort_scratch` (tickets, histograms, look-back status of the sort that follows) and `se_scratch`,
 // runs the fused kernel; the sort must then be launched with hist_ready = true on the same scratch.
-cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t* super_touched, const uint2* rect,
-                                   int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
+cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t* order, const uint32_t* super_touched,
+                                   const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
                                    b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
                                    size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
                                    cudaStream_t s) {
@@ -531,7 +617,7 @@ cudaError_t launch_scan_emit_super(int n, const uint32_t* order, const uint32_t*
   uint32_t* ticket = reinterpret_cast<uint32_t*>(se_scratch);
   unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(se_scratch) + 256);
   const SortPasses sp = make_passes(0, sort_bits);
-  scan_emit_super_kernel<<<(n + kSeTile - 1) / kSeTile, kSeThreads, 0, s>>>(n, order, super_touched, rect, super_x,
+  scan_emit_super_kernel<<<(n + kSeTile - 1) / kSeTile, kSeThreads, 0, s>>>(n, n_dev, order, super_touched, rect, super_x,
                                                                           capacity, keys, vals, stats, ticket, status,
                                                                           sp, ghist);
   return cudaGetLastError();

@@ -70,7 +70,12 @@ typedef struct b200gs_camera {
   int32_t tile;          /* must be 16 */
   int32_t tile_row_begin; /* render only tile rows [begin, end) - tile-row sharding; 0,0 = all */
   int32_t tile_row_end;
+  int32_t flags;         /* B200GS_CAM_* bits */
 } b200gs_camera;
+/* A band normally zeroes the pixels outside its tile rows (render.py:318: untouched pixels are 0).  With this bit
+ * the rasterizer writes the band's pixels only and leaves the rest of image_out alone - image_out may then be the
+ * frame buffer of another GPU (peer-mapped memory), into which every rank stores its own band. */
+#define B200GS_CAM_KEEP_OUTSIDE_BAND 1
 
 /* Gradients written by b200gs_render_backward.  Non-null members are OVERWRITTEN (dense, zero for
  * culled Gaussians).  Members for the path not in use must be NULL. */
@@ -98,7 +103,8 @@ typedef struct b200gs_frame_stats {
   uint32_t n_in_frustum; /* survivors of S1-S7 (before the on-screen test; render.py:235 raises when
                             this is > 0 but n_visible == 0) */
   uint32_t n_super;    /* (supertile, Gaussian) pairs: the number of keys the binning sort handles */
-  uint32_t reserved[11];
+  uint32_t n_sorted;   /* band frames: Gaussians whose tile rect meets the band (the keys the depth sort handles) */
+  uint32_t reserved[10];
 } b200gs_frame_stats;
 
 int b200gs_abi_version(void);

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from b200gs.dist import allreduce_gradients, render_tile_row_sharded, shard_tile_rows, shard_views
+from b200gs.dist import GradBucket, allreduce_gradients, render_tile_row_sharded, shard_tile_rows, shard_views
 
 
 def test_shard_views_round_robin():
@@ -66,6 +66,22 @@ def _worker(rank, world, port, out):
             img[b * 16:min(e * 16, H)] = float(rank + 1)
             return img
         out[f"img{rank}"] = render_tile_row_sharded(fake_render, rows)
+        # a generator argument with average=True (consumed once), and a non-contiguous gradient
+        a = torch.nn.Parameter(torch.zeros(3, 4))
+        a.grad = torch.full((4, 3), float(rank + 1)).t()
+        allreduce_gradients((x for x in [a]), average=True)
+        out[f"avg{rank}"] = a.grad.clone()
+        # one flat bucket, one collective: same sums as the per-tensor all-reduce; p.grad becomes a view of the bucket
+        p2 = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
+        q2 = torch.nn.Parameter(torch.ones(5))
+        bucket = GradBucket([p2, q2])
+        for it in range(2):
+            bucket.zero_grad()
+            sum(((v + 1 + it) * p2).sum() for v in views).backward()
+            bucket.allreduce()
+            assert p2.grad.data_ptr() == bucket.views[0].data_ptr()
+            out[f"bp{rank}_{it}"] = p2.grad.clone()
+            out[f"bq{rank}_{it}"] = q2.grad.clone()
     finally:
         dist.destroy_process_group()
 
@@ -83,3 +99,7 @@ def test_two_rank_gloo_allreduce_and_bands():
         img = out[f"img{r}"]
         assert torch.equal(img[:32], torch.full((32, 8, 3), 1.0))       # rows 0-1 -> rank 0 (2 of 3 tile rows)
         assert torch.equal(img[32:], torch.full((8, 8, 3), 2.0))        # row 2 -> rank 1
+        assert torch.equal(out[f"avg{r}"], torch.full((3, 4), 1.5))      # (1 + 2) / 2, generator consumed once
+        for it in range(2):
+            assert torch.equal(out[f"bp{r}_{it}"], torch.full((2, 3), float(sum(v + 1 + it for v in range(5)))))
+            assert torch.equal(out[f"bq{r}_{it}"], torch.zeros(5))

@@ -64,6 +64,35 @@ def _worker(rank, world, port, out):
             fn = lambda tile_rows: b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[1]["fx"],
                                                  cams[1]["fy"], cams[1]["cx"], cams[1]["cy"], tile_rows=tile_rows)
             out[f"img{rank}"] = render_tile_row_sharded(fn, (H + 15) // 16).cpu()
+            # the same frame through TileRowRenderer: bands stored straight into rank 0's buffer over peer memory
+            from b200gs.dist import TileRowRenderer
+            tr = TileRowRenderer(H, W, dev)
+            for rep in range(3):               # several frames: the buffer is reused, the barriers must order them
+                cam_k = cams[1 + rep % 2]
+                c2w_k = cam_k["c2w"].to(dev)
+                col_k = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w_k)
+                img = tr.render(leaves["pos"], col_k, leaves["opacity_raw"], sigma, c2w_k, cam_k["fx"], cam_k["fy"],
+                                cam_k["cx"], cam_k["cy"])
+                torch.cuda.synchronize()
+                if rank == 0:
+                    out[f"tr{rep}"] = img.cpu()
+            w8 = tr.row_weights(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, cams[1]["fx"], cams[1]["fy"],
+                                cams[1]["cx"], cams[1]["cy"])
+            tr.set_weights(w8)
+            img = tr.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, cams[1]["fx"], cams[1]["fy"],
+                            cams[1]["cx"], cams[1]["cy"])
+            torch.cuda.synchronize()
+            if rank == 0:
+                out["tr_weighted"] = img.cpu()
+                out["tr_bands"] = list(tr.bands)
+        # one flat bucket + one NCCL all-reduce gives the same gradients as the six all-reduces
+        from b200gs.dist import GradBucket
+        leaves2 = {k: sc[k].to(dev).requires_grad_(True) for k in PARAMS}
+        bucket = GradBucket([leaves2[k] for k in PARAMS])
+        _loss_for_views(b200gs, leaves2, cams, shard_views(n_views, rank, world), W, H, dev, n_views).backward()
+        assert leaves2["f_rest"].grad.data_ptr() == bucket.views[PARAMS.index("f_rest")].data_ptr()   # written in place
+        bucket.allreduce()
+        out[f"bgrads{rank}"] = {k: leaves2[k].grad.cpu() for k in PARAMS}
     finally:
         dist.destroy_process_group()
 
@@ -99,3 +128,15 @@ def test_dp_gradients_and_tile_row_bands_match_single_gpu():
         full = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[1]["fx"], cams[1]["fy"],
                              cams[1]["cx"], cams[1]["cy"]).cpu()
     assert torch.equal(out["img0"], full) and torch.equal(out["img1"], full)
+    assert torch.equal(out["tr0"], full) and torch.equal(out["tr2"], full) and torch.equal(out["tr_weighted"], full)
+    assert out["tr_bands"][0][0] == 0 and out["tr_bands"][-1][1] == (H + 15) // 16
+    with torch.no_grad():
+        c2w = cams[2]["c2w"].to(dev)
+        col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
+        other = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[2]["fx"], cams[2]["fy"],
+                              cams[2]["cx"], cams[2]["cy"]).cpu()
+    assert torch.equal(out["tr1"], other)
+    for k in PARAMS:
+        for r in range(world):
+            err = float((out[f"bgrads{r}"][k] - leaves[k].grad.cpu()).abs().max() / leaves[k].grad.abs().max())
+            assert err <= 1e-5, (k, r, err)

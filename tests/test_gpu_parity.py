@@ -17,6 +17,9 @@ from common import (GOLDEN_CASES, GRAD_CASES, PARAMS, canonical_lists, golden_in
 pytestmark = pytest.mark.gpu
 IMG_TOL = 1e-4
 GRAD_TOL = 1e-3
+# radius / tile-rect flips allowed per golden case (measured on a B200: see profiles/PARITY_r02.json); cases not
+# listed fall back to 1 in 2000 survivors
+RADIUS_FLIP_LIMIT = {}
 
 
 @pytest.fixture(scope="module")
@@ -126,7 +129,7 @@ def test_build_sigma_and_evaluate_sh(gs, name):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_forward_against_golden(gs, name, fused):
+def test_forward_against_golden(gs, name, fused, parity_log):
     G = load_golden(name)
     sc, cam = golden_inputs(G, "cuda")
     img, frame = _render_frame(gs, sc, cam, fused=fused)
@@ -158,24 +161,39 @@ def test_forward_against_golden(gs, name, fused):
     assert np.array_equal(vis, vis_ref), f"survivor sets differ in {(vis != vis_ref).sum()} Gaussians"
     assert frame.n_visible == gid.shape[0]
     assert np.array_equal(ex["depth"][gid], G["z"])
-    n_rad = int((ex["radius"][gid] != G["radius"]).sum())
-    n_rect = int((ex["rect"][gid] != G["rect"]).any(1).sum())
-    if fused:   # exp() of the log-scales is evaluated by a different libm on the GPU: allow 1-ulp flips
-        assert n_rad <= max(1, gid.shape[0] // 2000) and n_rect <= max(1, gid.shape[0] // 2000), (n_rad, n_rect)
-    else:
-        assert n_rad <= max(1, gid.shape[0] // 2000) and n_rect <= max(1, gid.shape[0] // 2000), (n_rad, n_rect)
-    if n_rad == 0 and n_rect == 0:
-        z_of = np.full(n, np.inf, np.float32)
-        z_of[gid] = G["z"]
-        t_ref, i_ref = canonical_lists(G["list_tile"], G["list_id"], z_of)
-        t_me, i_me = canonical_lists(ex["list_tile"], ex["list_id"], z_of)
-        assert np.array_equal(t_ref, t_me) and np.array_equal(i_ref, i_me)
+    rad_bad = ex["radius"][gid] != G["radius"]
+    rect_bad = (ex["rect"][gid] != G["rect"]).any(1)
+    n_rad, n_rect = int(rad_bad.sum()), int(rect_bad.sum())
+    # Radius = ceil(2.5 sqrt(lambda_max)) and the rect's floor() are step functions of fp32 values that the GPU forms
+    # with FMAs and its own exp/sqrt: a value within an ulp of an integer may land on the other side, exactly as it
+    # does between the reference's own fp32 and fp64 runs.  The count is bounded (1 in 2000) AND recorded
+    # (profiles/PARITY_r02.json); the list comparison below never depends on it being zero.
+    limit = RADIUS_FLIP_LIMIT.get(name, max(1, gid.shape[0] // 2000))
+    assert n_rad <= limit and n_rect <= limit, (n_rad, n_rect)
+    # per-tile lists against the REFERENCE, always: Gaussians whose rect flipped (none on most cases) are taken out
+    # of both sides, every other (tile, id) entry must match in order
+    z_of = np.full(n, np.inf, np.float32)
+    z_of[gid] = G["z"]
+    flipped = np.zeros(n, bool)
+    flipped[gid[rect_bad]] = True
+    keep_r, keep_m = ~flipped[G["list_id"]], ~flipped[ex["list_id"]]
+    t_ref, i_ref = canonical_lists(G["list_tile"][keep_r], G["list_id"][keep_r], z_of)
+    t_me, i_me = canonical_lists(ex["list_tile"][keep_m], ex["list_id"][keep_m], z_of)
+    assert np.array_equal(t_ref, t_me) and np.array_equal(i_ref, i_me)
+    if n_rect == 0:
         assert frame.n_isect == G["list_id"].shape[0]
     assert np.abs(ex["xy"][gid, 0] - G["u"]).max() <= 1e-4 and np.abs(ex["xy"][gid, 1] - G["v"]).max() <= 1e-4
     assert np.abs(ex["opacity"][gid] - G["opacity"]).max() <= 1e-6
     assert np.abs(ex["color"][gid] - G["color"][gid]).max() <= 2e-6
     # image
     rep = image_report(img.cpu().numpy(), G["image"], G["image64"], IMG_TOL)
+    parity_log[f"golden/{name}/{'fused' if fused else 'unfused'}"] = dict(
+        rep, V=int(gid.shape[0]), I=int(frame.n_isect), radius_mismatches=n_rad, rect_mismatches=n_rect,
+        survivors_equal=True, depth_bit_equal=True, lists_equal=True, lists_compared_excluding=int(flipped.sum()),
+        n_values=int(G["image"].size))
+    # Image: <= 1e-4 absolute, except pixels where a threshold test (q <= 6.25, alpha >= 1/128, T > 5e-5) flips for a
+    # pair within a few ulp of the threshold - which also happens between the reference's own fp32 and fp64 runs, so
+    # the number of such pixels is bounded by the reference's own fp32-vs-fp64 count (and recorded).
     assert rep["n_bad_min"] <= 2 * rep["n_bad_ref32_vs_ref64"] + 2, rep
     assert rep["max_vs_ref32"] <= max(0.012, 2 * rep["max_ref32_vs_ref64"]), rep
     if name != "edge_1500_97x71":
@@ -231,7 +249,7 @@ def test_empty_and_offscreen_behaviour(gs):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", GRAD_CASES)
-def test_gradients_against_reference_autograd(gs, name, fused, monkeypatch):
+def test_gradients_against_reference_autograd(gs, name, fused, monkeypatch, parity_log):
     monkeypatch.setenv("B200GS_FUSE", "1" if fused else "0")
     G = load_golden(name)
     sc, cam = golden_inputs(G, "cuda")
@@ -241,12 +259,15 @@ def test_gradients_against_reference_autograd(gs, name, fused, monkeypatch):
     img = gs.render(leaves["pos"], color, leaves["opacity_raw"], sigma, cam["c2w"], cam["H"], cam["W"], cam["fx"],
                     cam["fy"], cam["cx"], cam["cy"])
     (img * torch.from_numpy(G["loss_w"]).cuda()).sum().backward()
+    rec = {}
     for k in PARAMS:
         mine = leaves[k].grad.cpu().numpy()
         assert np.isfinite(mine).all(), k
         e32, e64 = grad_relerr(mine, G["grad_" + k]), grad_relerr(mine, G["grad64_" + k])
         noise = grad_relerr(G["grad_" + k], G["grad64_" + k])
+        rec[k] = {"vs_ref32": e32, "vs_ref64": e64, "ref32_vs_ref64": noise}
         assert min(e32, e64) <= max(GRAD_TOL, 2 * noise), (name, k, e32, e64, noise)
+    parity_log[f"golden_grads/{name}/{'fused' if fused else 'unfused'}"] = rec
 
 
 def test_gradient_accumulates_over_views(gs):
@@ -331,7 +352,7 @@ def test_full_size_invariants(gs, n, W, H, ls):
 @pytest.mark.parametrize("n,W,H,ls,view,seed", [(20_000, 325, 211, -3.6, 2, 21),     # C3-like aspect: 1-px edge column
                                                  (12_000, 480, 270, -3.3, 5, 22),     # 1080p aspect, 14-px edge row
                                                  (5_000, 64, 64, -2.2, 1, 23)])       # few tiles, long lists (many batches)
-def test_live_oracle_forward_backward(gs, n, W, H, ls, view, seed):
+def test_live_oracle_forward_backward(gs, n, W, H, ls, view, seed, parity_log):
     from oracle import gs_oracle as O
     sc = O.make_scene(n, seed=seed, log_scale=ls, unique_depth=True)
     cam = O.make_camera(W, H, view=view, n_views=8)
@@ -348,11 +369,13 @@ def test_live_oracle_forward_backward(gs, n, W, H, ls, view, seed):
     (img * w.cuda()).sum().backward()
     d = (img.detach().cpu() - img_ref.detach()).abs()
     n_bad = int((d > IMG_TOL).sum())
+    errs = {k: grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy()) for k in PARAMS}
+    parity_log[f"live_oracle/{n}_{W}x{H}"] = {"max_abs": float(d.max()), "n_gt_tol": n_bad, "n_values": int(d.numel()),
+                                               "grad_rel": errs}
     assert n_bad <= max(3, d.numel() // 50_000), (n_bad, float(d.max()))      # threshold-flip pixels only
     assert float(d.max()) <= 0.02
     for k in PARAMS:
-        err = grad_relerr(mine[k].grad.cpu().numpy(), ref[k].grad.numpy())
-        assert err <= 3 * GRAD_TOL if n_bad else err <= GRAD_TOL, (k, err, n_bad)
+        assert errs[k] <= 3 * GRAD_TOL if n_bad else errs[k] <= GRAD_TOL, (k, errs[k], n_bad)
 
 
 def test_speculative_capacity_overflow_is_redone_with_exact_buffers(gs):
@@ -504,3 +527,62 @@ def test_backward_is_linear_in_the_image_gradient_at_full_size(gs):
         scale = float(torch.maximum(a.abs().max(), b.abs().max()))
         assert scale > 0, k
         assert float((c - want).abs().max()) <= 2e-4 * scale, (k, float((c - want).abs().max()), scale)
+
+
+def test_deferred_tensors_behave_like_the_tensors_they_stand_for(gs, tmp_path):
+    """build_sigma_from_params / evaluate_sh return deferred tensors (api._Deferred) that only `render` can consume
+    without running the stand-alone kernel; everything else a script may do with them must give the eager result:
+    .cpu(), indexing, arithmetic, torch.save / torch.load, requires_grad / grad_fn, backward through them."""
+    from oracle import gs_oracle as O
+    sc = O.make_scene(2000, seed=3, log_scale=-3.0)
+    cam = O.make_camera(96, 64)
+    lv = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    c2w = cam["c2w"].cuda()
+    ref_sigma = O.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+    ref_color = O.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], cam["c2w"])
+    sigma = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+    color = gs.evaluate_sh(lv["f_dc"], lv["f_rest"], lv["pos"], c2w)
+    assert sigma.shape == (2000, 3, 3) and color.shape == (2000, 3) and sigma.dtype == torch.float32 and sigma.is_cuda
+    assert len(sigma) == 2000 and sigma.dim() == 3 and color.numel() == 6000
+    assert float((sigma.cpu() - ref_sigma).abs().max()) <= 2e-6 * float(ref_sigma.abs().max())
+    assert float((color[5:9].cpu() - ref_color[5:9]).abs().max()) <= 1e-6                       # indexing
+    assert float(((color * 2 + 1).cpu() - (ref_color * 2 + 1)).abs().max()) <= 2e-6             # arithmetic
+    assert sigma.requires_grad and color.requires_grad
+    torch.save({"sigma": sigma, "color": color.detach()}, tmp_path / "d.pt")                     # serialisation
+    back = torch.load(tmp_path / "d.pt")
+    assert float((back["sigma"].cpu() - ref_sigma).abs().max()) <= 2e-6 * float(ref_sigma.abs().max())
+    assert float((back["color"].cpu() - ref_color).abs().max()) <= 1e-6
+    # autograd through a materialised deferred tensor reaches the leaves
+    s2 = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+    (s2.sum() + gs.evaluate_sh(lv["f_dc"], lv["f_rest"], lv["pos"], c2w).sum()).backward()
+    assert lv["scale_raw"].grad is not None and lv["f_rest"].grad is not None and float(lv["f_dc"].grad.abs().max()) > 0
+    with torch.no_grad():
+        s3 = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+        assert not s3.requires_grad
+        assert float((s3.cpu() - ref_sigma).abs().max()) <= 2e-6 * float(ref_sigma.abs().max())
+
+
+def test_non_fp32_inputs_are_rejected(gs):
+    """The reference follows pos.dtype (render.py:318); this path computes in fp32 only and says so instead of
+    silently rounding an fp64 scene."""
+    from oracle import gs_oracle as O
+    sc = {k: v.cuda().double() for k, v in O.make_scene(64, seed=1).items()}
+    cam = O.make_camera(32, 32)
+    with pytest.raises(TypeError, match="float32"):
+        gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+    with pytest.raises(TypeError, match="float32"):
+        gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], cam["c2w"].cuda().double())
+    with pytest.raises(TypeError, match="float32"):
+        gs.render(sc["pos"], torch.zeros(64, 3, device="cuda", dtype=torch.float64), sc["opacity_raw"],
+                  torch.zeros(64, 3, 3, device="cuda", dtype=torch.float64), cam["c2w"].cuda(), 32, 32, 28., 28., 16., 16.)
+
+
+def test_mismatched_row_counts_raise_instead_of_reading_out_of_bounds(gs):
+    from oracle import gs_oracle as O
+    sc = {k: v.cuda() for k, v in O.make_scene(100, seed=1).items()}
+    cam = O.make_camera(32, 32)
+    c2w = cam["c2w"].cuda()
+    sigma = gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
+    color = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
+    with pytest.raises(ValueError):
+        gs.render(sc["pos"][:50], color, sc["opacity_raw"][:50], sigma, c2w, 32, 32, 28., 28., 16., 16.)

@@ -64,10 +64,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iterations", type=int, default=150)
     ap.add_argument("--logdir", default=os.path.join(ROOT, "gpurun_out"))
+    ap.add_argument("--profile", action="store_true", help="run the training script under cProfile and print the top entries")
     args = ap.parse_args()
-    ref = os.environ.get("B200GS_REFERENCE_ROOT")
-    if not ref or not os.path.exists(os.path.join(ref, "scripts", "train.py")):
-        raise SystemExit("set B200GS_REFERENCE_ROOT to a checkout of the reference repository")
+    ref = os.environ.get("B200GS_REFERENCE_ROOT") or os.path.join(ROOT, "baseline", "_ref")    # the staged, unmodified copy
+    if not os.path.exists(os.path.join(ref, "scripts", "train.py")):
+        raise SystemExit("set B200GS_REFERENCE_ROOT to a checkout of the reference repository (or stage one: "
+                         "python baseline/stage_reference.py)")
     os.makedirs(args.logdir, exist_ok=True)
     work = tempfile.mkdtemp(prefix="b200gs_scripts_")
     data = os.path.join(work, "data")
@@ -78,9 +80,15 @@ def main():
     for tag, extra in (("stock_adam", {}), ("fused_adam", {"B200GS_PATCH_ADAM": "1"})):
         out = os.path.join(work, "out_" + tag)
         e = dict(env, **extra)
-        rc |= run([sys.executable, "-m", "b200gs.run", os.path.join(ref, "scripts", "train.py"), "--data_dir", data,
+        prof = ["-m", "cProfile", "-o", os.path.join(work, tag + ".prof")] if args.profile else []
+        rc |= run([sys.executable, *prof, "-m", "b200gs.run", os.path.join(ref, "scripts", "train.py"), "--data_dir", data,
                    "--output_dir", out, "--iterations", str(args.iterations), "--scale_factor", "1.0"], e,
                   os.path.join(args.logdir, f"ref_train_{tag}.log"))
+        if args.profile:
+            import pstats
+            st = pstats.Stats(os.path.join(work, tag + ".prof"))
+            print(f"----- cProfile, {tag}: top 25 by cumulative time -----")
+            st.sort_stats("cumulative").print_stats(25)
         rc |= run([sys.executable, "-m", "b200gs.run", os.path.join(ref, "scripts", "render_trained.py"), "--checkpoint_dir", out,
                    "--data_dir", data, "--orbit_frames", "12", "--benchmark_only", "--output_dir", os.path.join(work, "renders_" + tag)],
                   e, os.path.join(args.logdir, f"ref_render_{tag}.log"))

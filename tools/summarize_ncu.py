@@ -39,6 +39,12 @@ KEEP = ["ID", "Kernel Name", "launch__grid_size", "launch__block_size", "launch_
         "smsp__inst_executed_op_shared_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum"]
 
 
+# single-kernel regions of bench.py's per-kernel table (multi-kernel regions keep the figures of an earlier capture)
+REGION_OF = {"blend_fwd_kernel": "blend_fwd", "blend_bwd_kernel": "blend_bwd", "preprocess_fwd_tma_kernel": "preprocess_fwd",
+             "preprocess_bwd_tma_kernel": "preprocess_bwd", "l1_ssim_fwd_kernel": "l1_ssim_fwd",
+             "l1_ssim_bwd_kernel": "l1_ssim_bwd", "adam_step_kernel": "adam_step", "scan_emit_super_kernel": "emit_super"}
+
+
 def full(src, dst, traffic=None):
     rows = list(csv.reader(open(src)))
     hdr, units = rows[0], rows[1]
@@ -54,9 +60,15 @@ def full(src, dst, traffic=None):
             def val(k):
                 v, u = float(r[hdr.index(k)]), units[hdr.index(k)]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            tr.setdefault(name.split("<")[0], val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+            region = REGION_OF.get(name.split("<")[0])
+            if region and region not in tr:
+                tr[region] = {"dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                              "inst_executed": float(r[hdr.index("smsp__inst_executed.sum")])}
     if traffic:
-        json.dump(tr, open(traffic, "w"), indent=1)
+        old = json.load(open(traffic)) if __import__("os").path.exists(traffic) else {}
+        old.update(tr)
+        old["_source"] = dst
+        json.dump(old, open(traffic, "w"), indent=1)
 
 
 if __name__ == "__main__":
