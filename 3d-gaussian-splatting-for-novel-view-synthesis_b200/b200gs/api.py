@@ -24,7 +24,20 @@ import torch
 
 from . import ops
 
-_TAG = "_b200gs_src"
+# Tags (what a derived tensor was computed from) live in a side table keyed by the tensor's identity, NOT in the
+# tensor's __dict__: Python state on a tensor changes how torch pickles it (torch.save of a tagged tensor would
+# need the tag to be picklable and loadable under weights_only), and a saved / copied tensor must be a plain tensor.
+_tags = {}
+
+
+def _set_tag(t, src) -> None:
+    key = id(t)
+    _tags[key] = (weakref.ref(t, lambda _r, k=key: _tags.pop(k, None)), src)
+
+
+def _get_tag(t):
+    e = _tags.get(id(t))
+    return e[1] if e is not None and e[0]() is t else None
 
 
 def _fusion_enabled() -> bool:
@@ -60,9 +73,9 @@ class _Deferred(torch.Tensor):
         if self._value is None:
             with torch.set_grad_enabled(self._grad_mode):
                 self._value = self._thunk()
-            src = getattr(self, _TAG, None)
+            src = _get_tag(self)
             if src is not None:
-                setattr(self._value, _TAG, src)
+                _set_tag(self._value, src)
             self._thunk = None
         return self._value
 
@@ -91,6 +104,10 @@ class _Deferred(torch.Tensor):
         args = torch.utils._pytree.tree_map(unwrap, args)
         kwargs = torch.utils._pytree.tree_map(unwrap, kwargs or {})
         return func(*args, **kwargs)
+
+    def __reduce_ex__(self, proto):
+        # torch.save / pickle / copy.deepcopy store the tensor this object stands for (a plain tensor)
+        return self.materialize().__reduce_ex__(proto)
 
     def __repr__(self):
         return f"_Deferred({'pending' if self._value is None else 'materialized'}, shape={tuple(self.shape)})"
@@ -129,7 +146,7 @@ def build_sigma_from_params(scale_raw: torch.Tensor, q_raw: torch.Tensor) -> tor
                           scale_raw.device, needs)
     else:
         sigma = ops._BuildSigma.apply(scale_raw, q_raw)
-    setattr(sigma, _TAG, _Source(scale_raw, q_raw))
+    _set_tag(sigma, _Source(scale_raw, q_raw))
     return sigma
 
 
@@ -146,7 +163,7 @@ def evaluate_sh(f_dc: torch.Tensor, f_rest: torch.Tensor, points: torch.Tensor, 
                           (points.shape[0], 3), points.dtype, points.device, needs)
     else:
         color = ops._EvaluateSH.apply(f_dc, f_rest, points, c2w.to(device=points.device))
-    setattr(color, _TAG, _Source(f_dc, f_rest, points, c2w))
+    _set_tag(color, _Source(f_dc, f_rest, points, c2w))
     return color
 
 
@@ -183,11 +200,11 @@ def _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, fa
     c2w_d = ops._f32c(c2w.to(device=pos.device))
     scale_raw = q_raw = f_dc = f_rest = None
     if _fusion_enabled():
-        src = getattr(sigma, _TAG, None)
+        src = _get_tag(sigma)
         got = src.resolve() if src is not None else None
         if got is not None:
             scale_raw, q_raw = got
-        src = getattr(color, _TAG, None)
+        src = _get_tag(color)
         got = src.resolve() if src is not None else None
         if got is not None and got[2] is pos and (got[3] is c2w or torch.equal(got[3].to(c2w_d.device), c2w_d)):
             f_dc, f_rest = got[0], got[1]

@@ -132,6 +132,49 @@ def _setup_dp():
     return rank, world
 
 
+def _install_trace():
+    """B200GS_RUN_TRACE=1: wall-clock totals of the host-side calls a training iteration makes (where does the host wait?),
+    printed when the script ends.  A debugging aid; changes nothing else."""
+    import atexit
+    import time
+    import torch
+    acc = {}
+
+    def wrap(owner, name, label=None):
+        fn = getattr(owner, name)
+        label = label or f"{getattr(owner, '__name__', owner)}.{name}"
+
+        def timed(*a, **kw):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **kw)
+            finally:
+                e = acc.setdefault(label, [0, 0.0])
+                e[0] += 1
+                e[1] += time.perf_counter() - t0
+        setattr(owner, name, timed)
+    wrap(torch.cuda, "empty_cache")
+    wrap(torch.cuda, "synchronize")
+    wrap(torch.Tensor, "backward", "Tensor.backward")
+    wrap(torch.Tensor, "item", "Tensor.item")
+    wrap(torch.Tensor, "cpu", "Tensor.cpu")
+    wrap(torch.Tensor, "to", "Tensor.to")
+    wrap(torch.nn.utils, "clip_grad_norm_")
+    wrap(torch.optim.Adam, "step", "Adam.step")
+    wrap(torch.optim.Adam, "__init__", "Adam.__init__")
+    for mod, attr in (("gaussian_splatting.render", "render"), ("gaussian_splatting.spherical_harmonics", "evaluate_sh"),
+                      ("gaussian_splatting.gaussian", "build_sigma_from_params"), ("gaussian_splatting.losses", "compute_loss")):
+        wrap(sys.modules[mod], attr, attr)
+    t_start = time.perf_counter()
+
+    def report():
+        total = time.perf_counter() - t_start
+        print(f"[b200gs.run trace] wall {total:.3f} s", file=sys.stderr)
+        for k, (n, t) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
+            print(f"[b200gs.run trace] {k:28s} calls {n:6d}  total {t:8.3f} s  mean {t / max(n, 1) * 1e3:8.3f} ms", file=sys.stderr)
+    atexit.register(report)
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     dp = bool(argv) and argv[0] == "--dp"
@@ -149,6 +192,8 @@ def main(argv=None):
     world = 1
     if dp:
         _, world = _setup_dp()
+    if os.environ.get("B200GS_RUN_TRACE") == "1":
+        _install_trace()
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")

@@ -13,14 +13,14 @@
 //      first counting (tile ranges), then writing.
 // The per-tile depth-sorted lists that come out are exactly the reference's; only their placement in the
 // list buffer is grouped by supertile instead of by ascending tile id (the blend only needs ranges[t]).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs {
 
 constexpr int kEmitBlock = 256;
-constexpr int kSplitThreads = 256;
 constexpr int kSplitParts = 4;     // CTAs per supertile: each takes a contiguous quarter of the supertile's list
-constexpr int kSplitWarps = kSplitThreads / 32;
 constexpr int kSuperTiles = kSuperX * kSuperY;   // 32: one bit per tile in a 32-bit mask
 
 // One thread per depth rank r.  Gaussian id = order[r]; its supertile pairs go to [offsets[r], +count).
@@ -103,12 +103,12 @@ __device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t m, int lane) {
 }
 
 constexpr int kSplitPer = 4;                                  // entries per thread and iteration
-constexpr int kSplitChunk = kSplitThreads * kSplitPer;        // 2048 entries per iteration
-constexpr int kSplitRows = kSplitWarps * kSplitPer;           // warp-chunks per iteration, in list order
 
 // One CTA per supertile.  WRITE == false: count the entries of each of its 32 tiles -> tile_count.
 // WRITE == true: derive the tile ranges from tile_count and write the per-tile lists.
-template <bool WRITE>
+// kSplitThreads: CTA size (256; a 128-thread variant - 512 entries per iteration for list quarters of ~650 entries -
+// was measured and is slower, see launch_split_super).
+template <bool WRITE, int kSplitThreads>
 __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32_t* __restrict__ keys,
                                                                     const uint32_t* __restrict__ vals,
                                                                     const uint2* __restrict__ rect,
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
                                                                     uint32_t* __restrict__ part_total,
                                                                     uint2* __restrict__ ranges,
                                                                     uint32_t* __restrict__ lists) {
+  constexpr int kSplitWarps = kSplitThreads / 32;
+  constexpr int kSplitChunk = kSplitThreads * kSplitPer;        // entries per iteration
+  constexpr int kSplitRows = kSplitWarps * kSplitPer;           // warp-chunks per iteration, in list order
   __shared__ uint32_t s_wc[kSplitRows][kSuperTiles];    // per-warp-chunk tile counts, then exclusive offsets
   __shared__ uint32_t s_run[kSuperTiles];               // entries already placed per tile
   __shared__ uint32_t s_base[kSuperTiles];              // start of each tile's list in `lists`
@@ -239,13 +242,17 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
   const int grid = super_x * super_y * kSplitParts;
   if (grid <= 0) return cudaSuccess;
   uint32_t* part_total = tile_count + (size_t)grid * kSuperTiles;     // one word per CTA, behind the per-tile counts
-  if (write) {
-    split_super_kernel<true><<<grid, kSplitThreads, 0, s>>>(keys, vals, rect, capacity, stats, super_x, tiles_x,
-                                                           tiles_y, tile_count, part_total, ranges, lists);
+  // measured on the headline frame (count + write): 256 threads 64.9 us, 128 threads 81.7 us
+  static const int threads = getenv("B200GS_SPLIT_THREADS") ? atoi(getenv("B200GS_SPLIT_THREADS")) : 256;
+#define GS_SPLIT_ARGS keys, vals, rect, capacity, stats, super_x, tiles_x, tiles_y, tile_count, part_total, ranges, lists
+  if (threads == 256) {
+    if (write) split_super_kernel<true, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);
+    else split_super_kernel<false, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);
   } else {
-    split_super_kernel<false><<<grid, kSplitThreads, 0, s>>>(keys, vals, rect, capacity, stats, super_x, tiles_x,
-                                                            tiles_y, tile_count, part_total, ranges, lists);
+    if (write) split_super_kernel<true, 128><<<grid, 128, 0, s>>>(GS_SPLIT_ARGS);
+    else split_super_kernel<false, 128><<<grid, 128, 0, s>>>(GS_SPLIT_ARGS);
   }
+#undef GS_SPLIT_ARGS
   return cudaGetLastError();
 }
 

@@ -28,7 +28,8 @@ def compare_frame(ex: Dict[str, np.ndarray], n_isect: int, n_visible: int, image
                   tol: float = 1e-4, image_ref64=None) -> dict:
     """`ex` = Frame.export() as numpy arrays; `proj`, `bins` = the oracle's Projected / Binned; images [H,W,3]."""
     n = ex["depth"].shape[0]
-    gid = proj.ids.numpy()
+    np_ = lambda t: t.detach().numpy()                   # the stages may sit on an autograd graph (backward tests)
+    gid = np_(proj.ids)
     vis = ex["tiles_touched"] >= 0
     vis_ref = np.zeros(n, bool)
     vis_ref[gid] = True
@@ -39,18 +40,18 @@ def compare_frame(ex: Dict[str, np.ndarray], n_isect: int, n_visible: int, image
     rep["survivors_differ"] = int((vis != vis_ref).sum())
     both = vis & vis_ref
     idx = gid[both[gid]]                               # reference survivors that the GPU also kept, in depth order
-    z_ref = proj.z.numpy()[both[gid]]
+    z_ref = np_(proj.z)[both[gid]]
     rep["depth_bit_equal"] = bool(np.array_equal(ex["depth"][idx], z_ref))
-    rad_bad = ex["radius"][idx] != proj.radius.numpy()[both[gid]]
-    rect_bad = (ex["rect"][idx] != proj.rect.numpy()[both[gid]]).any(1)
+    rad_bad = ex["radius"][idx] != np_(proj.radius)[both[gid]]
+    rect_bad = (ex["rect"][idx] != np_(proj.rect)[both[gid]]).any(1)
     rep["radius_mismatches"] = int(rad_bad.sum())
     rep["rect_mismatches"] = int(rect_bad.sum())
-    rep["max_abs_uv"] = float(max(np.abs(ex["xy"][idx, 0] - proj.u.numpy()[both[gid]]).max(initial=0.0),
-                                  np.abs(ex["xy"][idx, 1] - proj.v.numpy()[both[gid]]).max(initial=0.0)))
+    rep["max_abs_uv"] = float(max(np.abs(ex["xy"][idx, 0] - np_(proj.u)[both[gid]]).max(initial=0.0),
+                                  np.abs(ex["xy"][idx, 1] - np_(proj.v)[both[gid]]).max(initial=0.0)))
     # per-tile lists, canonicalised; Gaussians whose rect differs (if any) are taken out of BOTH sides and counted
     z_of = np.full(n, np.inf, np.float32)
-    z_of[gid] = proj.z.numpy()
-    ref_tile, ref_id = bins.tile_ids.numpy(), gid[bins.ranks.numpy()]
+    z_of[gid] = np_(proj.z)
+    ref_tile, ref_id = np_(bins.tile_ids), gid[np_(bins.ranks)]
     flipped = np.zeros(n, bool)
     flipped[idx[rect_bad]] = True
     flipped |= vis != vis_ref

@@ -40,6 +40,15 @@ def _gpu_frame(gs, sc, cam):
     return img, frame
 
 
+def _oracle_image64(sc, cam):
+    """The reference algorithm in fp64 (round-off arbiter for the threshold flips)."""
+    from oracle import gs_oracle as O
+    s64 = {k: v.double() for k, v in sc.items()}
+    with torch.no_grad():
+        return O.render_from_params(s64["pos"], s64["scale_raw"], s64["q_raw"], s64["opacity_raw"], s64["f_dc"], s64["f_rest"],
+                                    cam["c2w"].double(), cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"]).numpy()
+
+
 def _check_forward(rep, n_pixels_values):
     assert rep["survivors_differ"] == 0, rep
     assert rep["V_equal"] and rep["depth_bit_equal"], rep
@@ -50,9 +59,13 @@ def _check_forward(rep, n_pixels_values):
     assert rep["lists_equal"], rep
     if rep["rect_mismatches"] == 0:
         assert rep["I_equal"], rep
-    # threshold-flip pixels only (q <= 6.25, alpha >= 1/128, T > 5e-5 within a few ulp): at most 1 value in 50000
-    assert rep["n_gt_tol"] <= max(3, n_pixels_values // 50_000), rep
-    assert rep["max_abs"] <= 0.02, rep
+    # Image <= 1e-4 abs except threshold-flip pixels: q <= 6.25, alpha >= 1/128 (a jump of ~0.0078 T c) and T > 5e-5 flip
+    # for a pair within a few ulp of the threshold - also between the reference's OWN fp32 and fp64 runs, which is the
+    # yardstick: the GPU image must not differ from the fp32 reference in more values than 2x (+3) what the reference's
+    # fp64 run does (measured on the headline frame: 251 against 520 of 6.2 M values, profiles/PARITY_r02.json).
+    assert rep["n_gt_tol"] <= 2 * rep["ref32_vs_ref64_n_gt_tol"] + 3, rep
+    assert rep["max_abs"] <= max(0.02, 2 * rep["ref32_vs_ref64_max_abs"]), rep
+    assert rep["mean_abs"] <= 1e-6, rep
 
 
 def test_c2_100k_1080p_forward_backward_against_the_oracle(gs, parity_log):
@@ -70,11 +83,12 @@ def test_c2_100k_1080p_forward_backward_against_the_oracle(gs, parity_log):
     img_ref, proj, bins = O.render(ref["pos"], col, ref["opacity_raw"], sig, cam["c2w"], H, W, cam["fx"], cam["fy"],
                                    cam["cx"], cam["cy"], return_stages=True)
     (img_ref * w).sum().backward()
+    img64 = _oracle_image64(sc, cam)
     # GPU: integer stages through the introspection export, then the public API with autograd
     img0, frame = _gpu_frame(gs, sc, cam)
     ex = {k: v.numpy() for k, v in frame.export().items()}
     rep = PAR.compare_frame(ex, frame.n_isect, frame.n_visible, img0.cpu().numpy(), proj, bins, img_ref.detach().numpy(),
-                            tol=IMG_TOL)
+                            tol=IMG_TOL, image_ref64=img64)
     mine = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
     c2w = cam["c2w"].cuda()
     sigma = gs.build_sigma_from_params(mine["scale_raw"], mine["q_raw"])
@@ -104,7 +118,8 @@ def test_c3_1m_1297x840_forward_against_the_oracle(gs, parity_log):
                                        cam["c2w"], H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"], return_stages=True)
     img, frame = _gpu_frame(gs, sc, cam)
     ex = {k: v.numpy() for k, v in frame.export().items()}
-    rep = PAR.compare_frame(ex, frame.n_isect, frame.n_visible, img.cpu().numpy(), proj, bins, img_ref.numpy(), tol=IMG_TOL)
+    rep = PAR.compare_frame(ex, frame.n_isect, frame.n_visible, img.cpu().numpy(), proj, bins, img_ref.numpy(), tol=IMG_TOL,
+                            image_ref64=_oracle_image64(sc, cam))
     parity_log["C3_1M_1297x840_fwd"] = rep
     _check_forward(rep, H * W * 3)
 
@@ -149,7 +164,7 @@ def test_tile_row_bands_cull_compact_and_add_up_to_the_full_frame(gs, parity_log
                 img, fr = render(fused, (b, e))
                 assert fr.n_isect == int(per_row[b:e].sum())          # the band bins exactly its rows
                 assert fr.n_visible == fr_full.n_visible               # visibility is a property of the frame
-                assert float(img[:b * 16].abs().max(initial=0)) == 0.0 and float(img[min(e * 16, H):].abs().max(initial=0)) == 0.0
+                assert float(img[:b * 16].abs().sum()) == 0.0 and float(img[min(e * 16, H):].abs().sum()) == 0.0
                 acc += img
                 n_isect += fr.n_isect
                 render(fused, (b, e), keep=True, out=shared)

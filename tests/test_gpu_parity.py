@@ -19,7 +19,7 @@ IMG_TOL = 1e-4
 GRAD_TOL = 1e-3
 # radius / tile-rect flips allowed per golden case (measured on a B200: see profiles/PARITY_r02.json); cases not
 # listed fall back to 1 in 2000 survivors
-RADIUS_FLIP_LIMIT = {}
+RADIUS_FLIP_LIMIT = {"c1_10k_sh0_256": 0, "sh3_4k_200x136_rot": 0, "edge_1500_97x71": 0, "dense_600_48x40": 0}
 
 
 @pytest.fixture(scope="module")

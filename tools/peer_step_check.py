@@ -35,7 +35,7 @@ def main():
     opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15)
     opt = b200gs.PeerAdam([{"params": [mine[k]], "lr": LRS[k]} for k in SHAPES], lr=1e-3, eps=1e-15,
                           clip_params=[mine["pos"]], max_norm=1.0, multicast=multicast)
-    report = []
+    report, worst = [], {}
     for step in range(1, steps + 1):
         total = {k: None for k in SHAPES}
         for r in range(world):                      # every rank can rebuild every rank's gradient
@@ -57,6 +57,8 @@ def main():
         row = {"step": step}
         for k in SHAPES:
             a, b = mine[k].detach().flatten(), ref[k].detach().flatten()
+            err = float((a - b).abs().max() / b.abs().max())
+            worst[k] = max(worst.get(k, 0.0), err)                      # max-norm relative error over all steps
             bad = ((a - b).abs() > 2e-6 * b.abs().max()).nonzero().flatten()
             if bad.numel():
                 per = peer.slice_bounds(a.numel(), world, 0)[1]
@@ -64,16 +66,23 @@ def main():
                 row[k] = {"bad": int(bad.numel()), "owners": owners, "first": int(bad[0]), "last": int(bad[-1]),
                           "max_abs": float((a - b).abs().max())}
         report.append(row)
-    out = [None] * world
+    # replicas: every rank must hold bit-identical parameters after the last step
+    digest = torch.stack([mine[k].detach().double().sum() for k in SHAPES] +
+                         [mine[k].detach().view(torch.int32).long().sum().double() for k in SHAPES])
+    out, worsts, digests = [None] * world, [None] * world, [None] * world
     if world > 1:
         dist.all_gather_object(out, report)
+        dist.all_gather_object(worsts, worst)
+        dist.all_gather_object(digests, digest.cpu().tolist())
     else:
-        out = [report]
+        out, worsts, digests = [report], [worst], [digest.cpu().tolist()]
     if rank == 0:
         bad = [[row for row in rep if len(row) > 1] for rep in out]
         print(json.dumps({"n": n, "world": world, "steps": steps, "multicast": bool(opt.area.c_group.multicast),
-                          "mc_mode": os.environ.get("B200GS_PEER_MC_MODE"), "steps_with_mismatch": [len(b) for b in bad],
-                          "first": [b[:2] for b in bad]}))
+                          "steps_with_mismatch_per_rank": [len(b) for b in bad],
+                          "max_rel_err_vs_local_torch_adam_replay": {k: max(w[k] for w in worsts) for k in SHAPES},
+                          "tolerance": 2e-6, "replicas_bit_identical": all(d == digests[0] for d in digests),
+                          "first_mismatches": [b[:2] for b in bad]}))
     if world > 1:
         dist.destroy_process_group()
 
