@@ -175,6 +175,46 @@ def _install_trace():
     atexit.register(report)
 
 
+def _install_timeline():
+    """B200GS_RUN_TRACE=2: start/end timestamps of four calls per training iteration (backward, clip_grad_norm_,
+    optimizer.step, empty_cache) - the lightest instrumentation that still tells WHEN the host waits.  Printed at exit
+    as per-iteration totals in windows of 10 iterations."""
+    import atexit
+    import time
+    import torch
+    ev = []          # (label, t0, t1)
+
+    def wrap(owner, name, label):
+        fn = getattr(owner, name)
+
+        def timed(*a, **kw):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **kw)
+            finally:
+                ev.append((label, t0, time.perf_counter()))
+        setattr(owner, name, timed)
+    wrap(torch.Tensor, "backward", "backward")
+    wrap(torch.nn.utils, "clip_grad_norm_", "clip")
+    wrap(torch.optim.Adam, "step", "step")
+    wrap(torch.cuda, "empty_cache", "empty_cache")
+
+    def report():
+        steps = [e for e in ev if e[0] == "step"]
+        print(f"[b200gs.run timeline] {len(steps)} iterations", file=sys.stderr)
+        for w in range(0, len(steps), 10):
+            lo = steps[w][1]
+            hi = steps[min(w + 10, len(steps)) - 1][2]
+            n = min(w + 10, len(steps)) - w
+            inside = {}
+            for label, t0, t1 in ev:
+                if lo <= t0 <= hi:
+                    inside[label] = inside.get(label, 0.0) + (t1 - t0)
+            print(f"[b200gs.run timeline] it {w:4d}-{w + n - 1:4d}: {(hi - lo) / n * 1e3:8.3f} ms/it  " +
+                  "  ".join(f"{k} {v / n * 1e3:7.3f}" for k, v in sorted(inside.items())), file=sys.stderr)
+    atexit.register(report)
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     dp = bool(argv) and argv[0] == "--dp"
@@ -194,6 +234,8 @@ def main(argv=None):
         _, world = _setup_dp()
     if os.environ.get("B200GS_RUN_TRACE") == "1":
         _install_trace()
+    elif os.environ.get("B200GS_RUN_TRACE") == "2":
+        _install_timeline()
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
                                                                     const uint2* __restrict__ rect,
                                                                     uint32_t capacity,
                                                                     const b200gs_frame_stats* __restrict__ stats,
-                                                                    int super_x, int tiles_x, int tiles_y,
+                                                                    int super_x, int super_y0, int tiles_x, int tiles_y,
                                                                     uint32_t* __restrict__ tile_count,
                                                                     uint32_t* __restrict__ part_total,
                                                                     uint2* __restrict__ ranges,
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
   __shared__ uint32_t s_base[kSuperTiles];              // start of each tile's list in `lists`
   __shared__ uint32_t s_red[kSplitWarps];
   __shared__ uint32_t s_seg[2];
-  const int s = blockIdx.x / kSplitParts, part = blockIdx.x % kSplitParts, sx = s % super_x, sy = s / super_x;
+  // s = band-local supertile id (the sort key); (sx, sy) = its position in the frame
+  const int s = blockIdx.x / kSplitParts, part = blockIdx.x % kSplitParts, sx = s % super_x, sy = super_y0 + s / super_x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t count = stats->n_super;
   if (count > capacity || stats->overflow) count = 0;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
 }
 
 cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t* vals, const uint2* rect,
-                               uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y,
+                               uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y0, int super_y,
                                int tiles_x, int tiles_y, uint32_t* tile_count, uint2* ranges, uint32_t* lists,
                                cudaStream_t s) {
   const int grid = super_x * super_y * kSplitParts;
@@ -244,7 +245,7 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
   uint32_t* part_total = tile_count + (size_t)grid * kSuperTiles;     // one word per CTA, behind the per-tile counts
   // measured on the headline frame (count + write): 256 threads 64.9 us, 128 threads 81.7 us
   static const int threads = getenv("B200GS_SPLIT_THREADS") ? atoi(getenv("B200GS_SPLIT_THREADS")) : 256;
-#define GS_SPLIT_ARGS keys, vals, rect, capacity, stats, super_x, tiles_x, tiles_y, tile_count, part_total, ranges, lists
+#define GS_SPLIT_ARGS keys, vals, rect, capacity, stats, super_x, super_y0, tiles_x, tiles_y, tile_count, part_total, ranges, lists
   if (threads == 256) {
     if (write) split_super_kernel<true, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);
     else split_super_kernel<false, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);

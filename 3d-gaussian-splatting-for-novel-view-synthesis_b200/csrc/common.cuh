@@ -161,8 +161,8 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
                               size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready = false);
 // n_dev (optional): device-side count of live entries at the front of `order` (band frames compact their keys)
 cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t* order, const uint32_t* super_touched,
-                                   const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
-                                   b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
+                                   const uint2* rect, int super_x, int super_y0, uint32_t capacity, uint32_t* keys,
+                                   uint32_t* vals, b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
                                    size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
                                    cudaStream_t s);
 // (key, id) of every key != kCulledKey in index order -> out_keys / out_ids, their number -> *count_out (device)
@@ -173,8 +173,9 @@ cudaError_t launch_compact_keys(const uint32_t* keys, uint32_t n, uint32_t* out_
 cudaError_t launch_emit_super(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* super_touched,
                               const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
                               b200gs_frame_stats* stats, cudaStream_t s);
+// supertile rows [super_y0, super_y0 + super_y) (a band only bins, sorts and splits its own rows; ids are band-local)
 cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t* vals, const uint2* rect,
-                               uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y,
+                               uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y0, int super_y,
                                int tiles_x, int tiles_y, uint32_t* tile_count, uint2* ranges, uint32_t* lists,
                                cudaStream_t s);
 cudaError_t launch_fill_list_tiles(const uint2* ranges, int n_tiles, uint32_t count, int32_t* list_tile,

@@ -251,6 +251,40 @@ __device__ __forceinline__ void sh_color_global(const float* __restrict__ dc, co
   }
 }
 
+// Tile-row bands: a conservative "cannot touch rows [row_begin, row_end)" test that needs neither the covariance nor
+// the eigenvalues.  Sigma_2D = M Sigma M^T with M = J Rwc, so lambda_max(Sigma_2D) <= |J|_F^2 max_i s_i^2, hence
+//   radius = ceil(2.5 sqrt(clamp(lambda_max))) <= 2.5 sqrt(min(max(B, 1e-6), 1e4)) + 2,
+//   B = 1.002 max_i s_i^2 ((fx^2 + fy^2)/z^2 + (fx^2 x^2 + fy^2 y^2)/z^4)
+// (the 0.2 % and the +2 cover ceil() and every rounding in between).  A Gaussian whose centre row v is further than
+// that from the band cannot have a tile there (project_gaussian S9-S11); one that fails the opacity pre-cull or the
+// frustum test is dropped as it would be anyway.  ~40 instructions instead of the whole projection for the 7/8 of
+// the scene that an eighth of the frame does not see.
+__device__ __forceinline__ bool band_cannot_touch(const float p[3], const float sr[3], float opacity_raw, const Pose& ps,
+                                                  const RenderParams& rp) {
+  const float op = fminf(fmaxf(sigmoidf_(opacity_raw), 0.f), 0.999f);
+  if (!(op >= rp.alpha_pre)) return true;
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float acc = ps.r[3 * i] * p[0];
+    acc = fmaf(ps.r[3 * i + 1], p[1], acc);
+    acc = fmaf(ps.r[3 * i + 2], p[2], acc);
+    c[i] = acc + ps.t[i];
+  }
+  const float x = c[0], y = c[1], z = c[2];
+  const float fxx = rp.fx * x, fyy = rp.fy * y;
+  const bool vis = (z > 0.f) && (z > rp.near_plane) && (z < rp.far_plane) &&
+                   (fxx > z * rp.ulo) && (fxx < z * rp.uhi) && (fyy > z * rp.vlo) && (fyy < z * rp.vhi);
+  if (!vis) return true;
+  const float v = fyy / z + rp.cy;
+  const float smax = fmaxf(__expf(fmaxf(sr[0], fmaxf(sr[1], sr[2]))), 1e-6f);
+  const float invz = 1.0f / fmaxf(z, 1e-6f), invz2 = invz * invz;
+  const float jf2 = (rp.fx * rp.fx + rp.fy * rp.fy) * invz2 + (fxx * fxx + fyy * fyy) * invz2 * invz2;
+  const float B = 1.002f * smax * smax * jf2;
+  const float rb = 2.5f * sqrtf(fminf(fmaxf(B, 1e-6f), 1e4f)) + 2.f;      // NaN / inf -> comparisons false -> kept
+  return (v + rb < (float)(rp.row_begin * kTile)) || (v - rb >= (float)(rp.row_end * kTile));
+}
+
 template <bool BAND>
 __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
                                                                        RenderParams rp, FrameView f, int n_chunks,
@@ -262,6 +296,8 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
   __shared__ uint32_t s_dh[4][256];      // digit histograms of the depth keys (the depth sort's 4 passes)
+  __shared__ uint32_t s_cand_cnt[kPreBlock / 32];
+  __shared__ uint16_t s_cand[kPreBlock];  // BAND: stage rows of the Gaussians that may touch the band
   const int tid = threadIdx.x;
   if (tid < 16) s_c2w[tid] = c2w[tid];
   for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
@@ -310,11 +346,42 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       stage_rows<1>(g.opacity_raw, st.opac, n0, count);
       __syncthreads();
     }
-    if (tid < count) {
-      const int i = n0 + tid;
-      const float p[3] = {st.pos[3 * tid], st.pos[3 * tid + 1], st.pos[3 * tid + 2]};
-      const float sr[3] = {st.scale[3 * tid], st.scale[3 * tid + 1], st.scale[3 * tid + 2]};
-      const float4 q4 = reinterpret_cast<const float4*>(st.quat)[tid];
+    // BAND: every thread runs the cheap test on its Gaussian; the candidates that remain (about one in eight, in random
+    // positions) are compacted to the front of the CTA so that whole warps skip the expensive path - with the
+    // candidates left where they are every warp would still execute it for its four or so live lanes.
+    bool live = tid < count;
+    int j = tid;                                   // row of the stage this thread projects
+    if constexpr (BAND) {
+      bool cand = false;
+      if (live) {
+        const float p[3] = {st.pos[3 * tid], st.pos[3 * tid + 1], st.pos[3 * tid + 2]};
+        const float sr[3] = {st.scale[3 * tid], st.scale[3 * tid + 1], st.scale[3 * tid + 2]};
+        cand = !band_cannot_touch(p, sr, st.opac[tid], ps, rp);
+        if (!cand) {                               // (the frame counters of a band describe the band)
+          f.depth_key[n0 + tid] = kCulledKey;
+          f.super_touched[n0 + tid] = 0;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if ((tid & 31) == 0) s_cand_cnt[tid >> 5] = (uint32_t)__popc(m);
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kPreBlock / 32; ++w) {
+        const uint32_t c = s_cand_cnt[w];
+        if (w < (tid >> 5)) before += c;
+        total += c;
+      }
+      if (cand) s_cand[before + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
+      __syncthreads();
+      live = (uint32_t)tid < total;
+      if (live) j = s_cand[tid];
+    }
+    if (live) {
+      const int i = n0 + j;
+      const float p[3] = {st.pos[3 * j], st.pos[3 * j + 1], st.pos[3 * j + 2]};
+      const float sr[3] = {st.scale[3 * j], st.scale[3 * j + 1], st.scale[3 * j + 2]};
+      const float4 q4 = reinterpret_cast<const float4*>(st.quat)[j];
       const float q[4] = {q4.x, q4.y, q4.z, q4.w};
       QuatScale qs;
       quat_scale_forward(sr, q, qs);
@@ -322,7 +389,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       sigma_full(qs, full);
       const Cov3 S = sym_from_full(full);
       Projection o;
-      const bool vis = project_gaussian(p, S, st.opac[tid], ps, rp, o);
+      const bool vis = project_gaussian(p, S, st.opac[j], ps, rp, o);
       s7_count += (vis || o.offscreen) ? 1u : 0u;
       vis_count += vis ? 1u : 0u;
       // a survivor whose tile rect misses this rank's band [row_begin, row_end) is dropped from the frame
@@ -349,7 +416,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
           sh_color_global(g.f_dc + (size_t)i * 3, g.f_rest + (size_t)i * 45, Y, rgb);
         } else {
           float acc[3];
-          sh_color(&st.dc[3 * tid], &st.rest[45 * tid], Y, rgb, acc);
+          sh_color(&st.dc[3 * j], &st.rest[45 * j], Y, rgb, acc);
         }
         float eu, ev;
         conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);

@@ -326,6 +326,10 @@ __global__ void __launch_bounds__(kSortBlock, ONESWEEP_MIN_BLOCKS) onesweep_pass
   __shared__ uint32_t s_vbid;
 
   const uint32_t n = eff_count(n_host, n_dev);
+  // The grid is sized for the host's upper bound; with the count on the device (band frames, supertile pairs) most CTAs
+  // may have nothing to do.  Exactly ceil(n / tile) CTAs must work and ANY may (virtual ids come from the ticket), so
+  // the surplus leaves before taking a ticket or clearing shared memory.
+  if ((uint32_t)blockIdx.x * (uint32_t)kSortTile >= n) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_lb = warp == kSortWarps;
   if (tid == 0) s_vbid = atomicAdd(ticket, 1u);
@@ -519,20 +523,20 @@ constexpr int kSeTile = kSeThreads * kSeItems;   // 1024 depth ranks per block
 __global__ void __launch_bounds__(kSeThreads) scan_emit_super_kernel(
     int n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ order,
     const uint32_t* __restrict__ super_touched,
-    const uint2* __restrict__ rect, int super_x, uint32_t capacity, uint32_t* __restrict__ keys,
+    const uint2* __restrict__ rect, int super_x, int super_y0, uint32_t capacity, uint32_t* __restrict__ keys,
     uint32_t* __restrict__ vals, b200gs_frame_stats* __restrict__ stats, uint32_t* ticket,
     unsigned long long* status, SortPasses sp, uint32_t* __restrict__ ghist) {
   __shared__ uint32_t s_hist[kMaxPasses][kRadix];
   __shared__ uint32_t s_warp[kSeThreads / 32];
   __shared__ uint32_t s_tile, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = (int)eff_count((uint32_t)n_host, n_dev);   // band frames: only the compacted prefix of `order` is live
+  if (blockIdx.x == 0 && tid == 0 && stats->n_isect > capacity) stats->overflow = 1u;   // per-tile lists would not fit
+  if ((uint32_t)blockIdx.x * (uint32_t)kSeTile >= (uint32_t)n) return;   // surplus CTAs leave before taking a ticket
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = tid; i < kMaxPasses * kRadix; i += kSeThreads) (&s_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
-  if (tile == 0 && tid == 0 && stats->n_isect > capacity) stats->overflow = 1u;   // per-tile lists would not fit
-  const int n = (int)eff_count((uint32_t)n_host, n_dev);   // band frames: only the compacted prefix of `order` is live
-  if (tile * (uint32_t)kSeTile >= (uint32_t)n) return;      // uniform; no earlier tile ever waits on a later one
   const uint32_t r0 = tile * kSeTile + tid * kSeItems;
   uint32_t id[kSeItems], cnt[kSeItems], excl[kSeItems];
   uint32_t sum = 0;
@@ -581,7 +585,7 @@ __global__ void __launch_bounds__(kSeThreads) scan_emit_super_kernel(
     const int sy0 = (rc.y & 0xFFFF) / kSuperY, sy1 = (rc.y >> 16) / kSuperY;
     for (int sy = sy0; sy <= sy1; ++sy)
       for (int sx = sx0; sx <= sx1; ++sx) {
-        const uint32_t key = (uint32_t)(sy * super_x + sx);
+        const uint32_t key = (uint32_t)((sy - super_y0) * super_x + sx);    // supertile id, local to the band
         keys[off] = key;
         vals[off] = id[k];
         ++off;
@@ -602,8 +606,8 @@ size_t scan_emit_scratch_bytes(uint32_t n) { return 256 + ((size_t)(n + kSeTile 
 // Zeroes `sort_scratch` (tickets, histograms, look-back status of the sort that follows) and `se_scratch`,
 // runs the fused kernel; the sort must then be launched with hist_ready = true on the same scratch.
 cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t* order, const uint32_t* super_touched,
-                                   const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,
-                                   b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
+                                   const uint2* rect, int super_x, int super_y0, uint32_t capacity, uint32_t* keys,
+                                   uint32_t* vals, b200gs_frame_stats* stats, int sort_bits, void* sort_scratch,
                                    size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
                                    cudaStream_t s) {
   if (sort_scratch_bytes_ < sort_scratch_bytes(capacity) || se_scratch_bytes < scan_emit_scratch_bytes((uint32_t)(n > 0 ? n : 1)))
@@ -618,8 +622,8 @@ cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t*
   unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(se_scratch) + 256);
   const SortPasses sp = make_passes(0, sort_bits);
   scan_emit_super_kernel<<<(n + kSeTile - 1) / kSeTile, kSeThreads, 0, s>>>(n, n_dev, order, super_touched, rect, super_x,
-                                                                          capacity, keys, vals, stats, ticket, status,
-                                                                          sp, ghist);
+                                                                          super_y0, capacity, keys, vals, stats, ticket,
+                                                                          status, sp, ghist);
   return cudaGetLastError();
 }
 

@@ -98,7 +98,8 @@ typedef struct b200gs_sizes {
 /* Counters the device leaves in the first 64 bytes of the frame workspace. */
 typedef struct b200gs_frame_stats {
   uint32_t n_isect;    /* I: total (tile, Gaussian) intersections */
-  uint32_t n_visible;  /* V: Gaussians that survive every cull */
+  uint32_t n_visible;  /* V: Gaussians that survive every cull (a band frame may drop Gaussians that cannot touch its
+                          rows before the culls: its V, n_in_frustum and I describe the band, not the frame) */
   uint32_t overflow;   /* 1 if I exceeded isect_capacity in rasterize */
   uint32_t n_in_frustum; /* survivors of S1-S7 (before the on-screen test; render.py:235 raises when
                             this is > 0 but n_visible == 0) */

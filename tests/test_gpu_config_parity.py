@@ -163,7 +163,7 @@ def test_tile_row_bands_cull_compact_and_add_up_to_the_full_frame(gs, parity_log
             for b, e in zip(cuts[:-1], cuts[1:]):
                 img, fr = render(fused, (b, e))
                 assert fr.n_isect == int(per_row[b:e].sum())          # the band bins exactly its rows
-                assert fr.n_visible == fr_full.n_visible               # visibility is a property of the frame
+                assert fr.n_visible <= fr_full.n_visible               # a band's counters describe the band
                 assert float(img[:b * 16].abs().sum()) == 0.0 and float(img[min(e * 16, H):].abs().sum()) == 0.0
                 acc += img
                 n_isect += fr.n_isect

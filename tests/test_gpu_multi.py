@@ -90,8 +90,8 @@ def _worker(rank, world, port, out):
         leaves2 = {k: sc[k].to(dev).requires_grad_(True) for k in PARAMS}
         bucket = GradBucket([leaves2[k] for k in PARAMS])
         _loss_for_views(b200gs, leaves2, cams, shard_views(n_views, rank, world), W, H, dev, n_views).backward()
-        assert leaves2["f_rest"].grad.data_ptr() == bucket.views[PARAMS.index("f_rest")].data_ptr()   # written in place
-        bucket.allreduce()
+        bucket.allreduce()       # (several views per backward: whichever gradient arrives first is adopted, the rest is copied)
+        assert leaves2["f_rest"].grad.data_ptr() == bucket.views[PARAMS.index("f_rest")].data_ptr()
         out[f"bgrads{rank}"] = {k: leaves2[k].grad.cpu() for k in PARAMS}
     finally:
         dist.destroy_process_group()

@@ -586,3 +586,34 @@ def test_mismatched_row_counts_raise_instead_of_reading_out_of_bounds(gs):
     color = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
     with pytest.raises(ValueError):
         gs.render(sc["pos"][:50], color, sc["opacity_raw"][:50], sigma, c2w, 32, 32, 28., 28., 16., 16.)
+
+
+def test_grad_bucket_backward_writes_into_the_flat_buffer(gs):
+    """b200gs.dist.GradBucket on one GPU: with one view per backward the render backward writes each leaf's gradient
+    straight into its slot of the flat buffer (autograd adopts the view as .grad, no copy), the values are those of a
+    plain backward, and the slots are handed out again after allreduce() / zero_grad()."""
+    from b200gs.dist import GradBucket
+    from oracle import gs_oracle as O
+    sc = O.make_scene(3000, seed=4, log_scale=-3.0)
+    cam = O.make_camera(160, 112, view=1, n_views=6)
+    c2w = cam["c2w"].cuda()
+    w = torch.rand(112, 160, 3, generator=torch.Generator().manual_seed(0)).cuda()
+
+    def backward(lv):
+        sigma = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+        color = gs.evaluate_sh(lv["f_dc"], lv["f_rest"], lv["pos"], c2w)
+        img = gs.render(lv["pos"], color, lv["opacity_raw"], sigma, c2w, 112, 160, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        (img * w).sum().backward()
+    plain = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    backward(plain)
+    lv = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    bucket = GradBucket([lv[k] for k in PARAMS])
+    for rep in range(2):
+        bucket.zero_grad()
+        backward(lv)
+        for i, k in enumerate(PARAMS):
+            assert lv[k].grad.data_ptr() == bucket.views[i].data_ptr(), (rep, k)
+        bucket.allreduce()
+        for k in PARAMS:
+            scale = float(plain[k].grad.abs().max())
+            assert float((lv[k].grad - plain[k].grad).abs().max()) <= 2e-5 * scale, k

@@ -1,4 +1,5 @@
-"""Per-kernel times of one tile-row band of the C5 frame (6M Gaussians, 3840x2160, 8 bands) vs the whole frame."""
+"""Per-kernel times of one tile-row band of the C5 frame (6M Gaussians, 3840x2160; a central and an edge band of 8, the
+first band of 2) vs the whole frame, all on one GPU."""
 import ctypes
 import os
 import sys
@@ -33,7 +34,8 @@ with torch.no_grad():
         col = b200gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
         return b200gs.render(sc["pos"], col, sc["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
                              tile_rows=rows)
-    for rows in (None, bands[3]):
+    bands2 = shard_tile_rows((H + 15) // 16, 2)
+    for rows in (None, bands[3], bands[0], bands2[0]):
         for _ in range(3):
             frame(rows)
         torch.cuda.synchronize()
