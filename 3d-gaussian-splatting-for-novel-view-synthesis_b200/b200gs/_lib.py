@@ -68,7 +68,7 @@ class PeerTensor(Structure):
 
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
-                ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("n_sorted", c_uint32), ("reserved", c_uint32 * 10)]
+                ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("n_sorted", c_uint32), ("n_candidates", c_uint32), ("reserved", c_uint32 * 9)]
 
 
 # every symbol include/b200gs.h declares: name -> (restype, argtypes)

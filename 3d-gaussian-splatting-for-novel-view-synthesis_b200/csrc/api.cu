@@ -30,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -454,24 +454,45 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   if (gi.n > 0) {
     bool hist_done = false;
     CU(gs::radix_sort_prepare(gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, (uint32_t)gi.n, s));
-    PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s,
-                                                       gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch)), &hist_done));
-    // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
-    int in_a = 0;
+    uint32_t* hist = gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch));
     uint32_t* keys_a = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2);
     uint32_t* order = gs::ws_ptr<uint32_t>(frame_ws, L.order);
+    uint32_t* keys_b = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt);
+    uint32_t* order_b = gs::ws_ptr<uint32_t>(frame_ws, L.order_alt);
+    char* band_scratch = gs::ws_ptr<char>(frame_ws, L.band_scratch);
+    bool band_route = false;
+    if (is_band(rp)) {
+      // a band of tile rows, raw parameters: select the candidates with a cheap test, project only those (the
+      // candidate ids / keys sit in the sort's ping-pong buffers, which pass 0 only overwrites after the compaction)
+      // (flag words in `offsets`, unused by the fused binning; candidate ids / keys in the sort's ping-pong buffers)
+      PCU(R_BAND_SELECT, 2, gs::launch_band_select(gi, cam->c2w, rp, frame_ws, L, gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
+                                                   order_b, &stats->n_candidates, band_scratch, L.band_scratch_half,
+                                                   &band_route, s));
+      if (band_route)
+        PCU(R_PREPROCESS_FWD, 1, gs::launch_band_project(gi, cam->c2w, rp, frame_ws, L, order_b, &stats->n_candidates, keys_b,
+                                                         hist, s));
+      hist_done = band_route;
+    }
+    if (!band_route)
+      PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s, hist, &hist_done));
+    // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
+    int in_a = 0;
     if (is_band(rp)) {
       // a band keeps a fraction of the Gaussians: compact the live keys (stable) and sort those only
-      PCU(R_COMPACT, 1, gs::launch_compact_keys(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), (uint32_t)gi.n, keys_a, order,
-                                                &stats->n_sorted, gs::ws_ptr<void>(frame_ws, L.offsets), (size_t)gi.n * 4, s));
-      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(keys_a, order, keys_a, order,
-                               gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
+      if (band_route)
+        PCU(R_COMPACT, 1, gs::launch_compact_keys(keys_b, order_b, (uint32_t)gi.n, &stats->n_candidates, keys_a, order,
+                                                  &stats->n_sorted, band_scratch + L.band_scratch_half,
+                                                  L.band_scratch_half, s));
+      else
+        PCU(R_COMPACT, 1, gs::launch_compact_keys(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr, (uint32_t)gi.n,
+                                                  nullptr, keys_a, order, &stats->n_sorted,
+                                                  band_scratch + L.band_scratch_half, L.band_scratch_half, s));
+      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(keys_a, order, keys_a, order, keys_b, order_b,
                                (uint32_t)gi.n, &stats->n_sorted, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch),
                                L.scratch_bytes, &in_a, s, hist_done));
     } else {
       PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
-                               keys_a, order,
-                               gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt), gs::ws_ptr<uint32_t>(frame_ws, L.order_alt),
+                               keys_a, order, keys_b, order_b,
                                (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
                                &in_a, s, hist_done));
     }

@@ -48,6 +48,8 @@ struct FrameLayout {
   size_t tile_count;      // u32[supertiles*4*32] entries per tile and list quarter, supertile-major; + u32[supertiles*4] totals
   size_t final_T;         // float[P]
   size_t n_contrib;       // u32[P]  (#list entries consumed) | channel-overflow bits 29..31
+  size_t band_scratch;    // look-back state of the band kernels: [0, half) band_select, [half, 2 half) compact_keys
+  size_t band_scratch_half;
   size_t scratch;         // scan + sort scratch (sized for max(n, isect) users at call time)
   size_t scratch_bytes;
   size_t total;
@@ -95,6 +97,8 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.tile_count = take((size_t)ceil_div(ceil_div(W, kTile), kSuperX) * ceil_div(ceil_div(H, kTile), kSuperY) * (32 + 1) * 4 * 4);
   L.final_T = take(P * 4);
   L.n_contrib = take(P * 4);
+  L.band_scratch_half = align_up(512 + (N / 1024 + 2) * 8, 256);
+  L.band_scratch = take(2 * L.band_scratch_half);
   size_t a = scan_scratch_bytes((uint32_t)N);
   const size_t b = sort_scratch_bytes((uint32_t)N), c = scan_emit_scratch_bytes((uint32_t)N);
   if (c > a) a = c;
@@ -166,9 +170,20 @@ cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t*
                                    size_t sort_scratch_bytes_, void* se_scratch, size_t se_scratch_bytes,
                                    cudaStream_t s);
 // (key, id) of every key != kCulledKey in index order -> out_keys / out_ids, their number -> *count_out (device)
+// (n_dev: optional device-side count of the valid keys, n then being the host's upper bound; ids_in: optional ids to
+// carry instead of the key's position)
 size_t compact_scratch_bytes(uint32_t n);
-cudaError_t launch_compact_keys(const uint32_t* keys, uint32_t n, uint32_t* out_keys, uint32_t* out_ids,
-                                uint32_t* count_out, void* scratch, size_t scratch_bytes, cudaStream_t s);
+cudaError_t launch_compact_keys(const uint32_t* keys, const uint32_t* ids_in, uint32_t n, const uint32_t* n_dev,
+                                uint32_t* out_keys, uint32_t* out_ids, uint32_t* count_out, void* scratch,
+                                size_t scratch_bytes, cudaStream_t s);
+size_t band_select_scratch_bytes(int n);
+// flag_words: u32[ceil(n / 128) * 4] (one bit per Gaussian)
+cudaError_t launch_band_select(const GaussIn& g, const float* c2w, const RenderParams& rp, void* frame_ws,
+                               const FrameLayout& L, uint32_t* flag_words, uint32_t* cand_ids, uint32_t* n_cand,
+                               void* select_scratch, size_t select_scratch_bytes, bool* used, cudaStream_t s);
+cudaError_t launch_band_project(const GaussIn& g, const float* c2w, const RenderParams& rp, void* frame_ws,
+                                const FrameLayout& L, const uint32_t* cand_ids, const uint32_t* n_cand, uint32_t* cand_key,
+                                uint32_t* depth_hist, cudaStream_t s);
 
 cudaError_t launch_emit_super(int n, const uint32_t* order, const uint32_t* offsets, const uint32_t* super_touched,
                               const uint2* rect, int super_x, uint32_t capacity, uint32_t* keys, uint32_t* vals,

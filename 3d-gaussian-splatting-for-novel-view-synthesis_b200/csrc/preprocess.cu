@@ -227,30 +227,6 @@ struct __align__(128) PreStage {
 };
 constexpr uint32_t kPreStageBytes = kPreBlock * (45 + 4 + 3 + 3 + 3 + 1) * 4;
 
-// Tile-row bands (a large frame sharded over GPUs): most Gaussians miss the band, so only the 44 B the projection
-// needs go through the copy pipeline; the 192 B of SH coefficients are fetched - straight from global memory, one
-// row per thread - for the band's survivors only.
-struct __align__(128) PreStageBand {
-  float quat[kPreBlock * 4];
-  float pos[kPreBlock * 3];
-  float scale[kPreBlock * 3];
-  float opac[kPreBlock];
-};
-constexpr uint32_t kPreStageBandBytes = kPreBlock * (4 + 3 + 3 + 1) * 4;
-template <bool BAND> struct PreStageOf { using type = PreStage; };
-template <> struct PreStageOf<true> { using type = PreStageBand; };
-
-__device__ __forceinline__ void sh_color_global(const float* __restrict__ dc, const float* __restrict__ rest,
-                                                const float Y[16], float rgb[3]) {
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float acc = __ldg(dc + c) * Y[0];
-#pragma unroll
-    for (int k = 1; k < 16; ++k) acc = fmaf(__ldg(rest + 15 * c + k - 1), Y[k], acc);
-    rgb[c] = sigmoidf_(acc);
-  }
-}
-
 // Tile-row bands: a conservative "cannot touch rows [row_begin, row_end)" test that needs neither the covariance nor
 // the eigenvalues.  Sigma_2D = M Sigma M^T with M = J Rwc, so lambda_max(Sigma_2D) <= |J|_F^2 max_i s_i^2, hence
 //   radius = ceil(2.5 sqrt(clamp(lambda_max))) <= 2.5 sqrt(min(max(B, 1e-6), 1e4)) + 2,
@@ -285,19 +261,303 @@ __device__ __forceinline__ bool band_cannot_touch(const float p[3], const float 
   return (v + rb < (float)(rp.row_begin * kTile)) || (v - rb >= (float)(rp.row_end * kTile));
 }
 
-template <bool BAND>
+// ------------------------------------------------------------------------------------------------
+// Tile-row bands, raw-parameter route: two kernels instead of the fused one.
+//   band_select_kernel   every Gaussian: 28 B in (pos, scale_raw, opacity_raw), the cheap test above, the ids of the
+//                        candidates written in index order (block scan + decoupled look-back), depth_key = culled
+//   band_project_kernel  one thread per CANDIDATE (dense, no divergence): gathers its Gaussian's rows by id, full
+//                        projection, SH evaluation for the band's survivors, splat records; a depth key (or the culled
+//                        marker) per candidate, which compact_keys_kernel then compacts together with the ids.
+// A band of 1/8 of a 4K frame keeps ~1/8 of the scene: the fused kernel spent 280-330 us there whatever the band (one
+// thread per Gaussian: every warp still ran the whole projection for its few live lanes; compacting inside the CTA
+// serialised it into one warp per chunk), these two take the time of their bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 4;
+constexpr int kSelTile = kSelThreads * kSelItems;      // 1024 Gaussians per block
+
+// look-back state of band_expand_kernel (one status word per 32768 Gaussians)
+size_t band_select_scratch_bytes(int n) { return 256 + ((size_t)(n + 32767) / 32768 + 1) * 8; }
+
+// status word / look-back exactly as in scan_sort.cu (flag << 32 | value; 1 = aggregate, 2 = inclusive prefix)
+__device__ __forceinline__ uint32_t sel_lookback(unsigned long long* status, uint32_t tile, uint32_t tile_sum, int lane) {
+  auto st = [](unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  };
+  auto ld = [](const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  };
+  if (tile == 0) {
+    if (lane == 0) st(status, (2ull << 32) | tile_sum);
+    return 0;
+  }
+  if (lane == 0) st(status + tile, (1ull << 32) | tile_sum);
+  uint32_t prefix = 0;
+  int j = (int)tile - 1;
+  while (true) {
+    const int idx = j - lane;
+    const unsigned long long sv = (idx >= 0) ? ld(status + idx) : (2ull << 32);
+    const uint32_t flag = (uint32_t)(sv >> 32);
+    const unsigned ready = __ballot_sync(0xffffffffu, flag != 0);
+    const unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
+    const int pp = pref ? (__ffs(pref) - 1) : 32;
+    const unsigned need = (pp >= 31) ? 0xffffffffu : ((2u << pp) - 1u);
+    if ((ready & need) != need) { __nanosleep(20); continue; }
+    uint32_t c = (lane <= pp) ? (uint32_t)sv : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    prefix += c;
+    if (pp < 32) break;
+    j -= 32;
+  }
+  if (lane == 0) st(status + tile, (2ull << 32) | (uint32_t)(prefix + tile_sum));
+  return prefix;
+}
+
+// Step 1 of the selection: pure streaming, no cross-CTA dependency.  A warp stages 128 rows with coalesced 16-byte
+// loads, every lane tests four of them (item k of lane l = row 32 k + l) and the four ballots go out as flag words.
+__global__ void __launch_bounds__(kSelThreads) band_select_kernel(GaussIn g, const float* __restrict__ c2w, RenderParams rp,
+                                                                  uint32_t* __restrict__ depth_key,
+                                                                  uint32_t* __restrict__ flag_words) {
+  constexpr int kWarps = kSelThreads / 32;
+  constexpr int kPerWarp = 32 * kSelItems;                       // 128 Gaussians per warp and step
+  __shared__ __align__(16) float s_pos[kWarps][kPerWarp * 3];
+  __shared__ __align__(16) float s_scale[kWarps][kPerWarp * 3];
+  __shared__ __align__(16) float s_op[kWarps][kPerWarp];
+  __shared__ float s_c2w[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  __syncthreads();
+  const Pose ps = make_pose(s_c2w);
+  const int n_chunks = (g.n + kPerWarp - 1) / kPerWarp;
+  for (int chunk = blockIdx.x * kWarps + warp; chunk < n_chunks; chunk += gridDim.x * kWarps) {
+    const int w0 = chunk * kPerWarp;                                // first Gaussian of this warp's chunk
+    if (w0 + kPerWarp <= g.n) {                                     // 1536 + 1536 + 512 contiguous bytes
+      const float4* p4 = reinterpret_cast<const float4*>(g.pos + (size_t)w0 * 3);
+      const float4* s4 = reinterpret_cast<const float4*>(g.scale_raw + (size_t)w0 * 3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        reinterpret_cast<float4*>(s_pos[warp])[lane + 32 * k] = ld_stream_f4(p4 + lane + 32 * k);
+        reinterpret_cast<float4*>(s_scale[warp])[lane + 32 * k] = ld_stream_f4(s4 + lane + 32 * k);
+      }
+      reinterpret_cast<float4*>(s_op[warp])[lane] = ld_stream_f4(reinterpret_cast<const float4*>(g.opacity_raw + w0) + lane);
+    } else {
+      for (int e = lane; e < kPerWarp * 3; e += 32) {
+        const bool ok = w0 + e / 3 < g.n;
+        s_pos[warp][e] = ok ? g.pos[(size_t)w0 * 3 + e] : 0.f;
+        s_scale[warp][e] = ok ? g.scale_raw[(size_t)w0 * 3 + e] : 0.f;
+      }
+      for (int e = lane; e < kPerWarp; e += 32) s_op[warp][e] = (w0 + e < g.n) ? g.opacity_raw[w0 + e] : -1e30f;
+    }
+    __syncwarp();
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < kSelItems; ++k) {
+      const int e = 32 * k + lane;                                   // stride-3 rows: conflict-free
+      const float p[3] = {s_pos[warp][3 * e], s_pos[warp][3 * e + 1], s_pos[warp][3 * e + 2]};
+      const float sr[3] = {s_scale[warp][3 * e], s_scale[warp][3 * e + 1], s_scale[warp][3 * e + 2]};
+      const bool cand = (w0 + e < g.n) && !band_cannot_touch(p, sr, s_op[warp][e], ps, rp);
+      const unsigned bal = __ballot_sync(0xffffffffu, cand);
+      if (lane == k) mine = bal;
+      // every key starts out culled; band_project_kernel overwrites the survivors'
+      if (w0 + e < g.n) depth_key[w0 + e] = kCulledKey;
+    }
+    if (lane < kSelItems) flag_words[chunk * kSelItems + lane] = mine;   // word w covers Gaussians [32 w, 32 w + 32)
+    __syncwarp();
+  }
+}
+
+// Step 2: the flag words (one per 32 Gaussians - 750 KB for 6M) -> candidate ids in index order: popcounts, block scan,
+// decoupled look-back, expansion of the set bits.
+constexpr int kExpThreads = 256;
+constexpr int kExpItems = 4;
+constexpr int kExpTile = kExpThreads * kExpItems;       // 1024 words = 32768 Gaussians per block
+
+__global__ void __launch_bounds__(kExpThreads) band_expand_kernel(const uint32_t* __restrict__ flag_words, uint32_t n_words,
+                                                                  uint32_t* __restrict__ cand_ids,
+                                                                  uint32_t* __restrict__ n_cand_out, uint32_t* ticket,
+                                                                  unsigned long long* status) {
+  __shared__ uint32_t s_warp[kExpThreads / 32];
+  __shared__ uint32_t s_tile, s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t w0 = tile * kExpTile + tid * kExpItems;              // thread-contiguous words: index order is kept
+  uint32_t w[kExpItems], cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kExpItems; ++k) {
+    w[k] = (w0 + k < n_words) ? flag_words[w0 + k] : 0u;
+    cnt += (uint32_t)__popc(w[k]);
+  }
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int q = 0; q < kExpThreads / 32; ++q) {
+    const uint32_t t = s_warp[q];
+    if (q < warp) warp_off += t;
+    tile_sum += t;
+  }
+  if (warp == 0) {
+    const uint32_t prefix = sel_lookback(status, tile, tile_sum, lane);
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (tile == (n_words - 1) / kExpTile) *n_cand_out = prefix + tile_sum;
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_prefix + warp_off + (inc - cnt);
+#pragma unroll
+  for (int k = 0; k < kExpItems; ++k) {
+    uint32_t bits = w[k];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      cand_ids[off++] = (w0 + k) * 32u + (uint32_t)b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPreBlock) band_project_kernel(GaussIn g, const float* __restrict__ c2w, RenderParams rp,
+                                                                 FrameView f, const uint32_t* __restrict__ cand_ids,
+                                                                 const uint32_t* __restrict__ n_cand,
+                                                                 uint32_t* __restrict__ cand_key,
+                                                                 uint32_t* __restrict__ depth_hist) {
+  constexpr int kShStride = 49;                  // 3 + 45 coefficients, odd stride: conflict-free row reads
+  __shared__ float s_c2w[16];
+  __shared__ uint32_t s_tiles;
+  __shared__ uint32_t s_dh[4][256];
+  __shared__ float s_sh[kPreBlock / 32][32][kShStride];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 16) s_c2w[tid] = c2w[tid];
+  if (tid == 0) s_tiles = 0;
+  for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
+  __syncthreads();
+  const Pose ps = make_pose(s_c2w);
+  const uint32_t total = *n_cand;
+  uint32_t vis_count = 0, s7_count = 0, tiles_sum = 0;
+  // whole warps iterate together (the SH rows of a warp's survivors are fetched cooperatively)
+  for (uint32_t j0 = (blockIdx.x * (kPreBlock / 32) + warp) * 32; j0 < total; j0 += gridDim.x * kPreBlock) {
+    const uint32_t j = j0 + lane;
+    const bool have = j < total;
+    const uint32_t i = have ? cand_ids[j] : 0u;
+    bool want_sh = false;
+    Projection o;
+    float p[3] = {0.f, 0.f, 0.f};
+    int tv0 = 0, tv1 = 0, tiles = 0;
+    if (have) {
+      p[0] = __ldg(g.pos + (size_t)i * 3); p[1] = __ldg(g.pos + (size_t)i * 3 + 1); p[2] = __ldg(g.pos + (size_t)i * 3 + 2);
+      const float sr[3] = {__ldg(g.scale_raw + (size_t)i * 3), __ldg(g.scale_raw + (size_t)i * 3 + 1),
+                           __ldg(g.scale_raw + (size_t)i * 3 + 2)};
+      const float4 q4 = __ldg(reinterpret_cast<const float4*>(g.q_raw) + i);
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+      QuatScale qs;
+      quat_scale_forward(sr, q, qs);
+      float full[9];
+      sigma_full(qs, full);
+      const Cov3 S = sym_from_full(full);
+      const bool vis = project_gaussian(p, S, __ldg(g.opacity_raw + i), ps, rp, o);
+      s7_count += (vis || o.offscreen) ? 1u : 0u;
+      vis_count += vis ? 1u : 0u;
+      if (vis) {
+        tv0 = max(o.tv0, rp.row_begin); tv1 = min(o.tv1, rp.row_end - 1);
+        tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
+      }
+      want_sh = tiles > 0;
+      if (!want_sh) cand_key[j] = kCulledKey;
+    }
+    // SH rows of the warp's survivors: one row per step, the 48 coefficients read by 32 lanes side by side (a lane
+    // gathering its own row touches 32 different sectors per load instruction and thrashes L1)
+    unsigned need = __ballot_sync(0xffffffffu, want_sh);
+    __syncwarp();
+    // eight rows per step: sixteen to twenty-four loads in flight per lane before the first store.  (LDGSTS copies of all
+    // rows at once - no registers, 7 resident CTAs - measured slower: 158-177 us against 143-159 us per eighth of the 4K
+    // frame; what bounds this kernel is the scattered 32-byte sector traffic, ~275 MB per band, not the latency chain.)
+    constexpr int kRowsPerStep = 8;
+    while (need) {
+      int r[kRowsPerStep];
+      float a[kRowsPerStep], b[kRowsPerStep], c[kRowsPerStep];
+#pragma unroll
+      for (int u = 0; u < kRowsPerStep; ++u) {
+        r[u] = need ? (__ffs(need) - 1) : -1;
+        if (need) need &= need - 1;
+      }
+#pragma unroll
+      for (int u = 0; u < kRowsPerStep; ++u) {
+        a[u] = b[u] = c[u] = 0.f;
+        if (r[u] >= 0) {                                              // warp-uniform
+          const uint32_t ir = __shfl_sync(0xffffffffu, i, r[u]);
+          const float* rest = g.f_rest + (size_t)ir * 45;
+          a[u] = __ldg(rest + lane);
+          if (lane < 13) b[u] = __ldg(rest + 32 + lane);
+          if (lane < 3) c[u] = __ldg(g.f_dc + (size_t)ir * 3 + lane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowsPerStep; ++u)
+        if (r[u] >= 0) {
+          s_sh[warp][r[u]][3 + lane] = a[u];
+          if (lane < 13) s_sh[warp][r[u]][3 + 32 + lane] = b[u];
+          if (lane < 3) s_sh[warp][r[u]][lane] = c[u];
+        }
+    }
+    __syncwarp();
+    if (!want_sh) continue;
+    {
+    const ViewDir vd = view_dir(p, ps.cam);
+    float Y[16], rgb[3], acc[3];
+    sh_basis(vd.d, Y);
+    sh_color(&s_sh[warp][lane][0], &s_sh[warp][lane][3], Y, rgb, acc);
+    float eu, ev;
+    conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
+    write_splat_record(f, (int)i, o, rgb, eu, ev, rp);
+    const uint32_t dk = __float_as_uint(o.z);
+    cand_key[j] = dk;
+    f.depth_key[i] = dk;
+    f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
+    f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
+    tiles_sum += (uint32_t)tiles;
+    if (depth_hist) {
+      atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
+      atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
+    }
+    }
+  }
+  const uint32_t wv = __reduce_add_sync(0xffffffffu, vis_count), w7 = __reduce_add_sync(0xffffffffu, s7_count);
+  const uint32_t wt = __reduce_add_sync(0xffffffffu, tiles_sum);
+  if ((tid & 31) == 0) {
+    if (wv) atomicAdd(&f.stats->n_visible, wv);
+    if (w7) atomicAdd(&f.stats->n_in_frustum, w7);
+    if (wt) atomicAdd(&s_tiles, wt);
+  }
+  __syncthreads();
+  if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
+  if (depth_hist)
+    for (int i = tid; i < 4 * 256; i += kPreBlock) {
+      const uint32_t c = (&s_dh[0][0])[i];
+      if (c) atomicAdd(&depth_hist[i], c);
+    }
+}
+
+// (full frames only: a band of tile rows goes through band_select_kernel + band_project_kernel below)
 __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
                                                                        RenderParams rp, FrameView f, int n_chunks,
                                                                        uint32_t* __restrict__ depth_hist) {
-  using Stage = typename PreStageOf<BAND>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Stage* stage = reinterpret_cast<Stage*>(smem_raw);             // [2]
+  PreStage* stage = reinterpret_cast<PreStage*>(smem_raw);       // [2]
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
   __shared__ uint32_t s_dh[4][256];      // digit histograms of the depth keys (the depth sort's 4 passes)
-  __shared__ uint32_t s_cand_cnt[kPreBlock / 32];
-  __shared__ uint16_t s_cand[kPreBlock];  // BAND: stage rows of the Gaussians that may touch the band
   const int tid = threadIdx.x;
   if (tid < 16) s_c2w[tid] = c2w[tid];
   for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
@@ -313,14 +573,14 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
   // full chunks go through the bulk-copy engine; a ragged last chunk is staged by the threads
   auto issue = [&](int chunk, int buf) {
     const size_t n0 = (size_t)chunk * kPreBlock;
-    Stage& st = stage[buf];
+    PreStage& st = stage[buf];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
-    mbar_expect_tx(&s_bar[buf], BAND ? kPreStageBandBytes : kPreStageBytes);
-    if constexpr (!BAND) bulk_g2s(st.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
+    mbar_expect_tx(&s_bar[buf], kPreStageBytes);
+    bulk_g2s(st.rest, g.f_rest + n0 * 45, kPreBlock * 45 * 4, &s_bar[buf]);
     bulk_g2s(st.quat, g.q_raw + n0 * 4, kPreBlock * 4 * 4, &s_bar[buf]);
     bulk_g2s(st.pos, g.pos + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
     bulk_g2s(st.scale, g.scale_raw + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
-    if constexpr (!BAND) bulk_g2s(st.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
+    bulk_g2s(st.dc, g.f_dc + n0 * 3, kPreBlock * 3 * 4, &s_bar[buf]);
     bulk_g2s(st.opac, g.opacity_raw + n0, kPreBlock * 4, &s_bar[buf]);
   };
   auto is_full = [&](int chunk) { return (chunk + 1) * kPreBlock <= g.n; };
@@ -332,56 +592,25 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
     const int buf = it & 1;
     const int next = chunk + gridDim.x;
     if (next < n_chunks && is_full(next) && tid == 0) issue(next, buf ^ 1);
-    Stage& st = stage[buf];
+    PreStage& st = stage[buf];
     const int n0 = chunk * kPreBlock;
     const int count = min(kPreBlock, g.n - n0);
     if (is_full(chunk)) {
       mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
     } else {
-      if constexpr (!BAND) stage_rows<45>(g.f_rest, st.rest, n0, count);
+      stage_rows<45>(g.f_rest, st.rest, n0, count);
       stage_rows<4>(g.q_raw, st.quat, n0, count);
       stage_rows<3>(g.pos, st.pos, n0, count);
       stage_rows<3>(g.scale_raw, st.scale, n0, count);
-      if constexpr (!BAND) stage_rows<3>(g.f_dc, st.dc, n0, count);
+      stage_rows<3>(g.f_dc, st.dc, n0, count);
       stage_rows<1>(g.opacity_raw, st.opac, n0, count);
       __syncthreads();
     }
-    // BAND: every thread runs the cheap test on its Gaussian; the candidates that remain (about one in eight, in random
-    // positions) are compacted to the front of the CTA so that whole warps skip the expensive path - with the
-    // candidates left where they are every warp would still execute it for its four or so live lanes.
-    bool live = tid < count;
-    int j = tid;                                   // row of the stage this thread projects
-    if constexpr (BAND) {
-      bool cand = false;
-      if (live) {
-        const float p[3] = {st.pos[3 * tid], st.pos[3 * tid + 1], st.pos[3 * tid + 2]};
-        const float sr[3] = {st.scale[3 * tid], st.scale[3 * tid + 1], st.scale[3 * tid + 2]};
-        cand = !band_cannot_touch(p, sr, st.opac[tid], ps, rp);
-        if (!cand) {                               // (the frame counters of a band describe the band)
-          f.depth_key[n0 + tid] = kCulledKey;
-          f.super_touched[n0 + tid] = 0;
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      if ((tid & 31) == 0) s_cand_cnt[tid >> 5] = (uint32_t)__popc(m);
-      __syncthreads();
-      uint32_t before = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < kPreBlock / 32; ++w) {
-        const uint32_t c = s_cand_cnt[w];
-        if (w < (tid >> 5)) before += c;
-        total += c;
-      }
-      if (cand) s_cand[before + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
-      __syncthreads();
-      live = (uint32_t)tid < total;
-      if (live) j = s_cand[tid];
-    }
-    if (live) {
-      const int i = n0 + j;
-      const float p[3] = {st.pos[3 * j], st.pos[3 * j + 1], st.pos[3 * j + 2]};
-      const float sr[3] = {st.scale[3 * j], st.scale[3 * j + 1], st.scale[3 * j + 2]};
-      const float4 q4 = reinterpret_cast<const float4*>(st.quat)[j];
+    if (tid < count) {
+      const int i = n0 + tid;
+      const float p[3] = {st.pos[3 * tid], st.pos[3 * tid + 1], st.pos[3 * tid + 2]};
+      const float sr[3] = {st.scale[3 * tid], st.scale[3 * tid + 1], st.scale[3 * tid + 2]};
+      const float4 q4 = reinterpret_cast<const float4*>(st.quat)[tid];
       const float q[4] = {q4.x, q4.y, q4.z, q4.w};
       QuatScale qs;
       quat_scale_forward(sr, q, qs);
@@ -389,42 +618,36 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       sigma_full(qs, full);
       const Cov3 S = sym_from_full(full);
       Projection o;
-      const bool vis = project_gaussian(p, S, st.opac[j], ps, rp, o);
+      const bool vis = project_gaussian(p, S, st.opac[tid], ps, rp, o);
       s7_count += (vis || o.offscreen) ? 1u : 0u;
       vis_count += vis ? 1u : 0u;
-      // a survivor whose tile rect misses this rank's band [row_begin, row_end) is dropped from the frame
-      int tv0 = 0, tv1 = 0, tiles = 0;
-      if (vis) {
-        tv0 = max(o.tv0, rp.row_begin); tv1 = min(o.tv1, rp.row_end - 1);
-        tiles = (tv1 >= tv0) ? (o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1) : 0;
-      }
-      const bool in_frame = tiles > 0;
-      // BAND: the keys are compacted before the sort, so the histograms cover the band's survivors only
-      if (depth_hist && (!BAND || in_frame)) {
-        const uint32_t dk = in_frame ? __float_as_uint(o.z) : kCulledKey;
+      if (depth_hist) {            // (full frames only: a band's sort builds its own histograms after the compaction)
+        const uint32_t dk = vis ? __float_as_uint(o.z) : kCulledKey;
         atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
         atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
       }
-      if (!in_frame) {
+      if (!vis) {
         f.depth_key[i] = kCulledKey;
         f.super_touched[i] = 0;
       } else {
         const ViewDir vd = view_dir(p, ps.cam);
-        float Y[16], rgb[3];
+        float Y[16], acc[3], rgb[3];
         sh_basis(vd.d, Y);
-        if constexpr (BAND) {
-          sh_color_global(g.f_dc + (size_t)i * 3, g.f_rest + (size_t)i * 45, Y, rgb);
-        } else {
-          float acc[3];
-          sh_color(&st.dc[3 * j], &st.rest[45 * j], Y, rgb, acc);
-        }
+        sh_color(&st.dc[3 * tid], &st.rest[45 * tid], Y, rgb, acc);
         float eu, ev;
         conic_extent(o.A11, o.A12, o.A22, rp.chi2, o.op, rp.alpha_cutoff, eu, ev);
-        write_splat_record(f, i, o, rgb, eu, ev, rp);
-        f.depth_key[i] = __float_as_uint(o.z);
-        f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
-        tiles_sum += (uint32_t)tiles;
-        f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
+        // tile-row sharding (large bands): this rank only bins tile rows [row_begin, row_end)
+        const int tv0 = max(o.tv0, rp.row_begin), tv1 = min(o.tv1, rp.row_end - 1);
+        if (tv1 >= tv0) {
+          write_splat_record(f, i, o, rgb, eu, ev, rp);
+          f.depth_key[i] = __float_as_uint(o.z);
+          f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
+          tiles_sum += (uint32_t)((o.tu1 - o.tu0 + 1) * (tv1 - tv0 + 1));
+          f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
+        } else {
+          f.depth_key[i] = kCulledKey;
+          f.super_touched[i] = 0;
+        }
       }
     }
     __syncthreads();   // everyone is done with stage[buf] before it is refilled (two iterations from now)
@@ -740,6 +963,8 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
   const bool rc = g.scale_raw != nullptr, rs = g.f_dc != nullptr;
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   static const bool no_tma = getenv("B200GS_NO_TMA") != nullptr;
+  const bool band = rp.row_begin > 0 || rp.row_end < rp.tiles_y;
+  if (band) depth_hist = nullptr;
   if (rc && rs && !no_tma && aligned16(g.pos) && aligned16(g.scale_raw) && aligned16(g.q_raw) && aligned16(g.f_dc) &&
       aligned16(g.f_rest) && aligned16(g.opacity_raw)) {
     static int sm_count = 0;
@@ -747,17 +972,10 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(preprocess_fwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
+      cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
     }
-    if (rp.row_begin > 0 || rp.row_end < rp.tiles_y) {
-      // a band: 11 KB of stages per CTA, latency-bound on the per-survivor SH gathers; 90 registers x 128 threads
-      // -> 5 resident CTAs per SM
-      const int bgrid = grid < 5 * sm_count ? grid : 5 * sm_count;
-      preprocess_fwd_tma_kernel<true><<<bgrid, kPreBlock, 2 * sizeof(PreStageBand), s>>>(g, c2w, rp, f, grid, depth_hist);
-    } else {
-      const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
-      preprocess_fwd_tma_kernel<false><<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
-    }
+    const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
+    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
     if (hist_done) *hist_done = depth_hist != nullptr;
     return cudaGetLastError();
   }
@@ -765,6 +983,62 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
   else if (rc && !rs) preprocess_fwd_kernel<true, false><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
   else if (!rc && rs) preprocess_fwd_kernel<false, true><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
   else preprocess_fwd_kernel<false, false><<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f);
+  return cudaGetLastError();
+}
+
+// Band frames from raw parameters: select + project (see above).  cand_ids / cand_key: u32[n] each; select_scratch:
+// band_select_scratch_bytes(n) bytes, zeroed here.  *used = false when this route does not apply (precomputed
+// sigma / color, unaligned arrays): the caller then runs launch_preprocess_fwd, whose kernels clip to the band too.
+cudaError_t launch_band_select(const GaussIn& g, const float* c2w, const RenderParams& rp, void* ws, const FrameLayout& L,
+                               uint32_t* flag_words, uint32_t* cand_ids, uint32_t* n_cand, void* select_scratch,
+                               size_t select_scratch_bytes, bool* used, cudaStream_t s) {
+  *used = false;
+  if (g.n <= 0) return cudaSuccess;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  static const bool off = getenv("B200GS_NO_BAND_SELECT") != nullptr;
+  // select + project pays when the band is a small part of the frame (measured on the 6M / 4K frame: an eighth of the
+  // rows 150 us against 290 us for the fused kernel; half of the rows: the fused kernel wins)
+  static const int max_pct = getenv("B200GS_BAND_SELECT_MAX_PCT") ? atoi(getenv("B200GS_BAND_SELECT_MAX_PCT")) : 35;
+  if (off || !g.scale_raw || !g.f_dc || !aligned16(g.pos) || !aligned16(g.scale_raw) || !aligned16(g.q_raw) ||
+      !aligned16(g.opacity_raw) || (rp.row_end - rp.row_begin) * 100 > max_pct * rp.tiles_y)
+    return cudaSuccess;
+  if (select_scratch_bytes < band_select_scratch_bytes(g.n)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(select_scratch, 0, band_select_scratch_bytes(g.n), s);
+  if (e != cudaSuccess) return e;
+  const FrameView f = make_view(ws, L);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_chunks = ceil_div(g.n, 32 * kSelItems), want = ceil_div(n_chunks, kSelThreads / 32);
+  const int grid = want < 5 * sm_count ? want : 5 * sm_count;
+  band_select_kernel<<<grid, kSelThreads, 0, s>>>(g, c2w, rp, f.depth_key, flag_words);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const uint32_t n_words = (uint32_t)n_chunks * kSelItems;
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(select_scratch);
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(select_scratch) + 256);
+  band_expand_kernel<<<(n_words + kExpTile - 1) / kExpTile, kExpThreads, 0, s>>>(flag_words, n_words, cand_ids, n_cand, ticket,
+                                                                              status);
+  *used = true;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_project(const GaussIn& g, const float* c2w, const RenderParams& rp, void* ws, const FrameLayout& L,
+                                const uint32_t* cand_ids, const uint32_t* n_cand, uint32_t* cand_key, uint32_t* depth_hist,
+                                cudaStream_t s) {
+  if (g.n <= 0) return cudaSuccess;
+  const FrameView f = make_view(ws, L);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int want = ceil_div(g.n, kPreBlock);
+  const int grid = want < 5 * sm_count ? want : 5 * sm_count;     // 92 registers x 128 threads: 5 resident CTAs per SM
+  band_project_kernel<<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f, cand_ids, n_cand, cand_key, depth_hist);
   return cudaGetLastError();
 }
 

@@ -158,7 +158,11 @@ constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 4096 keys per
 
 size_t compact_scratch_bytes(uint32_t n) { return 256 + ((size_t)(n + kCompactTile - 1) / kCompactTile + 1) * 8; }
 
-__global__ void __launch_bounds__(kCompactThreads) compact_keys_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+__device__ __forceinline__ uint32_t eff_count(uint32_t n_host, const uint32_t* n_dev);
+
+__global__ void __launch_bounds__(kCompactThreads) compact_keys_kernel(const uint32_t* __restrict__ keys,
+                                                                       const uint32_t* __restrict__ ids_in,
+                                                                       uint32_t n_host, const uint32_t* __restrict__ n_dev,
                                                                        uint32_t* __restrict__ out_keys,
                                                                        uint32_t* __restrict__ out_ids,
                                                                        uint32_t* __restrict__ count_out,
@@ -166,6 +170,9 @@ __global__ void __launch_bounds__(kCompactThreads) compact_keys_kernel(const uin
   __shared__ uint32_t s_warp[kCompactThreads / 32];
   __shared__ uint32_t s_tile, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = eff_count(n_host, n_dev);
+  if (n == 0) { if (blockIdx.x == 0 && tid == 0) *count_out = 0; return; }
+  if ((uint32_t)blockIdx.x * (uint32_t)kCompactTile >= n) return;       // surplus CTAs (grid sized for the upper bound)
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -212,21 +219,22 @@ __global__ void __launch_bounds__(kCompactThreads) compact_keys_kernel(const uin
   for (int i = 0; i < kCompactItems; ++i)
     if (k[i] != kCulledKey) {
       out_keys[off] = k[i];
-      out_ids[off] = base + i;
+      out_ids[off] = ids_in ? ids_in[base + i] : base + i;
       ++off;
     }
 }
 
-cudaError_t launch_compact_keys(const uint32_t* keys, uint32_t n, uint32_t* out_keys, uint32_t* out_ids,
-                                uint32_t* count_out, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+cudaError_t launch_compact_keys(const uint32_t* keys, const uint32_t* ids_in, uint32_t n, const uint32_t* n_dev,
+                                uint32_t* out_keys, uint32_t* out_ids, uint32_t* count_out, void* scratch,
+                                size_t scratch_bytes, cudaStream_t s) {
   if (n == 0) return cudaMemsetAsync(count_out, 0, 4, s);
   if (scratch_bytes < compact_scratch_bytes(n)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);
   if (e != cudaSuccess) return e;
   uint32_t* ticket = reinterpret_cast<uint32_t*>(scratch);
   unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + 256);
-  compact_keys_kernel<<<(n + kCompactTile - 1) / kCompactTile, kCompactThreads, 0, s>>>(keys, n, out_keys, out_ids,
-                                                                                      count_out, ticket, status);
+  compact_keys_kernel<<<(n + kCompactTile - 1) / kCompactTile, kCompactThreads, 0, s>>>(keys, ids_in, n, n_dev, out_keys,
+                                                                                      out_ids, count_out, ticket, status);
   return cudaGetLastError();
 }
 

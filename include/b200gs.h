@@ -105,7 +105,8 @@ typedef struct b200gs_frame_stats {
                             this is > 0 but n_visible == 0) */
   uint32_t n_super;    /* (supertile, Gaussian) pairs: the number of keys the binning sort handles */
   uint32_t n_sorted;   /* band frames: Gaussians whose tile rect meets the band (the keys the depth sort handles) */
-  uint32_t reserved[10];
+  uint32_t n_candidates; /* band frames: Gaussians that passed the cheap band test and were projected */
+  uint32_t reserved[9];
 } b200gs_frame_stats;
 
 int b200gs_abi_version(void);

@@ -40,7 +40,7 @@ KEEP = ["ID", "Kernel Name", "launch__grid_size", "launch__block_size", "launch_
 
 
 # single-kernel regions of bench.py's per-kernel table (multi-kernel regions keep the figures of an earlier capture)
-REGION_OF = {"blend_fwd_kernel": "blend_fwd", "blend_bwd_kernel": "blend_bwd", "preprocess_fwd_tma_kernel": "preprocess_fwd",
+REGION_OF = {"blend_fwd_kernel": "blend_fwd", "blend_bwd_kernel": "blend_bwd", "blend_bwd_ppl_kernel": "blend_bwd", "preprocess_fwd_tma_kernel": "preprocess_fwd",
              "preprocess_bwd_tma_kernel": "preprocess_bwd", "l1_ssim_fwd_kernel": "l1_ssim_fwd",
              "l1_ssim_bwd_kernel": "l1_ssim_bwd", "adam_step_kernel": "adam_step", "scan_emit_super_kernel": "emit_super"}
 
