@@ -71,6 +71,13 @@ class _Deferred(torch.Tensor):
 
     def materialize(self) -> torch.Tensor:
         if self._value is None:
+            src = _get_tag(self)
+            if src is not None and src.resolve() is None:
+                # the reference computes sigma / colours at the call; computing them now from modified parameters
+                # would silently give different values
+                raise RuntimeError("b200gs: the parameters this tensor was computed from have been modified in place "
+                                   "since build_sigma_from_params / evaluate_sh was called (set B200GS_LAZY=0 for eager "
+                                   "evaluation at the call)")
             with torch.set_grad_enabled(self._grad_mode):
                 self._value = self._thunk()
             src = _get_tag(self)

@@ -155,6 +155,7 @@ def _sizes(lib, n: int, H: int, W: int, capacity: int):
 # first frame on a device is sized exactly), queue the whole frame without a mid-frame sync and wait only for the
 # event the library records once the frame's counters are final; a frame that did not fit is rasterized again with
 # exact buffers.  "sync": read I back between project and rasterize (one stream sync per frame, exact buffers).
+# The mark is kept per (device, N, H, W): unrelated scenes or resolutions in one process do not inflate each other's lists.
 _high_water = {}
 _blend_stream = {}       # device index -> torch stream the blend kernels go to (set by api.RenderPipeline)
 
@@ -208,7 +209,8 @@ class Frame:
         if self.out is not None and (tuple(image.shape) != (H, W, 3) or image.dtype != torch.float32 or
                                      not image.is_contiguous() or image.device != dev):
             raise ValueError("out must be a contiguous [H,W,3] float32 tensor on the device of the Gaussians")
-        spec_cap = _high_water.get(dev.index, 0) if mode == "speculative" else 0
+        self._hw_key = (dev.index, n, H, W)
+        spec_cap = _high_water.get(self._hw_key, 0) if mode == "speculative" else 0
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
                                              frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
         self._unchecked = None
@@ -253,8 +255,11 @@ class Frame:
             self._stats_pending = None
 
     def _grow(self, need: int) -> int:
-        cap = max(int(need * 1.25) + 1024, _high_water.get(self.device.index, 0))
-        _high_water[self.device.index] = cap
+        key = getattr(self, "_hw_key", None) or (self.device.index, int(self.g.n), int(self.cfg.H), int(self.cfg.W))
+        cap = max(int(need * 1.25) + 1024, _high_water.get(key, 0))
+        if len(_high_water) > 256:
+            _high_water.clear()
+        _high_water[key] = cap
         return cap
 
     def _read_stats(self, arr):
@@ -420,11 +425,20 @@ class _Rasterize(torch.autograd.Function):
         ctx.frame = frame
         ctx.shapes = [None if t is None else (t.shape, t.dtype) for t in
                       (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color)]
+        # the backward recomputes the projection from the inputs' live memory (nothing per Gaussian is saved twice):
+        # an in-place change between forward and backward must raise, as it does for tensors autograd saves itself
+        ctx.inputs = [(name, t, t._version) for name, t in
+                      zip(("pos", "opacity_raw", "scale_raw", "q_raw", "sigma", "f_dc", "f_rest", "color", "c2w"),
+                          (pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w)) if t is not None]
         return image
 
     @staticmethod
     def backward(ctx, grad_image):
         frame: Frame = ctx.frame
+        for name, t, version in ctx.inputs:
+            if t._version != version:
+                raise RuntimeError(f"b200gs.render: `{name}`, needed for the gradient computation, has been modified by an "
+                                   f"inplace operation since the forward (version {t._version}, expected {version})")
         dev = frame.device
         gi = _f32c(grad_image)
         n = int(frame.g.n)

@@ -86,6 +86,7 @@ __device__ __forceinline__ float splat_exponent(const float4& s0, const float4& 
 // splat: bounding box of the effective ellipse { q <= min(chi2, 2 ln(opacity / alpha_cutoff)) } (half-extents
 // precomputed per splat, conservative) against the block.  (An exact ellipse-vs-rectangle test was measured:
 // it costs more than the few extra visits it removes.)  Returns the number of entries.
+template <uint32_t kStride = kRecStride>
 __device__ __forceinline__ uint32_t compact_touching(uint32_t buf, uint32_t sa_list, int lim, int lane, float wcx,
                                                      float wcy, float hx = 3.5f, float hy = 1.5f) {
   uint32_t nw = 0;
@@ -93,7 +94,7 @@ __device__ __forceinline__ uint32_t compact_touching(uint32_t buf, uint32_t sa_l
   uint32_t a = buf + (uint32_t)lane * 16u;
   for (int jt = lane; jt - lane < lim; jt += 32, a += 512u) {
     const float2 c = lds_f2(a);                                   // (u, v); slots >= lim hold stale data: masked below
-    const float2 e = lds_f2(a + 2 * kRecStride + 8u);             // (ext_u, ext_v)
+    const float2 e = lds_f2(a + 2 * kStride + 8u);                // (ext_u, ext_v)
     const bool touch = (jt < lim) & (fabsf(c.x - wcx) <= e.x + hx) & (fabsf(c.y - wcy) <= e.y + hy);
     const unsigned m = __ballot_sync(0xffffffffu, touch);
     if (touch) sts_u32(sa_list + (nw + __popc(m & lt)) * 4u, a);

@@ -389,7 +389,7 @@ def test_speculative_capacity_overflow_is_redone_with_exact_buffers(gs):
     ref, fr = _render_frame(gs, sc, cam, mode="sync")
     fr.refresh_stats()
     assert fr.n_isect > 4000
-    dev = sc["pos"].device.index
+    dev = (sc["pos"].device.index, 30_000, 200, 320)      # the mark is kept per (device, N, H, W)
     saved = ops._high_water.get(dev, 0)
     try:
         ops._high_water[dev] = 1000                      # far too small for this frame
@@ -461,7 +461,7 @@ def test_render_pipeline_gives_the_same_frames(gs):
         side.synchronize()
         # a frame that overflows its speculative capacity while others are in flight is redone transparently
         from b200gs import ops
-        ops._high_water[0] = 2000
+        ops._high_water[(0, 60_000, 360, 640)] = 2000
         col = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2ws[0])
         redo = pipe.render(sc["pos"], col, sc["opacity_raw"], sigma, c2ws[0], 360, 640, K["fx"], K["fy"], K["cx"], K["cy"])
         pipe.synchronize()
@@ -617,3 +617,26 @@ def test_grad_bucket_backward_writes_into_the_flat_buffer(gs):
         for k in PARAMS:
             scale = float(plain[k].grad.abs().max())
             assert float((lv[k].grad - plain[k].grad).abs().max()) <= 2e-5 * scale, k
+
+
+def test_inplace_change_between_forward_and_backward_raises(gs):
+    """The backward recomputes the projection from the inputs' live memory, so an in-place modification after the
+    forward must raise (as autograd does for tensors it saves), and a deferred sigma whose sources changed must not be
+    evaluated from the new values."""
+    from oracle import gs_oracle as O
+    sc = O.make_scene(500, seed=2, log_scale=-3.0)
+    cam = O.make_camera(64, 48)
+    lv = {k: v.cuda().requires_grad_(True) for k, v in sc.items()}
+    c2w = cam["c2w"].cuda()
+    sigma = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+    color = gs.evaluate_sh(lv["f_dc"], lv["f_rest"], lv["pos"], c2w)
+    img = gs.render(lv["pos"], color, lv["opacity_raw"], sigma, c2w, 48, 64, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    with torch.no_grad():
+        lv["pos"].add_(0.01)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        img.sum().backward()
+    s2 = gs.build_sigma_from_params(lv["scale_raw"], lv["q_raw"])
+    with torch.no_grad():
+        lv["scale_raw"].mul_(1.1)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        s2.cpu()
