@@ -329,7 +329,12 @@ class Frame:
                    "debug_export_lists")
         out["list_tile"], out["list_id"] = out["list_tile"][:cnt], out["list_id"][:cnt]
         torch.cuda.current_stream(dev).synchronize()
-        return {k: v.cpu() for k, v in out.items()}
+        out = {k: v.cpu() for k, v in out.items()}
+        # behind the survivors the sorted order lists the culled Gaussians: report the survivors, in depth order
+        order = out["depth_order"].long()
+        order = order[(order >= 0) & (order < n)]
+        out["depth_order"] = order[out["tiles_touched"][order] >= 0].to(torch.int32)
+        return out
 
 
 def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
