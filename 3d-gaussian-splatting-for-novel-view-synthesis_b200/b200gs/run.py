@@ -36,6 +36,83 @@ import runpy
 import sys
 
 
+class ShardedRandomSampler:
+    """Sampler for `DataLoader(shuffle=True)` under `--dp`: ONE permutation of the views per epoch, drawn from a generator
+    that every rank seeds identically, of which rank r takes entries r, r + world, ... (padded by wrapping around, like
+    DistributedSampler, so that every rank sees the same number of views per epoch).  p ranks x batch b therefore visit
+    the same views per iteration as 1 rank x batch p*b."""
+
+    def __init__(self, n: int, rank: int, world: int, seed: int):
+        import torch
+        self.n, self.rank, self.world = int(n), int(rank), int(world)
+        self.gen = torch.Generator().manual_seed(int(seed) + 7919)      # same stream on every rank
+
+    def __iter__(self):
+        import torch
+        perm = torch.randperm(self.n, generator=self.gen).tolist()
+        total = -(-self.n // self.world) * self.world
+        perm = (perm * (total // max(self.n, 1) + 1))[:total]
+        return iter(perm[self.rank::self.world])
+
+    def __len__(self):
+        return -(-self.n // self.world)
+
+
+class GradientReducer:
+    """Reduces the gradients of the live optimizer's parameters ONCE per iteration - at the first of `clip_grad_norm_`
+    (train.py:536) / `optimizer.step()` (train.py:538) after a backward - through a `b200gs.dist.GradBucket` (one flat
+    buffer, one all-reduce) and divides by the world size, which completes the script's per-batch loss average
+    (train.py:514-521) to the global batch."""
+
+    def __init__(self, group=None):
+        self.group, self.bucket, self.params, self.reduced = group, None, None, False
+
+    def track(self, params):
+        """A (new) optimizer was constructed over `params` (the script re-creates it after every densification)."""
+        if self.params is not None and self.params[0].is_cuda:
+            from . import ops
+            ops.unregister_grad_sinks(self.params)
+        self.bucket, self.params, self.reduced = None, list(params), False
+
+    def ensure_reduced(self):
+        if self.reduced or not self.params:
+            return
+        if self.bucket is None:
+            from .dist import GradBucket
+            self.bucket = GradBucket(self.params, group=self.group)
+        self.bucket.allreduce(average=True)
+        self.reduced = True
+
+    def next_iteration(self):
+        self.reduced = False
+
+    def wrap_optimizer(self, cls):
+        reducer = self
+
+        class DataParallel(cls):
+            def __init__(self, params, *a, **kw):
+                super().__init__(params, *a, **kw)
+                reducer.track([p for g in self.param_groups for p in g["params"]])
+
+            def step(self, closure=None):
+                reducer.ensure_reduced()
+                out = super().step(closure)
+                reducer.next_iteration()
+                return out
+
+            def zero_grad(self, set_to_none=True):
+                reducer.next_iteration()
+                return super().zero_grad(set_to_none)
+        DataParallel.__name__ = cls.__name__
+        return DataParallel
+
+    def wrap_clip(self, fn):
+        def clip_grad_norm_(parameters, *a, **kw):
+            self.ensure_reduced()
+            return fn(parameters, *a, **kw)
+        return clip_grad_norm_
+
+
 def _setup_dp():
     """Everything `--dp` changes, applied BEFORE the script is imported.  Returns (rank, world)."""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -58,76 +135,24 @@ def _setup_dp():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", 0))
 
     # ---- views: one shared permutation per epoch, rank r takes entries r, r + world, ... ----------------------------
-    class ShardedRandomSampler(tud.Sampler):
-        def __init__(self, data_source):
-            self.n = len(data_source)
-            self.gen = torch.Generator().manual_seed(seed + 7919)      # same stream on every rank
-
-        def __iter__(self):
-            perm = torch.randperm(self.n, generator=self.gen).tolist()
-            total = -(-self.n // world) * world            # padded by wrapping around, like DistributedSampler:
-            perm = (perm * (total // max(self.n, 1) + 1))[:total]   # every rank gets the same number of views per epoch
-            return iter(perm[rank::world])
-
-        def __len__(self):
-            return -(-self.n // world)
-
     orig_init = tud.DataLoader.__init__
 
     def dl_init(self, dataset, *a, **kw):
         if kw.get("shuffle") and kw.get("sampler") is None and kw.get("batch_sampler") is None:
             kw["shuffle"] = False
-            kw["sampler"] = ShardedRandomSampler(dataset)
+            kw["sampler"] = ShardedRandomSampler(len(dataset), rank, world, seed)
         orig_init(self, dataset, *a, **kw)
     tud.DataLoader.__init__ = dl_init
 
     # ---- gradients: reduced once per iteration by whichever of clip_grad_norm_ / optimizer.step comes first ---------
-    from .dist import GradBucket
-    from . import ops
-    state = {"bucket": None, "params": None, "reduced": False}
-
-    def ensure_reduced():
-        if state["reduced"] or state["params"] is None:
-            return
-        if state["bucket"] is None:
-            state["bucket"] = GradBucket(state["params"])
-        state["bucket"].allreduce(average=True)
-        state["reduced"] = True
-
-    def wrap_optimizer(cls):
-        class DataParallel(cls):
-            def __init__(self, params, *a, **kw):
-                super().__init__(params, *a, **kw)
-                plist = [p for g in self.param_groups for p in g["params"]]
-                if state["params"] is not None:
-                    ops.unregister_grad_sinks(state["params"])         # the script re-creates the optimizer after densify
-                state.update(bucket=None, params=plist, reduced=False)
-
-            def step(self, closure=None):
-                ensure_reduced()
-                out = super().step(closure)
-                state["reduced"] = False
-                return out
-
-            def zero_grad(self, set_to_none=True):
-                state["reduced"] = False
-                return super().zero_grad(set_to_none)
-        DataParallel.__name__ = cls.__name__
-        return DataParallel
-
-    torch.optim.Adam = wrap_optimizer(torch.optim.Adam)
-    inner_clip = torch.nn.utils.clip_grad_norm_
-
-    def clip_grad_norm_(parameters, *a, **kw):
-        ensure_reduced()
-        return inner_clip(parameters, *a, **kw)
-    torch.nn.utils.clip_grad_norm_ = clip_grad_norm_
+    reducer = GradientReducer()
+    torch.optim.Adam = reducer.wrap_optimizer(torch.optim.Adam)
+    torch.nn.utils.clip_grad_norm_ = reducer.wrap_clip(torch.nn.utils.clip_grad_norm_)
 
     # ---- side effects: rank 0 only ---------------------------------------------------------------------------------------
     if rank != 0:
         torch.save = lambda *a, **kw: None
-        devnull = open(os.devnull, "w")
-        sys.stdout = devnull
+        sys.stdout = open(os.devnull, "w")
         os.environ.setdefault("TQDM_DISABLE", "1")
     return rank, world
 

@@ -10,6 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from b200gs.dist import GradBucket, allreduce_gradients, render_tile_row_sharded, shard_tile_rows, shard_views
+from b200gs.run import GradientReducer, ShardedRandomSampler
 
 
 def test_shard_views_round_robin():
@@ -103,3 +104,68 @@ def test_two_rank_gloo_allreduce_and_bands():
         for it in range(2):
             assert torch.equal(out[f"bp{r}_{it}"], torch.full((2, 3), float(sum(v + 1 + it for v in range(5)))))
             assert torch.equal(out[f"bq{r}_{it}"], torch.zeros(5))
+
+
+@pytest.mark.parametrize("n,world", [(12, 2), (12, 8), (7, 2), (5, 8), (1, 2)])
+def test_dp_launcher_sampler_shards_one_shared_permutation(n, world):
+    """`b200gs.run --dp`: p ranks x batch 1 visit, per iteration, the views 1 rank x batch p visits."""
+    per_rank = [list(iter(ShardedRandomSampler(n, r, world, seed=3))) for r in range(world)]
+    assert len({len(x) for x in per_rank}) == 1 == len({len(ShardedRandomSampler(n, r, world, 3)) for r in range(world)})
+    single = list(iter(ShardedRandomSampler(n, 0, 1, seed=3)))
+    assert sorted(single) == list(range(n))
+    padded = (single * (world + 1))[:len(per_rank[0]) * world]
+    for it in range(len(per_rank[0])):
+        assert [per_rank[r][it] for r in range(world)] == padded[it * world:(it + 1) * world]
+    # a second epoch draws a new permutation, the same on every rank
+    s0, s1 = ShardedRandomSampler(n, 0, world, 3), ShardedRandomSampler(n, min(1, world - 1), world, 3)
+    e1 = [list(iter(s0)), list(iter(s1))]
+    e2 = [list(iter(s0)), list(iter(s1))]
+    if n > 3:
+        assert e1 != e2
+    assert len(e2[0]) == len(e2[1])
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        p = torch.nn.Parameter(torch.randn(4, 3))
+        q = torch.nn.Parameter(torch.randn(5))
+        reducer = GradientReducer()
+        Adam = reducer.wrap_optimizer(torch.optim.Adam)
+        clip = reducer.wrap_clip(torch.nn.utils.clip_grad_norm_)
+        opt = Adam([{"params": [p], "lr": 0.1}, {"params": [q], "lr": 0.01}], eps=1e-15)
+        for it in range(3):
+            opt.zero_grad()
+            x = torch.full((4, 3), float(rank + 1 + it))
+            ((p * x).sum() + (q * (rank + 2)).sum()).backward()        # this rank's "view"
+            clip(p, max_norm=1.0)                                      # train.py:536 - triggers the reduction
+            if it == 0:
+                out[f"g{rank}"] = (p.grad.clone(), q.grad.clone())
+            opt.step()                                                 # must not reduce a second time
+        out[f"p{rank}"], out[f"q{rank}"] = p.detach().clone(), q.detach().clone()
+        # the script re-creates the optimizer after densification: new parameters are tracked
+        p2 = torch.nn.Parameter(torch.ones(2))
+        opt2 = Adam([{"params": [p2], "lr": 0.1}], eps=1e-15)
+        opt2.zero_grad()
+        (p2 * float(rank + 1)).sum().backward()
+        opt2.step()
+        out[f"g2_{rank}"] = p2.grad.clone()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_launcher_reduces_once_per_iteration_and_keeps_replicas_identical():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        out = dict(out)
+    # iteration 0: mean over the ranks of x (1 and 2) = 1.5, clipped to norm 1 by the script's own call; q: mean(2, 3)
+    gp, gq = out["g0"]
+    assert torch.allclose(gp, torch.full((4, 3), 1.5) / (1.5 * (12 ** 0.5) + 1e-6), atol=1e-6)
+    assert torch.equal(gq, torch.full((5,), 2.5))
+    assert torch.equal(out["g0"][0], out["g1"][0]) and torch.equal(out["g0"][1], out["g1"][1])
+    assert torch.equal(out["p0"], out["p1"]) and torch.equal(out["q0"], out["q1"])       # replicas never diverge
+    assert torch.equal(out["g2_0"], torch.full((2,), 1.5)) and torch.equal(out["g2_0"], out["g2_1"])
