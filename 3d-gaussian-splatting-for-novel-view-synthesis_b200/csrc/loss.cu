@@ -54,7 +54,33 @@ static LossLayout loss_layout(int n_img, int H, int W, bool with_grad) {
 
 size_t loss_workspace_bytes(int n_img, int H, int W, bool with_grad) { return loss_layout(n_img, H, W, with_grad).total; }
 
+// Packed FP32 (Blackwell FFMA2 / FMUL2): one instruction, two IEEE operations on a register pair - the same results as
+// two scalar fmaf / multiplies, half the issue slots.  The separable filter applies one tap weight to five quantities
+// at once, so the pairs (x, y) and (xx, yy) share their (w, w) operand.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // Loads the (kLossIn x kLossIn) halo tile of one channel of an interleaved [H,W,3] image, zero outside.
+// (One element per thread and step with a division by 42: a row-per-warp mapping without the division was measured and
+// is 11 % slower - 10 of its 32 lanes load the second half of a 42-wide row; the kernel is bound by load / shared-memory
+// instructions, not by arithmetic.)
 __device__ __forceinline__ void load_tile_hwc(const float* __restrict__ img, int H, int W, int c, int x0, int y0,
                                               float (*s)[kLossIn + 1]) {
   for (int i = threadIdx.x; i < kLossIn * kLossIn; i += kLossThreads) {
@@ -88,8 +114,9 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_fwd_kernel(const float* 
   const size_t img_off = (size_t)b * H * W * 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float w[11];
+  f32x2 w2[11];
 #pragma unroll
-  for (int t = 0; t < 11; ++t) w[t] = c_win[t];
+  for (int t = 0; t < 11; ++t) { w[t] = c_win[t]; w2[t] = pack2(w[t], w[t]); }
   float sum_l1 = 0.f, sum_s = 0.f;
   for (int c = 0; c < 3; ++c) {
     __syncthreads();     // previous channel's vertical pass is done with sh, sx, sy
@@ -100,50 +127,52 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_fwd_kernel(const float* 
     // inputs (each input is loaded once and feeds the up to 4 outputs it belongs to); lanes take consecutive rows
     for (int item = tid; item < kLossIn * (kLossTile / 4); item += kLossThreads) {
       const int r = item % kLossIn, q0 = (item / kLossIn) * 4;
-      float acc[4][5];
+      f32x2 a01[4], a23[4];       // (E[x], E[y]) and (E[xx], E[yy]) as register pairs
+      float a4[4];                // E[xy]
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc[j][m] = 0.f;
+      for (int j = 0; j < 4; ++j) { a01[j] = 0ull; a23[j] = 0ull; a4[j] = 0.f; }
 #pragma unroll
       for (int t = 0; t < 14; ++t) {
         const float x = sx[r][q0 + t], y = sy[r][q0 + t];
-        const float xx = x * x, yy = y * y, xy = x * y;
+        const f32x2 xy2 = pack2(x, y), sq2 = mul2(xy2, xy2);
+        const float xy = x * y;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = t - j;
           if (k >= 0 && k < 11) {
-            acc[j][0] = fmaf(w[k], x, acc[j][0]);
-            acc[j][1] = fmaf(w[k], y, acc[j][1]);
-            acc[j][2] = fmaf(w[k], xx, acc[j][2]);
-            acc[j][3] = fmaf(w[k], yy, acc[j][3]);
-            acc[j][4] = fmaf(w[k], xy, acc[j][4]);
+            a01[j] = fma2(w2[k], xy2, a01[j]);
+            a23[j] = fma2(w2[k], sq2, a23[j]);
+            a4[j] = fmaf(w[k], xy, a4[j]);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int m = 0; m < 5; ++m) sh[m][r][q0 + j] = acc[j][m];
+      for (int j = 0; j < 4; ++j) {
+        float e0, e1, e2, e3;
+        unpack2(a01[j], e0, e1);
+        unpack2(a23[j], e2, e3);
+        sh[0][r][q0 + j] = e0; sh[1][r][q0 + j] = e1; sh[2][r][q0 + j] = e2; sh[3][r][q0 + j] = e3;
+        sh[4][r][q0 + j] = a4[j];
+      }
     }
     __syncthreads();
     // vertical pass: a thread owns 4 vertically adjacent pixels of one column, same sliding window
-    float vacc[4][5];
+    f32x2 v01[4], v23[4];
+    float v4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int m = 0; m < 5; ++m) vacc[j][m] = 0.f;
+    for (int j = 0; j < 4; ++j) { v01[j] = 0ull; v23[j] = 0ull; v4[j] = 0.f; }
 #pragma unroll
     for (int t = 0; t < 14; ++t) {
-      float v[5];
-#pragma unroll
-      for (int m = 0; m < 5; ++m) v[m] = sh[m][4 * warp + t][lane];
+      const f32x2 p01 = pack2(sh[0][4 * warp + t][lane], sh[1][4 * warp + t][lane]);
+      const f32x2 p23 = pack2(sh[2][4 * warp + t][lane], sh[3][4 * warp + t][lane]);
+      const float p4 = sh[4][4 * warp + t][lane];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = t - j;
         if (k >= 0 && k < 11) {
-#pragma unroll
-          for (int m = 0; m < 5; ++m) vacc[j][m] = fmaf(w[k], v[m], vacc[j][m]);
+          v01[j] = fma2(w2[k], p01, v01[j]);
+          v23[j] = fma2(w2[k], p23, v23[j]);
+          v4[j] = fmaf(w[k], p4, v4[j]);
         }
       }
     }
@@ -151,7 +180,10 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_fwd_kernel(const float* 
     for (int k = 0; k < 4; ++k) {
       const int py = 4 * warp + k, px = lane;
       const int y = y0 + py, x = x0 + px;
-      const float mu1 = vacc[k][0], mu2 = vacc[k][1], exx = vacc[k][2], eyy = vacc[k][3], exy = vacc[k][4];
+      float mu1, mu2, exx, eyy;
+      unpack2(v01[k], mu1, mu2);
+      unpack2(v23[k], exx, eyy);
+      const float exy = v4[k];
       if (y < H && x < W) {
         const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
         const float s1 = exx - mu1_sq, s2 = eyy - mu2_sq, s12 = exy - mu12;
@@ -230,8 +262,9 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_bwd_kernel(const float* 
   const float g = grad_total ? *grad_total : 1.f;
   const float ks = k_ssim * g, k1 = k_l1 * g;
   float w[11];
+  f32x2 w2[11];
 #pragma unroll
-  for (int t = 0; t < 11; ++t) w[t] = c_win[t];
+  for (int t = 0; t < 11; ++t) { w[t] = c_win[t]; w2[t] = pack2(w[t], w[t]); }
   for (int c = 0; c < 3; ++c) {
     __syncthreads();
     const size_t plane = (size_t)(b * 3 + c) * H * W;
@@ -240,45 +273,45 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_bwd_kernel(const float* 
     __syncthreads();
     for (int item = tid; item < kLossIn * (kLossTile / 4); item += kLossThreads) {
       const int r = item % kLossIn, q0 = (item / kLossIn) * 4;
-      float acc[4][3];
+      f32x2 a01[4];
+      float a2[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int m = 0; m < 3; ++m) acc[j][m] = 0.f;
+      for (int j = 0; j < 4; ++j) { a01[j] = 0ull; a2[j] = 0.f; }
 #pragma unroll
       for (int t = 0; t < 14; ++t) {
-        const float v0 = sa[0][r][q0 + t], v1 = sa[1][r][q0 + t], v2 = sa[2][r][q0 + t];
+        const f32x2 p01 = pack2(sa[0][r][q0 + t], sa[1][r][q0 + t]);
+        const float p2 = sa[2][r][q0 + t];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = t - j;
           if (k >= 0 && k < 11) {
-            acc[j][0] = fmaf(w[k], v0, acc[j][0]);
-            acc[j][1] = fmaf(w[k], v1, acc[j][1]);
-            acc[j][2] = fmaf(w[k], v2, acc[j][2]);
+            a01[j] = fma2(w2[k], p01, a01[j]);
+            a2[j] = fmaf(w[k], p2, a2[j]);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int m = 0; m < 3; ++m) sh[m][r][q0 + j] = acc[j][m];
+      for (int j = 0; j < 4; ++j) {
+        float e0, e1;
+        unpack2(a01[j], e0, e1);
+        sh[0][r][q0 + j] = e0; sh[1][r][q0 + j] = e1; sh[2][r][q0 + j] = a2[j];
+      }
     }
     __syncthreads();
-    float vacc[4][3];
+    f32x2 v01[4];
+    float v2[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int m = 0; m < 3; ++m) vacc[j][m] = 0.f;
+    for (int j = 0; j < 4; ++j) { v01[j] = 0ull; v2[j] = 0.f; }
 #pragma unroll
     for (int t = 0; t < 14; ++t) {
-      const float v0 = sh[0][4 * warp + t][lane], v1 = sh[1][4 * warp + t][lane], v2 = sh[2][4 * warp + t][lane];
+      const f32x2 p01 = pack2(sh[0][4 * warp + t][lane], sh[1][4 * warp + t][lane]);
+      const float p2 = sh[2][4 * warp + t][lane];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = t - j;
         if (k >= 0 && k < 11) {
-          vacc[j][0] = fmaf(w[k], v0, vacc[j][0]);
-          vacc[j][1] = fmaf(w[k], v1, vacc[j][1]);
-          vacc[j][2] = fmaf(w[k], v2, vacc[j][2]);
+          v01[j] = fma2(w2[k], p01, v01[j]);
+          v2[j] = fmaf(w[k], p2, v2[j]);
         }
       }
     }
@@ -286,7 +319,9 @@ __global__ void __launch_bounds__(kLossThreads) l1_ssim_bwd_kernel(const float* 
     for (int k = 0; k < 4; ++k) {
       const int py = 4 * warp + k, px = lane;
       const int y = y0 + py, x = x0 + px;
-      const float gA = vacc[k][0], gB = vacc[k][1], gC = vacc[k][2];
+      float gA, gB;
+      unpack2(v01[k], gA, gB);
+      const float gC = v2[k];
       if (y < H && x < W) {
         const size_t o = img_off + ((size_t)y * W + x) * 3 + c;
         const float xv = pred[o], yv = target[o];

@@ -35,6 +35,20 @@ for n, W, H, ls in ((3000, 97, 71, -3.0), (20000, 200, 136, -3.6)):
         color = b200gs.evaluate_sh(q["f_dc"], q["f_rest"], q["pos"], c2w)
         band = b200gs.render(q["pos"], color, q["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
                              tile_rows=(1, 3))
+        # narrow bands (select + project + compact route, <= 35 % of the rows), fused and unfused, incl. the last ragged row
+        rows = (H + 15) // 16
+        full = b200gs.render(q["pos"], color, q["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        acc = torch.zeros_like(full)
+        for b in range(rows):
+            color = b200gs.evaluate_sh(q["f_dc"], q["f_rest"], q["pos"], c2w)
+            acc += b200gs.render(q["pos"], color, q["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
+                                 tile_rows=(b, b + 1))
+        assert torch.equal(acc, full), "bands of one tile row do not add up to the full frame"
+        one = b200gs.render(q["pos"], color * 1.0, q["opacity_raw"], sigma * 1.0, c2w, H, W, cam["fx"], cam["fy"], cam["cx"],
+                            cam["cy"], tile_rows=(rows - 1, rows))
+        from b200gs.dist import TileRowRenderer
+        tr = TileRowRenderer(H, W, q["pos"].device)
+        assert torch.equal(tr.render(q["pos"], color, q["opacity_raw"], sigma, c2w, cam["fx"], cam["fy"], cam["cx"], cam["cy"]), full)
         os.environ["B200GS_CAPACITY_MODE"] = "speculative"
         pipe = b200gs.RenderPipeline()
         ts = []
