@@ -127,6 +127,20 @@ SYMBOLS = {
 
 _lib = None
 
+_env_data = getattr(os.environ, "_data", None)
+
+
+def env(name: str, default=None):
+    """os.environ.get without the encode / decode round trip of every lookup (the render path reads a handful of
+    switches per frame, and they must stay live: tests flip them).  Falls back to os.environ.get."""
+    if _env_data is not None:
+        try:
+            v = _env_data.get(name.encode())
+            return default if v is None else v.decode()
+        except Exception:  # noqa: BLE001 - not the CPython posix layout
+            pass
+    return os.environ.get(name, default)
+
 
 class B200GSError(RuntimeError):
     pass

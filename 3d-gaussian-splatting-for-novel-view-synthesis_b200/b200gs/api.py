@@ -22,7 +22,7 @@ import weakref
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 # Tags (what a derived tensor was computed from) live in a side table keyed by the tensor's identity, NOT in the
 # tensor's __dict__: Python state on a tensor changes how torch pickles it (torch.save of a tagged tensor would
@@ -41,11 +41,11 @@ def _get_tag(t):
 
 
 def _fusion_enabled() -> bool:
-    return os.environ.get("B200GS_FUSE", "1") != "0"
+    return _lib.env("B200GS_FUSE", "1") != "0"
 
 
 def _lazy_enabled() -> bool:
-    return os.environ.get("B200GS_LAZY", "1") != "0"
+    return _lib.env("B200GS_LAZY", "1") != "0"
 
 
 _META_GETTERS = {"shape", "dtype", "device", "requires_grad", "ndim", "is_cuda", "layout", "is_leaf", "names",
@@ -196,7 +196,8 @@ def _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, fa
     the fused route (raw parameters) when the tags of `sigma` / `color` resolve, the tensors themselves otherwise."""
     ops._require_cuda(pos, "pos")
     for name, t in (("pos", pos), ("color", color), ("opacity_raw", opacity_raw), ("sigma", sigma)):
-        ops._require_f32(name, t)
+        if type(t) is not _Deferred:                   # a deferred tensor's dtype was checked when it was created
+            ops._require_f32(name, t)
     H, W = int(H), int(W)           # callers pass Python ints, 0-dim tensors (train.py:499) or floats
     cfg = ops.RenderConfig(H=H, W=W, fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), near=float(near),
                            far=float(far), pix_guard=float(pix_guard), T=int(T), min_conis=float(min_conis),
@@ -215,7 +216,7 @@ def _resolve(pos, color, opacity_raw, sigma, c2w, H, W, fx, fy, cx, cy, near, fa
         got = src.resolve() if src is not None else None
         if got is not None and got[2] is pos and (got[3] is c2w or torch.equal(got[3].to(c2w_d.device), c2w_d)):
             f_dc, f_rest = got[0], got[1]
-    strict = os.environ.get("B200GS_STRICT_OFFSCREEN", "1") != "0"
+    strict = _lib.env("B200GS_STRICT_OFFSCREEN", "1") != "0"
     return (pos, opacity_raw, scale_raw, q_raw, None if scale_raw is not None else _real(sigma),
             f_dc, f_rest, None if f_dc is not None else _real(color), c2w_d, cfg), strict
 

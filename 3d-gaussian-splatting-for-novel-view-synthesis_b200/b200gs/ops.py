@@ -27,7 +27,9 @@ def _require_cuda(t: torch.Tensor, name: str):
 def _require_f32(name: str, t: Optional[torch.Tensor]):
     """The reference is dtype-generic (its image follows pos.dtype, render.py:318); this path computes in fp32 only
     and refuses anything else rather than rounding it silently."""
-    if t is not None and t.is_floating_point() and t.dtype != torch.float32:
+    if t is None or t.dtype is torch.float32:          # the common case costs one attribute read
+        return
+    if t.is_floating_point():
         raise TypeError(f"b200gs: `{name}` is {t.dtype}; the CUDA path computes in float32 only (pass .float() tensors)")
 
 
@@ -191,7 +193,7 @@ class Frame:
         dev = self.device
         n = int(self.g.n)
         H, W = int(self.cfg.H), int(self.cfg.W)
-        mode = mode or os.environ.get("B200GS_CAPACITY_MODE", "speculative")
+        mode = mode or _lib.env("B200GS_CAPACITY_MODE", "speculative")
         stream = torch.cuda.current_stream(dev)
         st = ctypes.c_void_p(stream.cuda_stream)
         frame_bytes, _ = _sizes(lib, n, H, W, 0)
