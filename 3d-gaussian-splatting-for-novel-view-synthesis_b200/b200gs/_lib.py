@@ -17,6 +17,7 @@ OK = 0
 ERR_CAPACITY = -5
 TILE = 16
 CAM_KEEP_OUTSIDE_BAND = 1
+CAM_OVERLAPPED = 2
 
 
 class Gaussians(Structure):

@@ -212,6 +212,8 @@ class Frame:
                                      not image.is_contiguous() or image.device != dev):
             raise ValueError("out must be a contiguous [H,W,3] float32 tensor on the device of the Gaussians")
         self._hw_key = (dev.index, n, H, W)
+        if _blend_stream.get(dev.index) is not None:      # frame pipeline: the binning runs beside the previous blend
+            self.cam.flags |= _lib.CAM_OVERLAPPED
         spec_cap = _high_water.get(self._hw_key, 0) if mode == "speculative" else 0
         _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
                                              frame_bytes, None if spec_cap else stats_ptr, st), "render_project")

@@ -125,7 +125,7 @@ int super_dims(const gs::RenderParams& rp, int& super_x, int& super_y0, int& sup
 // where the supertile sort leaves its result: pass 0 writes the *_alt buffers, so odd pass counts end there
 struct SortedSuper { const uint32_t* keys; const uint32_t* vals; };
 SortedSuper sorted_super(void* isect_ws, const gs::IsectLayout& IL, int n_super_tiles) {
-  const int passes = (tile_bits(n_super_tiles) + 7) / 8;
+  const int passes = gs::sort_passes(0, tile_bits(n_super_tiles)).num;
   SortedSuper s;
   if (passes % 2 == 0) { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals); }
   else { s.keys = gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt); s.vals = gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt); }
@@ -453,50 +453,61 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   CU(cudaMemsetAsync(stats, 0, sizeof(b200gs_frame_stats), s));
   if (gi.n > 0) {
     bool hist_done = false;
-    CU(gs::radix_sort_prepare(gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, (uint32_t)gi.n, s));
+    CU(gs::radix_sort_prepare(gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, (uint32_t)gi.n, 0, rp.key_bits, s));
     uint32_t* hist = gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch));
-    uint32_t* keys_a = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2);
-    uint32_t* order = gs::ws_ptr<uint32_t>(frame_ws, L.order);
-    uint32_t* keys_b = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt);
-    uint32_t* order_b = gs::ws_ptr<uint32_t>(frame_ws, L.order_alt);
+    // the sorted (key, id) pairs always end in (sort_key_alt2, order); the radix passes ping-pong between that pair and
+    // (sort_key_alt, order_alt), so with an odd number of passes the source of the first pass sits in the second pair
+    const gs::DepthKeyPlan kp = gs::depth_key_plan(rp);
+    const bool odd = (kp.sp.num & 1) != 0;
+    uint32_t* dst_k = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2);
+    uint32_t* dst_v = gs::ws_ptr<uint32_t>(frame_ws, L.order);
+    uint32_t* tmp_k = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt);
+    uint32_t* tmp_v = gs::ws_ptr<uint32_t>(frame_ws, L.order_alt);
+    uint32_t* src_k = odd ? tmp_k : dst_k;         // where a band's compacted keys go (the first pass writes the other pair)
+    uint32_t* src_v = odd ? tmp_v : dst_v;
+    uint32_t* first_k = odd ? dst_k : tmp_k;
+    uint32_t* first_v = odd ? dst_v : tmp_v;
+    uint32_t* cand_k = gs::ws_ptr<uint32_t>(frame_ws, L.cand_key);
+    uint32_t* cand_v = gs::ws_ptr<uint32_t>(frame_ws, L.cand_id);
     char* band_scratch = gs::ws_ptr<char>(frame_ws, L.band_scratch);
     bool band_route = false;
     if (is_band(rp)) {
-      // a band of tile rows, raw parameters: select the candidates with a cheap test, project only those (the
-      // candidate ids / keys sit in the sort's ping-pong buffers, which pass 0 only overwrites after the compaction)
-      // (flag words in `offsets`, unused by the fused binning; candidate ids / keys in the sort's ping-pong buffers)
+      // a band of tile rows, raw parameters: select the candidates with a cheap test, project only those
+      // (flag words in `offsets`, unused by the fused binning)
       PCU(R_BAND_SELECT, 2, gs::launch_band_select(gi, cam->c2w, rp, frame_ws, L, gs::ws_ptr<uint32_t>(frame_ws, L.offsets),
-                                                   order_b, &stats->n_candidates, band_scratch, L.band_scratch_half,
+                                                   cand_v, &stats->n_candidates, band_scratch, L.band_scratch_half,
                                                    &band_route, s));
       if (band_route)
-        PCU(R_PREPROCESS_FWD, 1, gs::launch_band_project(gi, cam->c2w, rp, frame_ws, L, order_b, &stats->n_candidates, keys_b,
+        PCU(R_PREPROCESS_FWD, 1, gs::launch_band_project(gi, cam->c2w, rp, frame_ws, L, cand_v, &stats->n_candidates, cand_k,
                                                          hist, s));
       hist_done = band_route;
     }
     if (!band_route)
       PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, frame_ws, L, s, hist, &hist_done));
-    // S8: global depth order.  depth_key -> (sort_key_alt2, order) after 4 passes; ties keep index order.
+    // S8: global depth order.  depth_key -> (sort_key_alt2, order) after the radix passes; ties keep index order.
     int in_a = 0;
     if (is_band(rp)) {
       // a band keeps a fraction of the Gaussians: compact the live keys (stable) and sort those only
       if (band_route)
-        PCU(R_COMPACT, 1, gs::launch_compact_keys(keys_b, order_b, (uint32_t)gi.n, &stats->n_candidates, keys_a, order,
+        PCU(R_COMPACT, 1, gs::launch_compact_keys(cand_k, cand_v, (uint32_t)gi.n, &stats->n_candidates, src_k, src_v,
                                                   &stats->n_sorted, band_scratch + L.band_scratch_half,
                                                   L.band_scratch_half, s));
       else
         PCU(R_COMPACT, 1, gs::launch_compact_keys(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr, (uint32_t)gi.n,
-                                                  nullptr, keys_a, order, &stats->n_sorted,
+                                                  nullptr, src_k, src_v, &stats->n_sorted,
                                                   band_scratch + L.band_scratch_half, L.band_scratch_half, s));
-      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(keys_a, order, keys_a, order, keys_b, order_b,
-                               (uint32_t)gi.n, &stats->n_sorted, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch),
-                               L.scratch_bytes, &in_a, s, hist_done));
+      PCU(R_DEPTH_SORT, kp.sp.num + (hist_done ? 0 : 1),
+          gs::launch_radix_sort(src_k, src_v, src_k, src_v, first_k, first_v, (uint32_t)gi.n, &stats->n_sorted, 0, rp.key_bits,
+                                gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, &in_a, s, hist_done, kp.base,
+                                kp.max_key, (cam->flags & B200GS_CAM_OVERLAPPED) != 0));
     } else {
-      PCU(R_DEPTH_SORT, hist_done ? 4 : 5, gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr,
-                               keys_a, order, keys_b, order_b,
-                               (uint32_t)gi.n, nullptr, 0, 32, gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes,
-                               &in_a, s, hist_done));
+      PCU(R_DEPTH_SORT, kp.sp.num + (hist_done ? 0 : 1),
+          gs::launch_radix_sort(gs::ws_ptr<uint32_t>(frame_ws, L.depth_key), nullptr, src_k, src_v, first_k, first_v,
+                                (uint32_t)gi.n, nullptr, 0, rp.key_bits, gs::ws_ptr<void>(frame_ws, L.scratch),
+                                L.scratch_bytes, &in_a, s, hist_done, kp.base, kp.max_key,
+                                (cam->flags & B200GS_CAM_OVERLAPPED) != 0));
     }
-    if (!in_a) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
+    if ((in_a != 0) != !odd) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
   }
   if (stats_host) CU(publish_stats(stats, stats_host, s));
   return B200GS_OK;
@@ -548,11 +559,11 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
   if (stats_host) CU(publish_stats(stats, stats_host, s));
   if (stats_event) CU(cudaEventRecord((cudaEvent_t)stats_event, s));
   int in_a = 0;
-  PCU(R_TILE_SORT, (tile_bits(n_super_tiles) + 7) / 8,
+  PCU(R_TILE_SORT, gs::sort_passes(0, tile_bits(n_super_tiles)).num,
       gs::launch_radix_sort(keys, vals, keys, vals, gs::ws_ptr<uint32_t>(isect_ws, IL.keys_alt),
                             gs::ws_ptr<uint32_t>(isect_ws, IL.vals_alt), isect_capacity, &stats->n_super, 0,
                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes, &in_a, s,
-                            /*hist_ready=*/true));
+                            /*hist_ready=*/true, 0, 0xFFFFFFFFu, (cam->flags & B200GS_CAM_OVERLAPPED) != 0));
   const SortedSuper ss = sorted_super(isect_ws, IL, n_super_tiles);
   {
     ProfScope _scope(R_SPLIT, s, 2);

@@ -42,6 +42,8 @@ struct FrameLayout {
   size_t sort_key_alt2;   // u32[n]
   size_t order;           // u32[n]  Gaussian ids in depth order (sorted values)
   size_t order_alt;       // u32[n]
+  size_t cand_key;        // u32[n]  band frames: depth keys / ids of the band's candidates (before the compaction)
+  size_t cand_id;         // u32[n]
   size_t offsets;         // u32[n]  exclusive scan of super_touched in depth order
   size_t grad_acc;        // float[n*12] blend-backward accumulators (Mx,My,Mxx,Mxy,Myy,M0,r,g,b,+pad): moments of dL/dq
   size_t ranges;          // uint2[tiles] (start,end) per tile
@@ -69,6 +71,45 @@ struct FrameHeader {
   b200gs_frame_stats stats;   // 64 bytes
 };
 
+// Radix-sort pass plan (scan_sort.cu).  Digits are 8 bits wide, or 9 when that saves a pass (27-bit depth keys:
+// 3 passes); the global digit histograms a producer kernel may fill are laid out [pass][kSortMaxRadix].
+constexpr int kSortMaxPasses = 4;
+constexpr int kSortMaxRadix = 512;
+struct SortPasses {
+  int num;
+  int digit_bits;                  // 8 or 9: which instance of the pass kernel runs
+  int shift[kSortMaxPasses];
+  int bits[kSortMaxPasses];
+};
+SortPasses sort_passes(int begin_bit, int end_bit);
+
+// The depth sort's view of a depth key: sort key = min(float_bits(z) - base, max_key) (culled marker -> max_key), on the
+// key_bits low bits (RenderParams::key_base / key_bits).  The producers of the keys (preprocess kernels) use the same
+// plan to accumulate the digit histograms of all passes; the first radix pass applies the transform on load, so the
+// depth_key array itself keeps the raw float bits.
+struct DepthKeyPlan {
+  uint32_t base, max_key;
+  SortPasses sp;
+};
+inline DepthKeyPlan depth_key_plan(const RenderParams& rp) {
+  DepthKeyPlan kp;
+  kp.base = rp.key_base;
+  kp.max_key = rp.key_bits >= 32 ? 0xFFFFFFFFu : ((1u << rp.key_bits) - 1u);
+  kp.sp = sort_passes(0, rp.key_bits);
+  return kp;
+}
+__device__ __forceinline__ uint32_t depth_sort_key(uint32_t raw, uint32_t base, uint32_t max_key) {
+  const uint32_t k = raw - base;
+  return k < max_key ? k : max_key;
+}
+// s_dh: [kSortMaxPasses][kSortMaxRadix] shared-memory counters
+__device__ __forceinline__ void depth_hist_add(uint32_t* s_dh, const DepthKeyPlan& kp, uint32_t raw_key) {
+  const uint32_t k = depth_sort_key(raw_key, kp.base, kp.max_key);
+#pragma unroll
+  for (int p = 0; p < kSortMaxPasses; ++p)
+    if (p < kp.sp.num) atomicAdd(&s_dh[p * kSortMaxRadix + ((k >> kp.sp.shift[p]) & ((1u << kp.sp.bits[p]) - 1u))], 1u);
+}
+
 size_t scan_scratch_bytes(uint32_t n);
 size_t sort_scratch_bytes(uint32_t n);
 size_t scan_emit_scratch_bytes(uint32_t n);
@@ -90,6 +131,8 @@ inline FrameLayout frame_layout(int n, int H, int W) {
   L.sort_key_alt2 = take(N * 4);
   L.order = take(N * 4);
   L.order_alt = take(N * 4);
+  L.cand_key = take(N * 4);
+  L.cand_id = take(N * 4);
   L.offsets = take(N * 4);
   L.grad_acc = take(N * 12 * 4);
   L.ranges = take(tiles * 8);
@@ -144,8 +187,8 @@ struct GaussGrad {
 // histograms of the depth keys there and sets *hist_done (the depth sort then skips its histogram pass).
 cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const RenderParams& rp, void* frame_ws,
                                   const FrameLayout& L, cudaStream_t s, uint32_t* depth_hist = nullptr,
-                                  bool* hist_done = nullptr);
-cudaError_t radix_sort_prepare(void* scratch, size_t scratch_bytes, uint32_t n, cudaStream_t s);
+                                  bool* hist_done = nullptr);   // depth_hist: [kSortMaxPasses][kSortMaxRadix], plan = depth_key_plan(rp)
+cudaError_t radix_sort_prepare(void* scratch, size_t scratch_bytes, uint32_t n, int begin_bit, int end_bit, cudaStream_t s);
 uint32_t* radix_sort_hist(void* scratch);
 cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const float* c2w, const RenderParams& rp,
                                   void* frame_ws, const FrameLayout& L, cudaStream_t s);
@@ -162,7 +205,12 @@ cudaError_t launch_exclusive_scan(const uint32_t* in, const uint32_t* gather_idx
 cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_a,
                               uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
                               const uint32_t* n_dev, int begin_bit, int end_bit, void* scratch,
-                              size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready = false);
+                              size_t scratch_bytes, int* result_in_a, cudaStream_t s, bool hist_ready = false,
+                              uint32_t key_sub = 0, uint32_t key_max = 0xFFFFFFFFu, bool narrow = false);
+// narrow: small blocks (256 threads, 20 K registers, 38 KB) that fit beside a running blend kernel (frame pipeline);
+// otherwise 512-thread blocks of 7168 keys, one per SM at 1M keys
+// (key_sub, key_max): the first pass reads keys as min(key - key_sub, key_max) (depth keys, see DepthKeyPlan); the
+// ping-pong buffers then hold the transformed keys
 // n_dev (optional): device-side count of live entries at the front of `order` (band frames compact their keys)
 cudaError_t launch_scan_emit_super(int n, const uint32_t* n_dev, const uint32_t* order, const uint32_t* super_touched,
                                    const uint2* rect, int super_x, int super_y0, uint32_t capacity, uint32_t* keys,

@@ -10,6 +10,7 @@
 // Backward formulas are derived by hand (the reference has no backward code: autograd) and are
 // validated against the reference's autograd through tests/golden.
 #pragma once
+#include <string.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -36,6 +37,10 @@ struct RenderParams {          // by-value kernel argument; built on the host fr
   float chi2c, cut_e;          // blend gate terms: kBlendExpScale * chi2 and log2(alpha_cutoff) (see SplatRecord)
   int W, H, tiles_x, tiles_y;
   int row_begin, row_end;      // tile rows rendered by this rank [begin,end)
+  // depth-sort keys: a survivor has near < z < far and z > 0, so float_bits(z) - key_base fits key_bits bits with the
+  // all-ones value left for culled Gaussians (default near / far: 27 bits, three 9-bit radix passes instead of 4 x 8)
+  uint32_t key_base;
+  int key_bits;
 };
 
 // The reference multiplies fp32 tensors by Python floats: each scalar is rounded to fp32 at the op
@@ -64,6 +69,18 @@ inline void fill_render_params(RenderParams& rp, int H, int W, double fx, double
   rp.tiles_x = (W + 15) / 16;
   rp.tiles_y = (H + 15) / 16;
   rp.row_begin = 0; rp.row_end = rp.tiles_y;
+  {
+    auto fbits = [](float x) { uint32_t u; memcpy(&u, &x, 4); return u; };
+    const uint32_t lo = (rp.near_plane > 0.f) ? fbits(rp.near_plane) : 0u;          // z > max(near, 0)
+    const uint32_t hi = (rp.far_plane > 0.f && rp.far_plane <= 3.0e38f) ? fbits(rp.far_plane) : 0x7F800000u;
+    rp.key_base = 0; rp.key_bits = 32;
+    if (hi > lo) {
+      const uint32_t span = hi - lo;                     // live keys - lo are < span; the culled marker must exceed them
+      int b = 1;
+      while (b < 32 && ((1u << b) - 1u) < span) ++b;
+      if (b < 32) { rp.key_base = lo; rp.key_bits = b; }
+    }
+  }
 }
 
 struct Pose {                  // derived from c2w (utils.py:25-29, render.py:156-157)

@@ -431,16 +431,16 @@ __global__ void __launch_bounds__(kPreBlock) band_project_kernel(GaussIn g, cons
                                                                  FrameView f, const uint32_t* __restrict__ cand_ids,
                                                                  const uint32_t* __restrict__ n_cand,
                                                                  uint32_t* __restrict__ cand_key,
-                                                                 uint32_t* __restrict__ depth_hist) {
+                                                                 uint32_t* __restrict__ depth_hist, DepthKeyPlan kp) {
   constexpr int kShStride = 49;                  // 3 + 45 coefficients, odd stride: conflict-free row reads
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
-  __shared__ uint32_t s_dh[4][256];
+  __shared__ uint32_t s_dh[kSortMaxPasses * kSortMaxRadix];
   __shared__ float s_sh[kPreBlock / 32][32][kShStride];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 16) s_c2w[tid] = c2w[tid];
   if (tid == 0) s_tiles = 0;
-  for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
+  for (int i = tid; i < kSortMaxPasses * kSortMaxRadix; i += kPreBlock) s_dh[i] = 0;
   __syncthreads();
   const Pose ps = make_pose(s_c2w);
   const uint32_t total = *n_cand;
@@ -526,10 +526,7 @@ __global__ void __launch_bounds__(kPreBlock) band_project_kernel(GaussIn g, cons
     f.rect[i] = make_uint2((uint32_t)o.tu0 | ((uint32_t)o.tu1 << 16), (uint32_t)tv0 | ((uint32_t)tv1 << 16));
     f.super_touched[i] = (uint32_t)((o.tu1 / kSuperX - o.tu0 / kSuperX + 1) * (tv1 / kSuperY - tv0 / kSuperY + 1));
     tiles_sum += (uint32_t)tiles;
-    if (depth_hist) {
-      atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
-      atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
-    }
+    if (depth_hist) depth_hist_add(s_dh, kp, dk);
     }
   }
   const uint32_t wv = __reduce_add_sync(0xffffffffu, vis_count), w7 = __reduce_add_sync(0xffffffffu, s7_count);
@@ -542,8 +539,8 @@ __global__ void __launch_bounds__(kPreBlock) band_project_kernel(GaussIn g, cons
   __syncthreads();
   if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
   if (depth_hist)
-    for (int i = tid; i < 4 * 256; i += kPreBlock) {
-      const uint32_t c = (&s_dh[0][0])[i];
+    for (int i = tid; i < kSortMaxPasses * kSortMaxRadix; i += kPreBlock) {
+      const uint32_t c = s_dh[i];
       if (c) atomicAdd(&depth_hist[i], c);
     }
 }
@@ -551,16 +548,16 @@ __global__ void __launch_bounds__(kPreBlock) band_project_kernel(GaussIn g, cons
 // (full frames only: a band of tile rows goes through band_select_kernel + band_project_kernel below)
 __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g, const float* __restrict__ c2w,
                                                                        RenderParams rp, FrameView f, int n_chunks,
-                                                                       uint32_t* __restrict__ depth_hist) {
+                                                                       uint32_t* __restrict__ depth_hist, DepthKeyPlan kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PreStage* stage = reinterpret_cast<PreStage*>(smem_raw);       // [2]
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ float s_c2w[16];
   __shared__ uint32_t s_tiles;
-  __shared__ uint32_t s_dh[4][256];      // digit histograms of the depth keys (the depth sort's 4 passes)
+  __shared__ uint32_t s_dh[kSortMaxPasses * kSortMaxRadix];      // digit histograms of the depth keys (all passes of the depth sort)
   const int tid = threadIdx.x;
   if (tid < 16) s_c2w[tid] = c2w[tid];
-  for (int i = tid; i < 4 * 256; i += kPreBlock) (&s_dh[0][0])[i] = 0;
+  for (int i = tid; i < kSortMaxPasses * kSortMaxRadix; i += kPreBlock) s_dh[i] = 0;
   if (tid == 0) {
     s_tiles = 0;
     mbar_init(&s_bar[0], 1);
@@ -623,8 +620,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
       vis_count += vis ? 1u : 0u;
       if (depth_hist) {            // (full frames only: a band's sort builds its own histograms after the compaction)
         const uint32_t dk = vis ? __float_as_uint(o.z) : kCulledKey;
-        atomicAdd(&s_dh[0][dk & 255u], 1u); atomicAdd(&s_dh[1][(dk >> 8) & 255u], 1u);
-        atomicAdd(&s_dh[2][(dk >> 16) & 255u], 1u); atomicAdd(&s_dh[3][dk >> 24], 1u);
+        depth_hist_add(s_dh, kp, dk);
       }
       if (!vis) {
         f.depth_key[i] = kCulledKey;
@@ -663,8 +659,8 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_tma_kernel(GaussIn g
   __syncthreads();
   if (tid == 0 && s_tiles) atomicAdd(&f.stats->n_isect, s_tiles);
   if (depth_hist)
-    for (int i = tid; i < 4 * 256; i += kPreBlock) {
-      const uint32_t c = (&s_dh[0][0])[i];
+    for (int i = tid; i < kSortMaxPasses * kSortMaxRadix; i += kPreBlock) {
+      const uint32_t c = s_dh[i];
       if (c) atomicAdd(&depth_hist[i], c);
     }
 }
@@ -975,7 +971,7 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
       cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
     }
     const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
-    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist);
+    preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist, depth_key_plan(rp));
     if (hist_done) *hist_done = depth_hist != nullptr;
     return cudaGetLastError();
   }
@@ -1038,7 +1034,7 @@ cudaError_t launch_band_project(const GaussIn& g, const float* c2w, const Render
   }
   const int want = ceil_div(g.n, kPreBlock);
   const int grid = want < 5 * sm_count ? want : 5 * sm_count;     // 92 registers x 128 threads: 5 resident CTAs per SM
-  band_project_kernel<<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f, cand_ids, n_cand, cand_key, depth_hist);
+  band_project_kernel<<<grid, kPreBlock, 0, s>>>(g, c2w, rp, f, cand_ids, n_cand, cand_key, depth_hist, depth_key_plan(rp));
   return cudaGetLastError();
 }
 

@@ -76,6 +76,10 @@ typedef struct b200gs_camera {
  * the rasterizer writes the band's pixels only and leaves the rest of image_out alone - image_out may then be the
  * frame buffer of another GPU (peer-mapped memory), into which every rank stores its own band. */
 #define B200GS_CAM_KEEP_OUTSIDE_BAND 1
+/* The frame's binning kernels are queued beside other work of the caller (frame pipelining: the previous frame's blend
+ * is still running): the radix sorts then use their small block shape (256 threads, 20 K registers, 38 KB of shared
+ * memory), which finds room on a busy SM, instead of one large block per SM. */
+#define B200GS_CAM_OVERLAPPED 2
 
 /* Gradients written by b200gs_render_backward.  Non-null members are OVERWRITTEN (dense, zero for
  * culled Gaussians).  Members for the path not in use must be NULL. */
