@@ -18,6 +18,7 @@ ERR_CAPACITY = -5
 TILE = 16
 CAM_KEEP_OUTSIDE_BAND = 1
 CAM_OVERLAPPED = 2
+CAM_ROUTED = 4
 
 
 class Gaussians(Structure):
@@ -67,6 +68,11 @@ class PeerTensor(Structure):
     _fields_ = [("grad", c_void_p), ("numel", ctypes.c_int64), ("lr", c_double), ("step", c_int32), ("clip", c_int32)]
 
 
+class Route(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("seg_capacity", c_uint32), ("band_row", c_int32 * (MAX_PEERS + 1)),
+                ("band_ws", c_void_p * MAX_PEERS), ("band_ws_bytes", c_size_t)]
+
+
 class FrameStats(Structure):
     _fields_ = [("n_isect", c_uint32), ("n_visible", c_uint32), ("overflow", c_uint32),
                 ("n_in_frustum", c_uint32), ("n_super", c_uint32), ("n_sorted", c_uint32), ("n_candidates", c_uint32), ("reserved", c_uint32 * 9)]
@@ -111,6 +117,8 @@ SYMBOLS = {
                                       c_void_p, c_void_p]),
     "b200gs_peer_allreduce": (c_int, [POINTER(PeerGroup), POINTER(PeerLayout), POINTER(PeerTensor), c_int32,
                                       POINTER(c_uint32), c_void_p]),
+    "b200gs_route_project_slice": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, POINTER(Route), c_void_p]),
+    "b200gs_render_project_routed": (c_int, [POINTER(Camera), POINTER(Route), c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),
     "b200gs_debug_export_lists": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_uint32, c_int32, c_int32, c_int32,

@@ -186,8 +186,8 @@ class TileRowRenderer:
     `weights` (one number per tile row, e.g. intersections per row of an earlier frame - `row_weights()`) balances the
     bands.  One process (no process group) renders the whole frame locally.  Forward only."""
 
-    def __init__(self, H: int, W: int, device, group=None, root: int = 0, weights=None):
-        from . import peer
+    def __init__(self, H: int, W: int, device, group=None, root: int = 0, weights=None, routed=None):
+        from . import _lib, peer
         self.H, self.W, self.device, self.group, self.root = int(H), int(W), torch.device(device), group, int(root)
         self.n_rows = (self.H + 15) // 16
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -200,6 +200,12 @@ class TileRowRenderer:
         off = self.image.data_ptr() - self.area.buf.data_ptr()
         self.root_ptr = int(self.area.c_group.area[self.root]) + off
         self._buffers = [None, None]      # frame / intersection workspaces, reused from frame to frame
+        # routed ("sort-middle") bands: the per-Gaussian work is divided over the ranks as well, see _render_routed
+        if routed is None:
+            routed = _lib.env("B200GS_TILE_ROWS_ROUTED", "1") != "0"
+        self.routed = bool(routed) and self.world > 1
+        self._route = None                # (b200gs_route, N it was sized for, workspace area, band workspace view)
+        self._slice_ws = [None]
 
     def set_weights(self, weights=None):
         self.bands = shard_tile_rows(self.n_rows, self.world, weights)
@@ -216,6 +222,8 @@ class TileRowRenderer:
                                    kw.get("alpha_cutoff", 1 / 128.), (begin, end) if self.world > 1 else None)
             cfg = args[-1]
             cfg.out = self.image
+            if self.routed:
+                return self._render_routed(args)
             if self.world > 1:
                 cfg.keep_outside_band = True
                 cfg.out_ptr = self.root_ptr
@@ -224,6 +232,59 @@ class TileRowRenderer:
             frame.finish()
             if self.world > 1:
                 self.area.barrier()            # every band has landed in root's buffer
+        self.last_frame = frame
+        return image
+
+    # -- routed bands ----------------------------------------------------------------------------------------------
+    def _ensure_route(self, n: int):
+        """Band workspaces in peer-visible memory, sized for `n` Gaussians (collective when it has to allocate)."""
+        from . import _lib, ops, peer
+        if self._route is not None and self._route[1] >= n:
+            return self._route
+        self._route = None
+        per = max(32, -(-((n + self.world - 1) // self.world) // 32) * 32)     # slice length: a multiple of 32 entries
+        lib = _lib.load()
+        ws_bytes, _ = ops._sizes(lib, self.world * per, self.H, self.W, 0)
+        area = peer.PeerArea([(ws_bytes + 3) // 4], self.device, group=self.group, multicast=False)
+        ws = area.flat_params.view(torch.uint8)[:ws_bytes]
+        off = ws.data_ptr() - area.buf.data_ptr()
+        route = _lib.Route(world=self.world, rank=self.rank, seg_capacity=per, band_ws_bytes=ws_bytes)
+        for q in range(self.world):
+            route.band_ws[q] = int(area.c_group.area[q]) + off
+        self._route = (route, self.world * per, area, ws, per)
+        self._buffers[0] = ws             # the band's frame workspace IS the routed-to workspace
+        return self._route
+
+    def _render_routed(self, args):
+        """Sort-middle: this rank projects Gaussians [rank * N/p, (rank+1) * N/p) with the full frame's camera and
+        writes every survivor's splat record into the workspace of each band its tile rect meets (peer stores, index
+        order); after a flag barrier it depth-sorts, bins and blends what was routed to its own band.  Same per-tile
+        lists as the one-GPU frame, hence the same pixels."""
+        import copy
+        from . import ops
+        pos, cfg, c2w = args[0], args[-1], args[-2]
+        n = int(pos.shape[0])
+        route, _, area, ws, per = self._ensure_route(n)
+        for q, (b, _e) in enumerate(self.bands):          # shard_tile_rows: contiguous, band q = [cut q, cut q+1)
+            route.band_row[q] = min(b, self.n_rows)
+        route.band_row[self.world] = self.n_rows
+        full = copy.copy(cfg)
+        full.tile_row_begin = full.tile_row_end = 0
+        full.out, full.out_ptr, full.keep_outside_band = None, 0, False
+        cfg.keep_outside_band = True
+        cfg.out_ptr = self.root_ptr
+        lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        # root has consumed the previous frame and every rank has finished its previous band: frame buffer and band
+        # workspaces may be overwritten
+        self.area.barrier()
+        keep = ops.route_project_slice(*args[:8], c2w, full, route, lo, hi, self._slice_ws)
+        self.area.barrier()                # every segment of every band has landed
+        with torch.cuda.device(self.device):
+            frame = ops.RoutedFrame(route, cfg, c2w, self.device)
+            frame.keep = keep
+            image = frame.launch("speculative", self._buffers)
+        frame.finish()
+        self.area.barrier()                # every band has landed in root's buffer
         self.last_frame = frame
         return image
 

@@ -215,8 +215,7 @@ class Frame:
         if _blend_stream.get(dev.index) is not None:      # frame pipeline: the binning runs beside the previous blend
             self.cam.flags |= _lib.CAM_OVERLAPPED
         spec_cap = _high_water.get(self._hw_key, 0) if mode == "speculative" else 0
-        _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
-                                             frame_bytes, None if spec_cap else stats_ptr, st), "render_project")
+        self._project(lib, frame_bytes, None if spec_cap else stats_ptr, st)
         self._unchecked = None
         if spec_cap:
             # the whole frame is queued; the host will only wait until the counters are final (end of the binning
@@ -230,6 +229,10 @@ class Frame:
                             image, stats_ptr, st)
             self._stats_pending = (stream, stats_np)     # n_super is only known after rasterize
         return image
+
+    def _project(self, lib, frame_bytes, stats_ptr, st):
+        _lib.check(lib.b200gs_render_project(ctypes.byref(self.g), ctypes.byref(self.cam), _ptr(self.frame_ws),
+                                             frame_bytes, stats_ptr, st), "render_project")
 
     def finish(self):
         """Speculative frames: wait for the frame's counters (NOT for the frame) and rasterize again with exact
@@ -364,6 +367,43 @@ def _gaussians(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color):
                   sigma=None if sg_ is None else sg_.data_ptr(), f_dc=None if dc_ is None else dc_.data_ptr(),
                   f_rest=None if fr_ is None else fr_.data_ptr(), color=None if col_ is None else col_.data_ptr())
     return g, keep
+
+
+class RoutedFrame(Frame):
+    """A band of a tile-row sharded frame whose splat records were routed into `band_ws` by the ranks that projected
+    them (b200gs_route_project_slice; dist.TileRowRenderer): the projection step is the gather + depth sort of the routed
+    entries, everything behind it is the ordinary frame.  Entry ids are positions in the band workspace; forward only."""
+
+    def __init__(self, route, cam_cfg: RenderConfig, c2w: torch.Tensor, device):
+        g = Gaussians(n=int(route.world) * int(route.seg_capacity))
+        super().__init__(g, None, cam_cfg, c2w, device)
+        self.route = route
+        self.cam.flags |= _lib.CAM_ROUTED
+
+    def _project(self, lib, frame_bytes, stats_ptr, st):
+        _lib.check(lib.b200gs_render_project_routed(ctypes.byref(self.cam), ctypes.byref(self.route), _ptr(self.frame_ws),
+                                                    frame_bytes, stats_ptr, st), "render_project_routed")
+
+    def backward(self, grad_image, grads):
+        raise _lib.B200GSError("routed band frames are forward only")
+
+
+def route_project_slice(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg: RenderConfig, route,
+                        begin: int, end: int, buffers):
+    """Source role of a routed tile-row frame: project Gaussians [begin, end) with the FULL frame's camera and route the
+    survivors into the band workspaces named by `route`.  buffers = [slice workspace or None] (reused between frames)."""
+    lib = _lib.load()
+    sl = lambda t: None if t is None else t[begin:end]
+    g, keep = _gaussians(sl(pos), sl(opacity_raw), sl(scale_raw), sl(q_raw), sl(sigma), sl(f_dc), sl(f_rest), sl(color))
+    dev = pos.device
+    with torch.cuda.device(dev):
+        cam = cfg.to_c(c2w)
+        frame_bytes, _ = _sizes(lib, int(g.n), int(cfg.H), int(cfg.W), 0)
+        if buffers[0] is None or buffers[0].numel() < frame_bytes:
+            buffers[0] = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200gs_route_project_slice(ctypes.byref(g), ctypes.byref(cam), _ptr(buffers[0]), buffers[0].numel(),
+                                                  ctypes.byref(route), _stream(dev)), "route_project_slice")
+    return keep
 
 
 def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg, buffers=None):

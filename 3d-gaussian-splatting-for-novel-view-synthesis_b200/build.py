@@ -32,6 +32,7 @@ SOURCES = {
     "loss.cu": [],
     "optim.cu": [],
     "peer.cu": [],
+    "route.cu": [],
     "densify.cu": [],
     "api.cu": [],
 }

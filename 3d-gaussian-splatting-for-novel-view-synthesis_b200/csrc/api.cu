@@ -30,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_ROUTE, R_GATHER, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select", "route_slice", "gather_routed"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -110,6 +110,10 @@ int make_gauss(const b200gs_gaussians* g, gs::GaussIn& o) {
 }
 
 bool is_band(const gs::RenderParams& rp) { return rp.row_begin > 0 || rp.row_end < rp.tiles_y; }
+// frames whose depth-sorted ids are a compacted prefix counted on the device (stats->n_sorted)
+bool is_compacted(const gs::RenderParams& rp, const b200gs_camera* cam) {
+  return is_band(rp) || (cam->flags & B200GS_CAM_ROUTED) != 0;
+}
 
 // Supertile grid of the rows this frame renders: super_x columns, rows [super_y0, super_y0 + super_y).  A band numbers
 // its supertiles from its own first row, so that the binning sort handles ceil(log2(#band supertiles)) bits (one radix
@@ -513,6 +517,84 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   return B200GS_OK;
 }
 
+static int check_route(const b200gs_route* r, const char* who) {
+  if (!r || r->world < 1 || r->world > B200GS_MAX_PEERS || r->rank < 0 || r->rank >= r->world || r->seg_capacity == 0)
+    return fail(B200GS_ERR_ARG, std::string(who) + ": bad route (world, rank or seg_capacity)");
+  if ((unsigned long long)r->world * r->seg_capacity > 0x7FFFFFFFull)
+    return fail(B200GS_ERR_ARG, std::string(who) + ": world * seg_capacity does not fit 31 bits");
+  for (int q = 0; q < r->world; ++q) {
+    if (!r->band_ws[q]) return fail(B200GS_ERR_ARG, std::string(who) + ": unmapped band workspace");
+    if (r->band_row[q + 1] < r->band_row[q] || r->band_row[q] < 0)
+      return fail(B200GS_ERR_ARG, std::string(who) + ": band rows must be non-decreasing");
+  }
+  return B200GS_OK;
+}
+
+int b200gs_route_project_slice(const b200gs_gaussians* g_slice, const b200gs_camera* cam, void* slice_ws,
+                               size_t slice_bytes, const b200gs_route* route, void* stream) {
+  gs::RenderParams rp;
+  gs::GaussIn gi;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  rc = make_gauss(g_slice, gi);
+  if (rc) return rc;
+  if ((rc = check_route(route, "route_project_slice"))) return rc;
+  if (is_band(rp)) return fail(B200GS_ERR_ARG, "route_project_slice: the camera must describe the full frame");
+  if ((uint32_t)gi.n > route->seg_capacity) return fail(B200GS_ERR_CAPACITY, "route_project_slice: slice larger than a segment");
+  if (!slice_ws) return fail(B200GS_ERR_ARG, "slice_ws is null");
+  const gs::FrameLayout SL = gs::frame_layout(gi.n, rp.H, rp.W);
+  const gs::FrameLayout BL = gs::frame_layout((int)(route->world * route->seg_capacity), rp.H, rp.W);
+  if (slice_bytes < SL.total) return fail(B200GS_ERR_WORKSPACE, "slice workspace too small");
+  if (route->band_ws_bytes < BL.total) return fail(B200GS_ERR_WORKSPACE, "band workspace too small");
+  // the counters of the routing pass live in the slice workspace's (unused) sort sections [order, grad_acc)
+  const size_t scratch_bytes = SL.grad_acc - SL.order;
+  if (scratch_bytes < gs::route_scratch_bytes(gi.n, route->world)) return fail(B200GS_ERR_WORKSPACE, "route scratch");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(gs::ws_ptr<b200gs_frame_stats>(slice_ws, SL.header), 0, sizeof(b200gs_frame_stats), s));
+  if (gi.n > 0)       // an empty slice (more ranks than 32-entry groups) still reports its zero totals to every band
+    PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, slice_ws, SL, s, nullptr, nullptr));
+  PCU(R_ROUTE, 3, gs::launch_route_slice(gi.n, slice_ws, SL, route, BL, gs::ws_ptr<void>(slice_ws, SL.order),
+                                         scratch_bytes, s));
+  return B200GS_OK;
+}
+
+int b200gs_render_project_routed(const b200gs_camera* cam, const b200gs_route* route, void* frame_ws,
+                                 size_t frame_bytes, b200gs_frame_stats* stats_host, void* stream) {
+  gs::RenderParams rp;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  if ((rc = check_route(route, "render_project_routed"))) return rc;
+  if (!(cam->flags & B200GS_CAM_ROUTED)) return fail(B200GS_ERR_ARG, "render_project_routed: camera without B200GS_CAM_ROUTED");
+  if (!frame_ws) return fail(B200GS_ERR_ARG, "frame_ws is null");
+  const int n = (int)(route->world * route->seg_capacity);
+  const gs::FrameLayout L = gs::frame_layout(n, rp.H, rp.W);
+  if (frame_bytes < L.total) return fail(B200GS_ERR_WORKSPACE, "frame workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  b200gs_frame_stats* stats = gs::ws_ptr<b200gs_frame_stats>(frame_ws, L.header);
+  CU(cudaMemsetAsync(stats, 0, sizeof(b200gs_frame_stats), s));
+  CU(gs::radix_sort_prepare(gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, (uint32_t)n, 0, rp.key_bits, s));
+  uint32_t* hist = gs::radix_sort_hist(gs::ws_ptr<void>(frame_ws, L.scratch));
+  const gs::DepthKeyPlan kp = gs::depth_key_plan(rp);
+  const bool odd = (kp.sp.num & 1) != 0;            // see b200gs_render_project: the result ends in (sort_key_alt2, order)
+  uint32_t* dst_k = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt2);
+  uint32_t* dst_v = gs::ws_ptr<uint32_t>(frame_ws, L.order);
+  uint32_t* tmp_k = gs::ws_ptr<uint32_t>(frame_ws, L.sort_key_alt);
+  uint32_t* tmp_v = gs::ws_ptr<uint32_t>(frame_ws, L.order_alt);
+  uint32_t* src_k = odd ? tmp_k : dst_k;
+  uint32_t* src_v = odd ? tmp_v : dst_v;
+  uint32_t* first_k = odd ? dst_k : tmp_k;
+  uint32_t* first_v = odd ? dst_v : tmp_v;
+  PCU(R_GATHER, 1, gs::launch_gather_routed(route->world, route->seg_capacity, frame_ws, L, src_k, src_v, hist, kp, s));
+  int in_a = 0;
+  PCU(R_DEPTH_SORT, kp.sp.num,
+      gs::launch_radix_sort(src_k, src_v, src_k, src_v, first_k, first_v, (uint32_t)n, &stats->n_sorted, 0, rp.key_bits,
+                            gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, &in_a, s, /*hist_ready=*/true, kp.base,
+                            kp.max_key, (cam->flags & B200GS_CAM_OVERLAPPED) != 0));
+  if ((in_a != 0) != !odd) return fail(B200GS_ERR_ARG, "internal: depth sort result buffer");
+  if (stats_host) CU(publish_stats(stats, stats_host, s));
+  return B200GS_OK;
+}
+
 int b200gs_render_rasterize(const b200gs_camera* cam, int32_t n, void* frame_ws, size_t frame_bytes, void* isect_ws,
                             size_t isect_bytes, uint32_t isect_capacity, float* image_out,
                             b200gs_frame_stats* stats_host, void* stream) {
@@ -548,9 +630,9 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
   uint32_t* lists = gs::ws_ptr<uint32_t>(isect_ws, IL.lists);
   // a frame that overflowed a speculative capacity is rasterized again with exact buffers: start clean
   CU(cudaMemsetAsync(&stats->overflow, 0, sizeof(uint32_t), s));
-  if (is_band(rp))     // the split kernels only visit the band's supertiles: every other tile has an empty list
+  if (is_compacted(rp, cam))     // the split kernels only visit the band's supertiles: every other tile has an empty list
     CU(cudaMemsetAsync(gs::ws_ptr<uint2>(frame_ws, L.ranges), 0, (size_t)rp.tiles_x * rp.tiles_y * sizeof(uint2), s));
-  PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, is_band(rp) ? &stats->n_sorted : nullptr, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
+  PCU(R_EMIT, 1, gs::launch_scan_emit_super(n, is_compacted(rp, cam) ? &stats->n_sorted : nullptr, gs::ws_ptr<uint32_t>(frame_ws, L.order), gs::ws_ptr<uint32_t>(frame_ws, L.super_touched),
                                             gs::ws_ptr<uint2>(frame_ws, L.rect), super_x, super_y0, isect_capacity, keys, vals, stats,
                                             tile_bits(n_super_tiles), gs::ws_ptr<void>(isect_ws, IL.scratch), IL.scratch_bytes,
                                             gs::ws_ptr<void>(frame_ws, L.scratch), L.scratch_bytes, s));

@@ -70,6 +70,10 @@ struct IsectLayout {
 struct FrameHeader {
   b200gs_frame_stats stats;   // 64 bytes
 };
+// routed band frames (route.cu): per source rank (entries, intersections) of the rank's segment, uint2[B200GS_MAX_PEERS],
+// inside the 256-byte header section behind the statistics
+constexpr size_t kRouteInOffset = 64;
+static_assert(kRouteInOffset + B200GS_MAX_PEERS * 8 <= 256, "route_in must fit the header section");
 
 // Radix-sort pass plan (scan_sort.cu).  Digits are 8 bits wide, or 9 when that saves a pass (27-bit depth keys:
 // 3 passes); the global digit histograms a producer kernel may fill are laid out [pass][kSortMaxRadix].
@@ -257,6 +261,13 @@ cudaError_t launch_densify_plan(int n, const float* opacity_raw, const float* sc
                                 cudaStream_t s);
 cudaError_t launch_densify_apply(int n, const void* ws, const float* const in[6], float* const out[6], const float* noise,
                                  cudaStream_t s);
+
+// route.cu: tile-row bands with the per-Gaussian work divided over the ranks (project a slice, route the records)
+size_t route_scratch_bytes(int n, int world);
+cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& SL, const b200gs_route* route,
+                               const FrameLayout& BL, void* scratch, size_t scratch_bytes, cudaStream_t s);
+cudaError_t launch_gather_routed(int world, uint32_t seg_cap, void* band_ws, const FrameLayout& BL, uint32_t* out_keys,
+                                 uint32_t* out_ids, uint32_t* depth_hist, const DepthKeyPlan& kp, cudaStream_t s);
 
 // peer.cu: data-parallel optimizer step over NVLink peer memory
 int peer_layout_compute(const int64_t* numel, int n_tensors, int world, b200gs_peer_layout* out);

@@ -80,6 +80,10 @@ typedef struct b200gs_camera {
  * is still running): the radix sorts then use their small block shape (256 threads, 20 K registers, 38 KB of shared
  * memory), which finds room on a busy SM, instead of one large block per SM. */
 #define B200GS_CAM_OVERLAPPED 2
+/* The frame workspace already holds the band's splat records, routed there by b200gs_route_project_slice (set by
+ * b200gs_render_project_routed's callers for the rasterize call of the same frame): the rasterizer then takes the
+ * number of live entries from the device-side counter whatever the band's extent. */
+#define B200GS_CAM_ROUTED 4
 
 /* Gradients written by b200gs_render_backward.  Non-null members are OVERWRITTEN (dense, zero for
  * culled Gaussians).  Members for the path not in use must be NULL. */
@@ -306,6 +310,33 @@ int b200gs_peer_adam_step(const b200gs_peer_group* group, const b200gs_peer_layo
  * every tensors[t].grad is replaced by the sum over the ranks. */
 int b200gs_peer_allreduce(const b200gs_peer_group* group, const b200gs_peer_layout* layout,
                           const b200gs_peer_tensor* tensors, int32_t n_tensors, uint32_t* epoch, void* stream);
+
+/* ---- Tile-row bands with the per-Gaussian work divided over the ranks ("sort-middle") --------------------------------
+ * The reference projects every Gaussian once (render.py:104-258) and then loops over independent tiles
+ * (render.py:325-399).  With one process per GPU, rank r projects the Gaussians [r*N/p, (r+1)*N/p) and writes each
+ * survivor's splat record, depth key and tile rect (clamped to the band) into the frame workspace of every rank whose
+ * band of tile rows the rect meets - over peer-mapped memory, in index order, into segment r of that workspace
+ * (seg_capacity entries per source rank, >= the largest slice, so nothing can overflow).  After a cross-GPU barrier
+ * (b200gs_peer_barrier) each rank continues its band with b200gs_render_project_routed + b200gs_render_rasterize*
+ * (camera flags B200GS_CAM_ROUTED, usually B200GS_CAM_KEEP_OUTSIDE_BAND with image_out = the root's frame buffer).
+ * Band workspaces are laid out by b200gs_workspace_sizes(world * seg_capacity, H, W, ...); a routed entry's id is its
+ * position there.  Per-tile lists, and therefore the pixels, are those of the one-GPU frame bit for bit. */
+typedef struct b200gs_route {
+  int32_t world, rank;
+  uint32_t seg_capacity;                    /* entries per (source rank, band) segment */
+  int32_t band_row[B200GS_MAX_PEERS + 1];   /* band q = tile rows [band_row[q], band_row[q+1]) */
+  void* band_ws[B200GS_MAX_PEERS];          /* band q's frame workspace as mapped into THIS process */
+  size_t band_ws_bytes;
+} b200gs_route;
+/* Source role: project `g_slice` (this rank's slice; cam = the FULL frame, no tile-row range) into the private
+ * `slice_ws` (b200gs_workspace_sizes(g_slice->n, H, W, ...) bytes) and route the survivors. */
+int b200gs_route_project_slice(const b200gs_gaussians* g_slice, const b200gs_camera* cam, void* slice_ws,
+                               size_t slice_bytes, const b200gs_route* route, void* stream);
+/* Destination role, after the barrier: gathers the routed entries of this band (cam = the band's camera: tile-row
+ * range + B200GS_CAM_ROUTED) and depth-sorts them; the frame then continues with b200gs_render_rasterize* called with
+ * n = world * seg_capacity and the same camera.  Statistics: V = entries routed here, I = their intersections. */
+int b200gs_render_project_routed(const b200gs_camera* cam, const b200gs_route* route, void* frame_ws,
+                                 size_t frame_bytes, b200gs_frame_stats* stats_host, void* stream);
 
 /* Per-region CUDA-event profiling (bench.py's per-kernel table).  enable(1) starts recording an event
  * pair around every kernel group launched through this library; collect() synchronises the device,
