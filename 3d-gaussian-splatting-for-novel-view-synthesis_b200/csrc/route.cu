@@ -23,6 +23,7 @@
 namespace gs {
 
 constexpr int kRouteThreads = 256;
+constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kRouteScanThreads = 1024;
 
 struct RouteParams {                       // by-value kernel argument
@@ -42,39 +43,45 @@ __device__ __forceinline__ RouteHit route_test(bool live, int tv0, int tv1, int 
   return h;
 }
 
-// per (band, warp of 32 consecutive slice entries): how many entries go to the band, and their tile intersections there
+// per (band, block of kRouteThreads consecutive slice entries): how many entries go to the band, and their tile
+// intersections there
 __global__ void __launch_bounds__(kRouteThreads) route_count_kernel(uint32_t n, const uint32_t* __restrict__ depth_key,
                                                                     const uint2* __restrict__ rect, RouteParams rp,
-                                                                    uint32_t n_warps, uint32_t* __restrict__ counts,
+                                                                    uint32_t n_blocks, uint32_t* __restrict__ counts,
                                                                     uint32_t* __restrict__ tiles) {
+  __shared__ uint32_t s_c[B200GS_MAX_PEERS][kRouteWarps], s_t[B200GS_MAX_PEERS][kRouteWarps];
   const uint32_t i = blockIdx.x * kRouteThreads + threadIdx.x;
-  const uint32_t gw = i >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < n && depth_key[i] != kCulledKey;
   uint2 rc = make_uint2(0u, 0u);
   if (live) rc = rect[i];
   const int tu0 = rc.x & 0xFFFF, tu1 = rc.x >> 16, tv0 = rc.y & 0xFFFF, tv1 = rc.y >> 16;
-  if (gw >= n_warps) return;
   for (int b = 0; b < rp.world; ++b) {
     const RouteHit h = route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]);
     const uint32_t m = __ballot_sync(0xffffffffu, h.hit);
-    const uint32_t t = __reduce_add_sync(0xffffffffu, h.hit ? (uint32_t)((tu1 - tu0 + 1) * (h.hi - h.lo + 1)) : 0u);
-    if (lane == 0) {
-      counts[(size_t)b * n_warps + gw] = __popc(m);
-      tiles[(size_t)b * n_warps + gw] = t;
-    }
+    const uint32_t t = m ? __reduce_add_sync(0xffffffffu, h.hit ? (uint32_t)((tu1 - tu0 + 1) * (h.hi - h.lo + 1)) : 0u) : 0u;
+    if (lane == 0) { s_c[b][warp] = __popc(m); s_t[b][warp] = t; }
+  }
+  __syncthreads();
+  if (threadIdx.x < rp.world) {
+    const int b = threadIdx.x;
+    uint32_t c = 0, t = 0;
+#pragma unroll
+    for (int w = 0; w < kRouteWarps; ++w) { c += s_c[b][w]; t += s_t[b][w]; }
+    counts[(size_t)b * n_blocks + blockIdx.x] = c;
+    tiles[(size_t)b * n_blocks + blockIdx.x] = t;
   }
 }
 
-// one block per band: exclusive scan of the band's per-warp counts in place, totals into the band's header
-__global__ void __launch_bounds__(kRouteScanThreads) route_scan_kernel(uint32_t n_warps, uint32_t* __restrict__ counts,
+// one block per band: exclusive scan of the band's per-block counts in place, totals into the band's header
+__global__ void __launch_bounds__(kRouteScanThreads) route_scan_kernel(uint32_t n_blocks, uint32_t* __restrict__ counts,
                                                                        const uint32_t* __restrict__ tiles, RouteParams rp) {
   __shared__ uint32_t s_c[kRouteScanThreads / 32], s_t[kRouteScanThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* c = counts + (size_t)b * n_warps;
-  const uint32_t* t = tiles + (size_t)b * n_warps;
-  const uint32_t per = (n_warps + kRouteScanThreads - 1) / kRouteScanThreads;
-  const uint32_t i0 = min((uint32_t)tid * per, n_warps), i1 = min(i0 + per, n_warps);
+  uint32_t* c = counts + (size_t)b * n_blocks;
+  const uint32_t* t = tiles + (size_t)b * n_blocks;
+  const uint32_t per = (n_blocks + kRouteScanThreads - 1) / kRouteScanThreads;
+  const uint32_t i0 = min((uint32_t)tid * per, n_blocks), i1 = min(i0 + per, n_blocks);
   uint32_t sum = 0, tsum = 0;
   for (uint32_t i = i0; i < i1; ++i) { sum += c[i]; tsum += t[i]; }
   uint32_t inc = sum;
@@ -105,24 +112,30 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
                                                                     const float4* __restrict__ rec0,
                                                                     const float4* __restrict__ rec1,
                                                                     const float4* __restrict__ rec2, RouteParams rp,
-                                                                    uint32_t n_warps, const uint32_t* __restrict__ base) {
+                                                                    uint32_t n_blocks, const uint32_t* __restrict__ base) {
+  __shared__ uint32_t s_c[B200GS_MAX_PEERS][kRouteWarps];
   const uint32_t i = blockIdx.x * kRouteThreads + threadIdx.x;
-  const uint32_t gw = i >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t key = kCulledKey;
   if (i < n) key = depth_key[i];
   const bool live = key != kCulledKey;
-  if (gw >= n_warps || !__any_sync(0xffffffffu, live)) return;
   uint2 rc = make_uint2(0u, 0u);
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
   if (live) { rc = rect[i]; a0 = rec0[i]; a1 = rec1[i]; a2 = rec2[i]; }
   const int tu0 = rc.x & 0xFFFF, tu1 = rc.x >> 16, tv0 = rc.y & 0xFFFF, tv1 = rc.y >> 16;
   for (int b = 0; b < rp.world; ++b) {
+    const uint32_t m = __ballot_sync(0xffffffffu, route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]).hit);
+    if (lane == 0) s_c[b][warp] = __popc(m);
+  }
+  __syncthreads();
+  for (int b = 0; b < rp.world; ++b) {
     const RouteHit h = route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]);
     const uint32_t m = __ballot_sync(0xffffffffu, h.hit);
     if (!h.hit) continue;
-    const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_warps + gw] + __popc(m & lt);
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += s_c[b][w];
+    const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_blocks + blockIdx.x] + before + __popc(m & lt);
     char* w = rp.ws[b];
     reinterpret_cast<float4*>(w + rp.rec0)[pos] = a0;
     reinterpret_cast<float4*>(w + rp.rec1)[pos] = a1;
@@ -134,10 +147,9 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
   }
 }
 
-size_t route_scratch_bytes(int n, int world) {
-  const size_t n_warps = (size_t)((n > 0 ? n : 1) + 31) / 32;
-  return 2 * (size_t)world * n_warps * sizeof(uint32_t);
-}
+static uint32_t route_blocks(int n) { return (uint32_t)(((n > 0 ? n : 1) + kRouteThreads - 1) / kRouteThreads); }
+
+size_t route_scratch_bytes(int n, int world) { return 2 * (size_t)world * route_blocks(n) * sizeof(uint32_t); }
 
 static RouteParams make_route_params(const b200gs_route* r, const FrameLayout& BL) {
   RouteParams p;
@@ -155,24 +167,24 @@ cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& S
                                const FrameLayout& BL, void* scratch, size_t scratch_bytes, cudaStream_t s) {
   if (scratch_bytes < route_scratch_bytes(n, route->world)) return cudaErrorInvalidValue;
   const RouteParams p = make_route_params(route, BL);
-  const uint32_t n_warps = (uint32_t)((n > 0 ? n : 1) + 31) / 32;
+  const uint32_t n_blocks = route_blocks(n);
   uint32_t* counts = reinterpret_cast<uint32_t*>(scratch);
-  uint32_t* tiles = counts + (size_t)route->world * n_warps;
+  uint32_t* tiles = counts + (size_t)route->world * n_blocks;
   const uint32_t un = (uint32_t)(n > 0 ? n : 0);
-  const int grid = (int)((n_warps * 32u + kRouteThreads - 1) / kRouteThreads);
+  const int grid = (int)n_blocks;
   route_count_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
-                                                    ws_ptr<uint2>(slice_ws, SL.rect), p, n_warps, counts, tiles);
-  route_scan_kernel<<<route->world, kRouteScanThreads, 0, s>>>(n_warps, counts, tiles, p);
+                                                    ws_ptr<uint2>(slice_ws, SL.rect), p, n_blocks, counts, tiles);
+  route_scan_kernel<<<route->world, kRouteScanThreads, 0, s>>>(n_blocks, counts, tiles, p);
   route_write_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
                                                     ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
                                                     ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2), p,
-                                                    n_warps, counts);
+                                                    n_blocks, counts);
   return cudaGetLastError();
 }
 
 // ---- destination side -------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherItems = 4;
+constexpr int kGatherItems = 8;
 constexpr int kGatherTile = kGatherThreads * kGatherItems;
 
 __global__ void __launch_bounds__(kGatherThreads) gather_routed_kernel(int world, uint32_t seg_cap,

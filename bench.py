@@ -377,7 +377,7 @@ def measure_tile_rows(env, steps, warm):
     del sc, sigma
     torch.cuda.empty_cache()
     return {"ms_per_frame": ms / steps, "frames_per_s": steps / (ms * 1e-3), "launches": int(launches), "bands": tr.bands,
-            "balanced": weights is not None, "checksum_root": checksum, **stats}
+            "balanced": weights is not None, "checksum_root": checksum, "routed": bool(tr.routed), **stats}
 
 
 def run_b200gs(args):
@@ -430,8 +430,13 @@ def run_mode_tile_rows(env, args):
                          "frames/s", r["ms_per_frame"] * env.K, env.K, "strong",
                          {"workload": TILE_ROWS_WORKLOAD["name"], "bands": r["bands"], "balanced_by_row_weights": r["balanced"],
                           "V": r["V"], "I_band_rank0": r["I_band"], "checksum_root": r["checksum_root"],
-                          "parallelism": f"one band of tile rows per rank ({env.world}); Gaussians replicated; bands stored "
-                                         "straight into rank 0's frame buffer over NVLink peer memory, no collective",
+                          "routed": r["routed"],
+                          "parallelism": (f"one band of tile rows per rank ({env.world}); every rank projects 1/{env.world} of "
+                                          "the Gaussians and routes the splat records to the bands over NVLink peer memory "
+                                          "(sort-middle), bands stored straight into rank 0's frame buffer, no collective")
+                          if r["routed"] else
+                                         (f"one band of tile rows per rank ({env.world}); Gaussians replicated; bands stored "
+                                          "straight into rank 0's frame buffer over NVLink peer memory, no collective"),
                           "l2_policy": "inputs larger than L2: 1.4 GB of parameters per frame"})
         line.update(gpu_launches=r["launches"], clocks=clocks)
         emit(line)

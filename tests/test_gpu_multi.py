@@ -66,16 +66,28 @@ def _worker(rank, world, port, out):
             out[f"img{rank}"] = render_tile_row_sharded(fn, (H + 15) // 16).cpu()
             # the same frame through TileRowRenderer: bands stored straight into rank 0's buffer over peer memory
             from b200gs.dist import TileRowRenderer
+            # ... with the Gaussians replicated (every rank culls all of them to its band), and routed: every rank
+            # projects its slice and writes the splat records into the bands' workspaces over peer memory
+            tr_rep = TileRowRenderer(H, W, dev, routed=False)
             tr = TileRowRenderer(H, W, dev)
-            for rep in range(3):               # several frames: the buffer is reused, the barriers must order them
+            assert tr.routed and not tr_rep.routed
+            for rep in range(3):               # several frames: the buffers are reused, the barriers must order them
                 cam_k = cams[1 + rep % 2]
                 c2w_k = cam_k["c2w"].to(dev)
-                col_k = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w_k)
-                img = tr.render(leaves["pos"], col_k, leaves["opacity_raw"], sigma, c2w_k, cam_k["fx"], cam_k["fy"],
-                                cam_k["cx"], cam_k["cy"])
-                torch.cuda.synchronize()
-                if rank == 0:
-                    out[f"tr{rep}"] = img.cpu()
+                for name, t in (("tr", tr), ("trrep", tr_rep)):
+                    col_k = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w_k)
+                    img = t.render(leaves["pos"], col_k, leaves["opacity_raw"], sigma, c2w_k, cam_k["fx"], cam_k["fy"],
+                                   cam_k["cx"], cam_k["cy"])
+                    torch.cuda.synchronize()
+                    if rank == 0:
+                        out[f"{name}{rep}"] = img.cpu()
+            # precomputed sigma / colour tensors (no tags): the routed slices are views of them
+            from b200gs import api
+            img = tr.render(leaves["pos"], api._real(col).clone(), leaves["opacity_raw"], api._real(sigma).clone(), c2w,
+                            cams[1]["fx"], cams[1]["fy"], cams[1]["cx"], cams[1]["cy"])
+            torch.cuda.synchronize()
+            if rank == 0:
+                out["tr_unfused"] = img.cpu()
             w8 = tr.row_weights(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, cams[1]["fx"], cams[1]["fy"],
                                 cams[1]["cx"], cams[1]["cy"])
             tr.set_weights(w8)
@@ -129,13 +141,19 @@ def test_dp_gradients_and_tile_row_bands_match_single_gpu():
                              cams[1]["cx"], cams[1]["cy"]).cpu()
     assert torch.equal(out["img0"], full) and torch.equal(out["img1"], full)
     assert torch.equal(out["tr0"], full) and torch.equal(out["tr2"], full) and torch.equal(out["tr_weighted"], full)
+    assert torch.equal(out["trrep0"], full) and torch.equal(out["trrep2"], full)
+    with torch.no_grad():
+        from b200gs import api
+        unfused = b200gs.render(leaves["pos"], api._real(col).clone(), leaves["opacity_raw"], api._real(sigma).clone(), c2w,
+                                H, W, cams[1]["fx"], cams[1]["fy"], cams[1]["cx"], cams[1]["cy"]).cpu()
+    assert torch.equal(out["tr_unfused"], unfused)
     assert out["tr_bands"][0][0] == 0 and out["tr_bands"][-1][1] == (H + 15) // 16
     with torch.no_grad():
         c2w = cams[2]["c2w"].to(dev)
         col = b200gs.evaluate_sh(leaves["f_dc"], leaves["f_rest"], leaves["pos"], c2w)
         other = b200gs.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, H, W, cams[2]["fx"], cams[2]["fy"],
                               cams[2]["cx"], cams[2]["cy"]).cpu()
-    assert torch.equal(out["tr1"], other)
+    assert torch.equal(out["tr1"], other) and torch.equal(out["trrep1"], other)
     for k in PARAMS:
         for r in range(world):
             err = float((out[f"bgrads{r}"][k] - leaves[k].grad.cpu()).abs().max() / leaves[k].grad.abs().max())
