@@ -184,7 +184,16 @@ class TileRowRenderer:
         img = tr.render(pos, color, opacity_raw, sigma, c2w, fx, fy, cx, cy)    # complete on root, in stream order
 
     `weights` (one number per tile row, e.g. intersections per row of an earlier frame - `row_weights()`) balances the
-    bands.  One process (no process group) renders the whole frame locally.  Forward only."""
+    bands.  One process (no process group) renders the whole frame locally.  Forward only.
+
+    By default (`routed`, world > 1) the per-Gaussian work is divided over the ranks as well: every rank projects its
+    1/world slice of the Gaussians and writes the survivors' splat records into the workspaces of the bands they touch
+    over peer memory (csrc/route.cu); `routed=False` keeps the Gaussians replicated.
+
+    `render(..., defer_check=True)` queues the frame without waiting for its intersection counters (the only host
+    synchronisation of a frame); the check - and the rare re-rasterization of a band whose lists outgrew their buffers -
+    then happens at the start of the next `render()` or in `finish()`, before any input of that frame is overwritten;
+    `finish()` / the counter `redone` say whether it happened (the frame buffer was incomplete until then)."""
 
     def __init__(self, H: int, W: int, device, group=None, root: int = 0, weights=None, routed=None):
         from . import _lib, peer
@@ -206,6 +215,8 @@ class TileRowRenderer:
         self.routed = bool(routed) and self.world > 1
         self._route = None                # (b200gs_route, N it was sized for, workspace area, band workspace view)
         self._slice_ws = [None]
+        self._pending = None              # frame whose counters have not been looked at yet (defer_check)
+        self.redone = 0                   # deferred frames that had to be rasterized again (finish())
 
     def set_weights(self, weights=None):
         self.bands = shard_tile_rows(self.n_rows, self.world, weights)
@@ -215,6 +226,8 @@ class TileRowRenderer:
         begin, end = self.bands[self.rank]
         if end <= begin:
             begin = end = self.n_rows
+        defer = bool(kw.get("defer_check", False))
+        self.finish()
         with torch.no_grad():
             args, _ = api._resolve(pos, color, opacity_raw, sigma, c2w, self.H, self.W, fx, fy, cx, cy,
                                    kw.get("near", 0.01), kw.get("far", 100.0), kw.get("pix_guard", 32), kw.get("T", 16),
@@ -223,17 +236,29 @@ class TileRowRenderer:
             cfg = args[-1]
             cfg.out = self.image
             if self.routed:
-                return self._render_routed(args)
+                return self._render_routed(args, defer)
             if self.world > 1:
                 cfg.keep_outside_band = True
                 cfg.out_ptr = self.root_ptr
                 self.area.barrier()            # root has consumed the previous frame: its buffer may be overwritten
             image, frame = ops.launch_frame(*args, buffers=self._buffers)
-            frame.finish()
+            if not defer:
+                frame.finish()
             if self.world > 1:
                 self.area.barrier()            # every band has landed in root's buffer
         self.last_frame = frame
+        self._pending = frame if defer else None
         return image
+
+    def finish(self) -> bool:
+        """Looks at the counters of a frame queued with `defer_check=True`.  Returns True when this rank's band did not
+        fit its intersection lists and was rasterized again - from inputs that stay untouched until this rank enters
+        the next frame's first barrier; whatever consumed the frame buffer before that saw an incomplete band (the lists
+        are sized 1.25 x the largest frame seen so far, so this needs a jump in the view)."""
+        frame, self._pending = self._pending, None
+        redone = bool(frame.finish()) if frame is not None else False
+        self.redone += int(redone)
+        return redone
 
     # -- routed bands ----------------------------------------------------------------------------------------------
     def _ensure_route(self, n: int):
@@ -255,7 +280,7 @@ class TileRowRenderer:
         self._buffers[0] = ws             # the band's frame workspace IS the routed-to workspace
         return self._route
 
-    def _render_routed(self, args):
+    def _render_routed(self, args, defer=False):
         """Sort-middle: this rank projects Gaussians [rank * N/p, (rank+1) * N/p) with the full frame's camera and
         writes every survivor's splat record into the workspace of each band its tile rect meets (peer stores, index
         order); after a flag barrier it depth-sorts, bins and blends what was routed to its own band.  Same per-tile
@@ -283,9 +308,11 @@ class TileRowRenderer:
             frame = ops.RoutedFrame(route, cfg, c2w, self.device)
             frame.keep = keep
             image = frame.launch("speculative", self._buffers)
-        frame.finish()
+        if not defer:
+            frame.finish()
         self.area.barrier()                # every band has landed in root's buffer
         self.last_frame = frame
+        self._pending = frame if defer else None
         return image
 
     def row_weights(self, pos, color, opacity_raw, sigma, c2w, fx, fy, cx, cy, **kw):

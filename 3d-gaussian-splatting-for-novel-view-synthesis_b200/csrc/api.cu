@@ -30,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_ROUTE, R_GATHER, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_ROUTE, R_GATHER, R_BARRIER, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select", "route_slice", "gather_routed"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select", "route_slice", "gather_routed", "peer_barrier"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -63,6 +63,11 @@ struct ProfScope {
     ProfScope _scope(region, s, launches);      \
     CU(expr);                                   \
   } while (0)
+
+bool env_is(const char* name, const char* value) {
+  const char* v = getenv(name);
+  return v && !strcmp(v, value);
+}
 
 int tile_bits(int n_tiles) {
   int b = 1;
@@ -396,8 +401,8 @@ static int check_peer_group(const b200gs_peer_group* g, const char* who) {
 int b200gs_peer_barrier(const b200gs_peer_group* group, uint32_t* epoch, void* stream) {
   if (int rc = check_peer_group(group, "peer_barrier")) return rc;
   if (!epoch) return fail(B200GS_ERR_ARG, "peer_barrier: null epoch");
-  CU(gs::launch_peer_barrier(group, ++*epoch, (cudaStream_t)stream));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_BARRIER, 1, gs::launch_peer_barrier(group, ++*epoch, s));
   return B200GS_OK;
 }
 
@@ -673,7 +678,8 @@ int b200gs_render_rasterize_split(const b200gs_camera* cam, int32_t n, void* fra
   } else {
     CU(cudaMemsetAsync(image_out, 0, (size_t)rp.H * rp.W * 3 * sizeof(float), s));
   }
-  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s, blend_stream != stream));
+  PCU(R_BLEND_FWD, 1, gs::launch_blend_fwd(rp, frame_ws, L, lists, image_out, s, blend_stream != stream,
+                                           (cam->flags & B200GS_CAM_KEEP_OUTSIDE_BAND) != 0 && !env_is("B200GS_ROW_STORES", "0")));
   return B200GS_OK;
 }
 

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
                                                                   const float4* __restrict__ rec2,
                                                                   float* __restrict__ image,
                                                                   float* __restrict__ final_T,
-                                                                  uint32_t* __restrict__ n_contrib) {
+                                                                  uint32_t* __restrict__ n_contrib, int row_stores) {
   __shared__ float4 s_rec[3][kBlendThreads];
   __shared__ uint32_t s_list[kBlendWarps][kBlendThreads];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,16 +175,39 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(RenderParams r
     if (C0 > 1.f) flags |= 1u << 29;
     if (C1 > 1.f) flags |= 1u << 30;
     if (C2 > 1.f) flags |= 1u << 31;
-    image[3 * pix + 0] = fminf(fmaxf(C0, 0.f), 1.f);
-    image[3 * pix + 1] = fminf(fmaxf(C1, 0.f), 1.f);
-    image[3 * pix + 2] = fminf(fmaxf(C2, 0.f), 1.f);
     final_T[pix] = T;
     n_contrib[pix] = flags;
+    if (!row_stores) {
+      image[3 * pix + 0] = fminf(fmaxf(C0, 0.f), 1.f);
+      image[3 * pix + 1] = fminf(fmaxf(C1, 0.f), 1.f);
+      image[3 * pix + 2] = fminf(fmaxf(C2, 0.f), 1.f);
+    }
+  }
+  if (!row_stores) return;
+  // Frame buffer on ANOTHER GPU (tile-row bands: image = a peer-mapped address): the tile's 16 x 16 x 3 colours leave
+  // through shared memory, so that every store instruction of a warp writes 128 consecutive bytes of an image row (a
+  // tile row is 192 B) instead of every third float of four rows - whole 32-byte sectors, each written once, a third of
+  // the write requests on NVLink.  (Into local memory the L2 merges the three partial stores and this costs 2 %.)
+  float* s_out = reinterpret_cast<float*>(&s_rec[0][0]);
+  __syncthreads();                        // every warp is done with the staged records
+  {
+    const int o = 3 * ((((warp >> 1) << 2) + (lane >> 3)) * kTile + ((warp & 1) << 3) + (lane & 7));
+    s_out[o + 0] = fminf(fmaxf(C0, 0.f), 1.f);
+    s_out[o + 1] = fminf(fmaxf(C1, 0.f), 1.f);
+    s_out[o + 2] = fminf(fmaxf(C2, 0.f), 1.f);
+  }
+  __syncthreads();
+  const int x0 = tile_x * kTile, y0 = tile_y * kTile;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int f = k * kBlendThreads + (int)threadIdx.x;
+    const int r = f / (3 * kTile), j = f - r * (3 * kTile);
+    if (y0 + r < rp.H && x0 + j / 3 < rp.W) image[3 * ((size_t)(y0 + r) * rp.W + x0) + j] = s_out[f];
   }
 }
 
 cudaError_t launch_blend_fwd(const RenderParams& rp, const void* ws, const FrameLayout& L, const uint32_t* vals,
-                             float* image, cudaStream_t s, bool overlapped) {
+                             float* image, cudaStream_t s, bool overlapped, bool row_stores) {
   const int rows = rp.row_end - rp.row_begin;
   if (rows <= 0 || rp.tiles_x <= 0) return cudaSuccess;
   dim3 grid(rp.tiles_x, rows);
@@ -201,13 +224,13 @@ cudaError_t launch_blend_fwd(const RenderParams& rp, const void* ws, const Frame
     blend_fwd_kernel<true><<<grid, kBlendThreads, 0, s>>>(
         rp, ws_ptr<uint2>(ws, L.ranges), vals, ws_ptr<float4>(ws, L.rec0), ws_ptr<float4>(ws, L.rec1),
         ws_ptr<float4>(ws, L.rec2), image, const_cast<float*>(ws_ptr<float>(ws, L.final_T)),
-        const_cast<uint32_t*>(ws_ptr<uint32_t>(ws, L.n_contrib)));
+        const_cast<uint32_t*>(ws_ptr<uint32_t>(ws, L.n_contrib)), row_stores ? 1 : 0);
     return cudaGetLastError();
   }
   blend_fwd_kernel<false><<<grid, kBlendThreads, 0, s>>>(
       rp, ws_ptr<uint2>(ws, L.ranges), vals, ws_ptr<float4>(ws, L.rec0), ws_ptr<float4>(ws, L.rec1),
       ws_ptr<float4>(ws, L.rec2), image, const_cast<float*>(ws_ptr<float>(ws, L.final_T)),
-      const_cast<uint32_t*>(ws_ptr<uint32_t>(ws, L.n_contrib)));
+      const_cast<uint32_t*>(ws_ptr<uint32_t>(ws, L.n_contrib)), row_stores ? 1 : 0);
   return cudaGetLastError();
 }
 

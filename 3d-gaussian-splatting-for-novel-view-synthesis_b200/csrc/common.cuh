@@ -285,7 +285,7 @@ cudaError_t launch_l1_ssim_bwd(const float* pred, const float* target, int n_img
                                cudaStream_t s);
 
 cudaError_t launch_blend_fwd(const RenderParams& rp, const void* frame_ws, const FrameLayout& L, const uint32_t* vals,
-                             float* image, cudaStream_t s, bool overlapped = false);
+                             float* image, cudaStream_t s, bool overlapped = false, bool row_stores = false);
 cudaError_t launch_blend_bwd(const RenderParams& rp, void* frame_ws, const FrameLayout& L, const uint32_t* vals,
                              const float* image_grad, int n, cudaStream_t s);
 

@@ -18,11 +18,14 @@
 //                 (depth sort, pair emission, supertile sort, split, blend into the root's frame buffer).
 // A routed entry's "Gaussian id" is its position in the band's workspace; nothing downstream needs the global id (forward
 // only).  Segments have room for a whole slice (seg_cap >= slice size), so nothing can overflow.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace gs {
 
-constexpr int kRouteThreads = 256;
+constexpr int kRouteThreads = 512;
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kRouteScanThreads = 1024;
 
@@ -107,12 +110,13 @@ __global__ void __launch_bounds__(kRouteScanThreads) route_scan_kernel(uint32_t 
     *reinterpret_cast<uint2*>(rp.ws[b] + rp.route_in + (size_t)rp.rank * sizeof(uint2)) = make_uint2(total, ttotal);
 }
 
-__global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, const uint32_t* __restrict__ depth_key,
-                                                                    const uint2* __restrict__ rect,
-                                                                    const float4* __restrict__ rec0,
-                                                                    const float4* __restrict__ rec1,
-                                                                    const float4* __restrict__ rec2, RouteParams rp,
-                                                                    uint32_t n_blocks, const uint32_t* __restrict__ base) {
+// Variant with per-warp runs (no staging): B200GS_ROUTE_WRITE=warp, kept for the comparison recorded in DESIGN.md.
+__global__ void __launch_bounds__(kRouteThreads) route_write_warp_kernel(uint32_t n, const uint32_t* __restrict__ depth_key,
+                                                                         const uint2* __restrict__ rect,
+                                                                         const float4* __restrict__ rec0,
+                                                                         const float4* __restrict__ rec1,
+                                                                         const float4* __restrict__ rec2, RouteParams rp,
+                                                                         uint32_t n_blocks, const uint32_t* __restrict__ base) {
   __shared__ uint32_t s_c[B200GS_MAX_PEERS][kRouteWarps];
   const uint32_t i = blockIdx.x * kRouteThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -147,6 +151,105 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
   }
 }
 
+// The entries of one block are first compacted into shared memory, grouped by band and in index order inside a band,
+// and then copied out as contiguous runs - ~kRouteThreads / world entries, i.e. around a kilobyte per array, band and
+// block - because consecutive Gaussians of a slice land in different bands and NVLink wants large write requests
+// (per-warp compaction gave 64-byte runs: 133 us for the routing pass at 8 ranks against 49 us into local memory).
+// A block whose entries (counted once per band they meet) exceed the staging capacity goes band by band instead.
+constexpr int kRouteStage = 768;           // staged entries per block: 48 KB of dynamic shared memory
+constexpr size_t kRouteStageBytes = (size_t)kRouteStage * (3 * 16 + 8 + 4 + 4);
+
+struct RouteStage {
+  float4 *r0, *r1, *r2;
+  uint2* rect;
+  uint32_t *key, *sup;
+};
+
+__device__ __forceinline__ void route_copy_out(const RouteStage& st, const RouteParams& rp, int b, size_t pos, uint32_t k0,
+                                               uint32_t k) {
+  char* w = rp.ws[b];
+  reinterpret_cast<float4*>(w + rp.rec0)[pos] = st.r0[k0 + k];
+  reinterpret_cast<float4*>(w + rp.rec1)[pos] = st.r1[k0 + k];
+  reinterpret_cast<float4*>(w + rp.rec2)[pos] = st.r2[k0 + k];
+  reinterpret_cast<uint32_t*>(w + rp.depth_key)[pos] = st.key[k0 + k];
+  reinterpret_cast<uint2*>(w + rp.rect)[pos] = st.rect[k0 + k];
+  reinterpret_cast<uint32_t*>(w + rp.super_touched)[pos] = st.sup[k0 + k];
+}
+
+__global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, const uint32_t* __restrict__ depth_key,
+                                                                    const uint2* __restrict__ rect,
+                                                                    const float4* __restrict__ rec0,
+                                                                    const float4* __restrict__ rec1,
+                                                                    const float4* __restrict__ rec2, RouteParams rp,
+                                                                    uint32_t n_blocks, const uint32_t* __restrict__ base) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ uint32_t s_c[B200GS_MAX_PEERS][kRouteWarps];
+  __shared__ uint32_t s_off[B200GS_MAX_PEERS + 1];      // first staged slot of band b (single-pass route)
+  RouteStage st;
+  st.r0 = reinterpret_cast<float4*>(s_dyn);
+  st.r1 = st.r0 + kRouteStage;
+  st.r2 = st.r1 + kRouteStage;
+  st.rect = reinterpret_cast<uint2*>(st.r2 + kRouteStage);
+  st.key = reinterpret_cast<uint32_t*>(st.rect + kRouteStage);
+  st.sup = st.key + kRouteStage;
+  const int tid = threadIdx.x;
+  const uint32_t i = blockIdx.x * kRouteThreads + tid;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t key = kCulledKey;
+  if (i < n) key = depth_key[i];
+  const bool live = key != kCulledKey;
+  uint2 rc = make_uint2(0u, 0u);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+  if (live) { rc = rect[i]; a0 = rec0[i]; a1 = rec1[i]; a2 = rec2[i]; }
+  const int tu0 = rc.x & 0xFFFF, tu1 = rc.x >> 16, tv0 = rc.y & 0xFFFF, tv1 = rc.y >> 16;
+  for (int b = 0; b < rp.world; ++b) {
+    const uint32_t m = __ballot_sync(0xffffffffu, route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]).hit);
+    if (lane == 0) s_c[b][warp] = __popc(m);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int b = 0; b < rp.world; ++b) {
+      s_off[b] = run;
+#pragma unroll
+      for (int w = 0; w < kRouteWarps; ++w) run += s_c[b][w];
+    }
+    s_off[rp.world] = run;
+  }
+  __syncthreads();
+  const uint32_t total = s_off[rp.world];
+  if (total == 0) return;
+  const bool single = total <= (uint32_t)kRouteStage;
+  for (int b = 0; b < rp.world; ++b) {
+    const uint32_t off_b = s_off[b], cnt = s_off[b + 1] - off_b;
+    if (cnt == 0) continue;                // block-uniform
+    const RouteHit h = route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]);
+    const uint32_t m = __ballot_sync(0xffffffffu, h.hit);
+    if (h.hit) {
+      uint32_t k = (single ? off_b : 0u) + __popc(m & lt);
+      for (int w = 0; w < warp; ++w) k += s_c[b][w];
+      st.r0[k] = a0; st.r1[k] = a1; st.r2[k] = a2;
+      st.key[k] = key;
+      st.rect[k] = make_uint2(rc.x, (uint32_t)h.lo | ((uint32_t)h.hi << 16));
+      st.sup[k] = (uint32_t)((tu1 / kSuperX - tu0 / kSuperX + 1) * (h.hi / kSuperY - h.lo / kSuperY + 1));
+    }
+    if (single) continue;
+    __syncthreads();                       // band by band: cnt <= kRouteThreads <= kRouteStage
+    const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_blocks + blockIdx.x];
+    for (uint32_t k = tid; k < cnt; k += kRouteThreads) route_copy_out(st, rp, b, pos + k, 0u, k);
+    __syncthreads();
+  }
+  if (!single) return;
+  __syncthreads();
+  for (uint32_t k = tid; k < total; k += kRouteThreads) {
+    int b = 0;
+    while (s_off[b + 1] <= k) ++b;
+    const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_blocks + blockIdx.x] + (k - s_off[b]);
+    route_copy_out(st, rp, b, pos, 0u, k);
+  }
+}
+
 static uint32_t route_blocks(int n) { return (uint32_t)(((n > 0 ? n : 1) + kRouteThreads - 1) / kRouteThreads); }
 
 size_t route_scratch_bytes(int n, int world) { return 2 * (size_t)world * route_blocks(n) * sizeof(uint32_t); }
@@ -175,7 +278,20 @@ cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& S
   route_count_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
                                                     ws_ptr<uint2>(slice_ws, SL.rect), p, n_blocks, counts, tiles);
   route_scan_kernel<<<route->world, kRouteScanThreads, 0, s>>>(n_blocks, counts, tiles, p);
-  route_write_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
+  const char* variant = getenv("B200GS_ROUTE_WRITE");
+  if (variant && !strcmp(variant, "warp")) {
+    route_write_warp_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
+                                                           ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
+                                                           ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2),
+                                                           p, n_blocks, counts);
+    return cudaGetLastError();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(route_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteStageBytes);
+    attr_set = true;
+  }
+  route_write_kernel<<<grid, kRouteThreads, kRouteStageBytes, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
                                                     ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
                                                     ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2), p,
                                                     n_blocks, counts);

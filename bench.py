@@ -360,24 +360,62 @@ def measure_tile_rows(env, steps, warm):
         sigma = gs.build_sigma_from_params(sc["scale_raw"], sc["q_raw"])
         tr = TileRowRenderer(wl["H"], wl["W"], dev)
 
+        defer = os.environ.get("B200GS_TILE_ROWS_DEFER", "1") != "0"
+
         def frame(_i):
+            # frames are queued back to back: the one host wait of a frame (for its intersection counters) moves to the
+            # start of the next call, so the host runs ahead of the GPU (TileRowRenderer.render, defer_check)
             col = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
-            return tr.render(sc["pos"], col, sc["opacity_raw"], sigma, c2w, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+            return tr.render(sc["pos"], col, sc["opacity_raw"], sigma, c2w, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
+                             defer_check=defer)
         weights = None
         if env.world > 1:      # balance the bands by the intersections per tile row of this view
             col = gs.evaluate_sh(sc["f_dc"], sc["f_rest"], sc["pos"], c2w)
             weights = tr.row_weights(sc["pos"], col, sc["opacity_raw"], sigma, c2w, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
             tr.set_weights(weights)
         ms, launches = env.timed(frame, steps, max(warm, 3))
+        tr.finish()
+        redone = tr.redone
         img = frame(0)
+        tr.finish()
         torch.cuda.synchronize()
         env.barrier()
         checksum = float(img.double().sum()) if env.rank == tr.root else 0.0
         stats = dict(V=tr.last_frame.n_visible, I_band=tr.last_frame.n_isect)
+        # per kernel group, this rank (CUDA events inside the library around every group; a separate, untimed pass)
+        lib = env.lib
+        lib.b200gs_profile_enable(1)
+        for i in range(5):
+            frame(i)
+        tr.finish()
+        torch.cuda.synchronize()
+        ms_buf, call_buf = (ctypes.c_float * 32)(), (ctypes.c_int32 * 32)()
+        k = lib.b200gs_profile_collect(ms_buf, call_buf, 32)
+        lib.b200gs_profile_enable(0)
+        regions = {lib.b200gs_profile_region_name(r).decode(): round(1e3 * ms_buf[r] / 5, 1) for r in range(k) if call_buf[r]}
+        env.barrier()
+        # measured alternatives (one knob changed at a time; every rank reads the same environment)
+        variants = {}
+        if os.environ.get("B200GS_TILE_ROWS_SWEEP") and env.world > 1:
+            for name, knob, val in (("route_write_per_warp_runs", "B200GS_ROUTE_WRITE", "warp"),
+                                    ("blend_strided_pixel_stores", "B200GS_ROW_STORES", "0"),
+                                    ("host_waits_for_counters_every_frame", None, None)):
+                if knob:
+                    os.environ[knob] = val
+                else:
+                    defer = False
+                vms, _ = env.timed(frame, 20, 3)
+                tr.finish()
+                variants[name] = round(vms / 20, 4)
+                if knob:
+                    del os.environ[knob]
+                else:
+                    defer = os.environ.get("B200GS_TILE_ROWS_DEFER", "1") != "0"
     del sc, sigma
     torch.cuda.empty_cache()
     return {"ms_per_frame": ms / steps, "frames_per_s": steps / (ms * 1e-3), "launches": int(launches), "bands": tr.bands,
-            "balanced": weights is not None, "checksum_root": checksum, "routed": bool(tr.routed), **stats}
+            "balanced": weights is not None, "checksum_root": checksum, "routed": bool(tr.routed), "deferred_check": defer,
+            "frames_redone": int(redone), "regions_us_per_frame": regions, "variants_ms_per_frame": variants, **stats}
 
 
 def run_b200gs(args):
@@ -430,7 +468,9 @@ def run_mode_tile_rows(env, args):
                          "frames/s", r["ms_per_frame"] * env.K, env.K, "strong",
                          {"workload": TILE_ROWS_WORKLOAD["name"], "bands": r["bands"], "balanced_by_row_weights": r["balanced"],
                           "V": r["V"], "I_band_rank0": r["I_band"], "checksum_root": r["checksum_root"],
-                          "routed": r["routed"],
+                          "routed": r["routed"], "deferred_check": r["deferred_check"], "frames_redone": r["frames_redone"],
+                          "kernel_groups_us_per_frame_rank0": r["regions_us_per_frame"],
+                          "variants_ms_per_frame": r["variants_ms_per_frame"],
                           "parallelism": (f"one band of tile rows per rank ({env.world}); every rank projects 1/{env.world} of "
                                           "the Gaussians and routes the splat records to the bands over NVLink peer memory "
                                           "(sort-middle), bands stored straight into rank 0's frame buffer, no collective")

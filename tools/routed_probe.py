@@ -11,6 +11,7 @@ import ctypes
 import json
 import os
 import sys
+import time
 
 import torch
 
@@ -70,12 +71,14 @@ def main():
             prof = rep == 2
             if prof:
                 lib.b200gs_profile_enable(1)
-            src, dst = [], []
+            src, dst, host_src, host_dst = [], [], [], []
             for r in range(world):
                 lo, hi = min(n, r * per), min(n, (r + 1) * per)
                 a, b = ev(), ev()
                 a.record()
+                t0 = time.perf_counter()
                 keep = ops.route_project_slice(*args[:8], c2w, cfg, routes[r], lo, hi, slice_ws)
+                host_src.append(round(1e6 * (time.perf_counter() - t0), 1))
                 b.record()
                 torch.cuda.synchronize()
                 src.append(round(1e3 * a.elapsed_time(b), 1))
@@ -89,8 +92,10 @@ def main():
                 band.out = image
                 a, b = ev(), ev()
                 a.record()
+                t0 = time.perf_counter()
                 fr = ops.RoutedFrame(routes[r], band, c2w, dev)
                 fr.launch("speculative", isect[r])
+                host_dst.append(round(1e6 * (time.perf_counter() - t0), 1))
                 b.record()
                 fr.finish()
                 torch.cuda.synchronize()
@@ -99,6 +104,7 @@ def main():
                 if prof and r in (0, world // 2):
                     out[f"dst_regions_band{r}"] = collect()
             out["src_us"], out["dst_us"] = src, dst
+            out["host_src_us"], out["host_dst_us"] = host_src, host_dst
             out["V"], out["I"] = [f.n_visible for f in frames], [f.n_isect for f in frames]
         lib.b200gs_profile_enable(0)
         full = b200gs.render(sc["pos"], col, sc["opacity_raw"], sigma, c2w, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
