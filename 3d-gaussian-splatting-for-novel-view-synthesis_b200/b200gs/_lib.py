@@ -19,6 +19,7 @@ TILE = 16
 CAM_KEEP_OUTSIDE_BAND = 1
 CAM_OVERLAPPED = 2
 CAM_ROUTED = 4
+ROUTE_RECORDS_LATER = 1
 
 
 class Gaussians(Structure):
@@ -70,7 +71,8 @@ class PeerTensor(Structure):
 
 class Route(Structure):
     _fields_ = [("world", c_int32), ("rank", c_int32), ("seg_capacity", c_uint32), ("band_row", c_int32 * (MAX_PEERS + 1)),
-                ("band_ws", c_void_p * MAX_PEERS), ("band_ws_bytes", c_size_t)]
+                ("band_ws", c_void_p * MAX_PEERS), ("band_ws_bytes", c_size_t), ("flags", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
 
 
 class FrameStats(Structure):
@@ -118,6 +120,7 @@ SYMBOLS = {
     "b200gs_peer_allreduce": (c_int, [POINTER(PeerGroup), POINTER(PeerLayout), POINTER(PeerTensor), c_int32,
                                       POINTER(c_uint32), c_void_p]),
     "b200gs_route_project_slice": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_size_t, POINTER(Route), c_void_p]),
+    "b200gs_route_records": (c_int, [c_int32, POINTER(Camera), c_void_p, c_size_t, POINTER(Route), c_void_p]),
     "b200gs_render_project_routed": (c_int, [POINTER(Camera), POINTER(Route), c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200gs_render_host": (c_int, [POINTER(Gaussians), POINTER(Camera), c_void_p, c_void_p, POINTER(FrameStats)]),
     "b200gs_debug_export": (c_int, [c_int32, c_void_p, c_size_t, c_int32, c_int32] + [c_void_p] * 10),

@@ -214,6 +214,10 @@ class TileRowRenderer:
             routed = _lib.env("B200GS_TILE_ROWS_ROUTED", "1") != "0"
         self.routed = bool(routed) and self.world > 1
         self._route = None                # (b200gs_route, N it was sized for, workspace area, band workspace view)
+        # the 48-byte splat records cross NVLink on a second stream, beside the destinations' depth sort; only the 16
+        # bytes per entry the binning needs are on the critical path (B200GS_ROUTE_SPLIT=0: everything in one go)
+        self.split_records = self.routed and _lib.env("B200GS_ROUTE_SPLIT", "1") != "0"
+        self._side = None
         self._slice_ws = [None]
         self._pending = None              # frame whose counters have not been looked at yet (defer_check)
         self.redone = 0                   # deferred frames that had to be rasterized again (finish())
@@ -302,11 +306,29 @@ class TileRowRenderer:
         # root has consumed the previous frame and every rank has finished its previous band: frame buffer and band
         # workspaces may be overwritten
         self.area.barrier()
+        from . import _lib
+        route.flags = _lib.ROUTE_RECORDS_LATER if self.split_records else 0
         keep = ops.route_project_slice(*args[:8], c2w, full, route, lo, hi, self._slice_ws)
-        self.area.barrier()                # every segment of every band has landed
+        hook = None
+        if self.split_records:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(self.device), torch.cuda.Event(), torch.cuda.Event())
+            side, ev_meta, ev_rec = self._side
+            main = torch.cuda.current_stream(self.device)
+            ev_meta.record(main)
+            side.wait_event(ev_meta)
+            with torch.cuda.stream(side):
+                ops.route_records(hi - lo, c2w, full, route, self._slice_ws)
+                ev_rec.record(side)
+
+            def hook():                    # between the band's depth sort and its rasterize phase
+                main.wait_event(ev_rec)
+                self.area.barrier()        # every record of every band has landed
+        self.area.barrier()                # every segment's keys / rects of every band have landed
         with torch.cuda.device(self.device):
             frame = ops.RoutedFrame(route, cfg, c2w, self.device)
             frame.keep = keep
+            frame.after_project = hook
             image = frame.launch("speculative", self._buffers)
         if not defer:
             frame.finish()

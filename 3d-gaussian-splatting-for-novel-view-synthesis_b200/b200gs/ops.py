@@ -379,10 +379,13 @@ class RoutedFrame(Frame):
         super().__init__(g, None, cam_cfg, c2w, device)
         self.route = route
         self.cam.flags |= _lib.CAM_ROUTED
+        self.after_project = None         # called between the depth sort and the rasterize phase (records-later barrier)
 
     def _project(self, lib, frame_bytes, stats_ptr, st):
         _lib.check(lib.b200gs_render_project_routed(ctypes.byref(self.cam), ctypes.byref(self.route), _ptr(self.frame_ws),
                                                     frame_bytes, stats_ptr, st), "render_project_routed")
+        if self.after_project is not None:
+            self.after_project()
 
     def backward(self, grad_image, grads):
         raise _lib.B200GSError("routed band frames are forward only")
@@ -404,6 +407,17 @@ def route_project_slice(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest,
         _lib.check(lib.b200gs_route_project_slice(ctypes.byref(g), ctypes.byref(cam), _ptr(buffers[0]), buffers[0].numel(),
                                                   ctypes.byref(route), _stream(dev)), "route_project_slice")
     return keep
+
+
+def route_records(n_slice: int, c2w, cfg: RenderConfig, route, buffers):
+    """Second half of the source role (route.flags has ROUTE_RECORDS_LATER): the splat records of the slice projected by
+    the last `route_project_slice` on `buffers`, written on the CURRENT stream (ordered after that call by the caller)."""
+    lib = _lib.load()
+    dev = buffers[0].device
+    with torch.cuda.device(dev):
+        cam = cfg.to_c(c2w)
+        _lib.check(lib.b200gs_route_records(int(n_slice), ctypes.byref(cam), _ptr(buffers[0]), buffers[0].numel(),
+                                            ctypes.byref(route), _stream(dev)), "route_records")
 
 
 def launch_frame(pos, opacity_raw, scale_raw, q_raw, sigma, f_dc, f_rest, color, c2w, cfg, buffers=None):

@@ -30,10 +30,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 // --- optional per-region CUDA-event profiling (bench.py's per-kernel roofline table) ---------------------
 enum Region { R_PREPROCESS_FWD = 0, R_DEPTH_SORT, R_SCAN, R_EMIT, R_TILE_SORT, R_SPLIT, R_BLEND_FWD, R_BLEND_BWD,
-              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_ROUTE, R_GATHER, R_BARRIER, R_COUNT };
+              R_PREPROCESS_BWD, R_EVAL_SH, R_BUILD_SIGMA, R_EVAL_SH_BWD, R_BUILD_SIGMA_BWD, R_LOSS_FWD, R_LOSS_BWD, R_ADAM, R_CLIP, R_PEER_STEP, R_PEER_ALLREDUCE, R_COMPACT, R_BAND_SELECT, R_ROUTE, R_GATHER, R_BARRIER, R_ROUTE_REC, R_COUNT };
 const char* kRegionNames[R_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_super", "super_sort", "split_tiles",
                                      "blend_fwd", "blend_bwd", "preprocess_bwd", "evaluate_sh", "build_sigma",
-                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select", "route_slice", "gather_routed", "peer_barrier"};
+                                     "evaluate_sh_bwd", "build_sigma_bwd", "l1_ssim_fwd", "l1_ssim_bwd", "adam_step", "clip_grad_norm", "peer_adam_step", "peer_allreduce", "compact_keys", "band_select", "route_slice", "gather_routed", "peer_barrier", "route_records"};
 struct ProfRec { int region; cudaEvent_t a, b; };
 struct Profiler {
   std::mutex mu;
@@ -558,8 +558,28 @@ int b200gs_route_project_slice(const b200gs_gaussians* g_slice, const b200gs_cam
   CU(cudaMemsetAsync(gs::ws_ptr<b200gs_frame_stats>(slice_ws, SL.header), 0, sizeof(b200gs_frame_stats), s));
   if (gi.n > 0)       // an empty slice (more ranks than 32-entry groups) still reports its zero totals to every band
     PCU(R_PREPROCESS_FWD, 1, gs::launch_preprocess_fwd(gi, cam->c2w, rp, slice_ws, SL, s, nullptr, nullptr));
+  const bool split = (route->flags & B200GS_ROUTE_RECORDS_LATER) != 0;
   PCU(R_ROUTE, 3, gs::launch_route_slice(gi.n, slice_ws, SL, route, BL, gs::ws_ptr<void>(slice_ws, SL.order),
-                                         scratch_bytes, s));
+                                         scratch_bytes, split ? gs::kRouteMeta : gs::kRouteAll, s));
+  return B200GS_OK;
+}
+
+int b200gs_route_records(int32_t n_slice, const b200gs_camera* cam, void* slice_ws, size_t slice_bytes,
+                         const b200gs_route* route, void* stream) {
+  gs::RenderParams rp;
+  int rc = make_params(cam, rp);
+  if (rc) return rc;
+  if ((rc = check_route(route, "route_records"))) return rc;
+  if (n_slice < 0 || (uint32_t)n_slice > route->seg_capacity) return fail(B200GS_ERR_ARG, "route_records: bad slice length");
+  if (!slice_ws) return fail(B200GS_ERR_ARG, "slice_ws is null");
+  const gs::FrameLayout SL = gs::frame_layout(n_slice, rp.H, rp.W);
+  const gs::FrameLayout BL = gs::frame_layout((int)(route->world * route->seg_capacity), rp.H, rp.W);
+  if (slice_bytes < SL.total) return fail(B200GS_ERR_WORKSPACE, "slice workspace too small");
+  if (route->band_ws_bytes < BL.total) return fail(B200GS_ERR_WORKSPACE, "band workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_ROUTE_REC, 1, gs::launch_route_slice(n_slice, slice_ws, SL, route, BL,
+                                             gs::ws_ptr<void>(slice_ws, SL.order), SL.grad_acc - SL.order,
+                                             gs::kRouteRecords, s));
   return B200GS_OK;
 }
 

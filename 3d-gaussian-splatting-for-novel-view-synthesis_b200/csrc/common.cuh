@@ -264,8 +264,9 @@ cudaError_t launch_densify_apply(int n, const void* ws, const float* const in[6]
 
 // route.cu: tile-row bands with the per-Gaussian work divided over the ranks (project a slice, route the records)
 size_t route_scratch_bytes(int n, int world);
+enum { kRouteAll = 0, kRouteMeta = 1, kRouteRecords = 2 };
 cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& SL, const b200gs_route* route,
-                               const FrameLayout& BL, void* scratch, size_t scratch_bytes, cudaStream_t s);
+                               const FrameLayout& BL, void* scratch, size_t scratch_bytes, int what, cudaStream_t s);
 cudaError_t launch_gather_routed(int world, uint32_t seg_cap, void* band_ws, const FrameLayout& BL, uint32_t* out_keys,
                                  uint32_t* out_ids, uint32_t* depth_hist, const DepthKeyPlan& kp, cudaStream_t s);
 

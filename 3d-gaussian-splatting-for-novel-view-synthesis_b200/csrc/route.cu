@@ -165,17 +165,25 @@ struct RouteStage {
   uint32_t *key, *sup;
 };
 
+// META: depth key, tile rect, supertile count (16 B per entry - all the destination needs until its blend);
+// REC: the three float4 of the splat record (48 B per entry - what the blend reads).
+template <bool META, bool REC>
 __device__ __forceinline__ void route_copy_out(const RouteStage& st, const RouteParams& rp, int b, size_t pos, uint32_t k0,
                                                uint32_t k) {
   char* w = rp.ws[b];
-  reinterpret_cast<float4*>(w + rp.rec0)[pos] = st.r0[k0 + k];
-  reinterpret_cast<float4*>(w + rp.rec1)[pos] = st.r1[k0 + k];
-  reinterpret_cast<float4*>(w + rp.rec2)[pos] = st.r2[k0 + k];
-  reinterpret_cast<uint32_t*>(w + rp.depth_key)[pos] = st.key[k0 + k];
-  reinterpret_cast<uint2*>(w + rp.rect)[pos] = st.rect[k0 + k];
-  reinterpret_cast<uint32_t*>(w + rp.super_touched)[pos] = st.sup[k0 + k];
+  if (REC) {
+    reinterpret_cast<float4*>(w + rp.rec0)[pos] = st.r0[k0 + k];
+    reinterpret_cast<float4*>(w + rp.rec1)[pos] = st.r1[k0 + k];
+    reinterpret_cast<float4*>(w + rp.rec2)[pos] = st.r2[k0 + k];
+  }
+  if (META) {
+    reinterpret_cast<uint32_t*>(w + rp.depth_key)[pos] = st.key[k0 + k];
+    reinterpret_cast<uint2*>(w + rp.rect)[pos] = st.rect[k0 + k];
+    reinterpret_cast<uint32_t*>(w + rp.super_touched)[pos] = st.sup[k0 + k];
+  }
 }
 
+template <bool META, bool REC>
 __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, const uint32_t* __restrict__ depth_key,
                                                                     const uint2* __restrict__ rect,
                                                                     const float4* __restrict__ rec0,
@@ -201,7 +209,10 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
   const bool live = key != kCulledKey;
   uint2 rc = make_uint2(0u, 0u);
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-  if (live) { rc = rect[i]; a0 = rec0[i]; a1 = rec1[i]; a2 = rec2[i]; }
+  if (live) {
+    rc = rect[i];
+    if (REC) { a0 = rec0[i]; a1 = rec1[i]; a2 = rec2[i]; }
+  }
   const int tu0 = rc.x & 0xFFFF, tu1 = rc.x >> 16, tv0 = rc.y & 0xFFFF, tv1 = rc.y >> 16;
   for (int b = 0; b < rp.world; ++b) {
     const uint32_t m = __ballot_sync(0xffffffffu, route_test(live, tv0, tv1, rp.row[b], rp.row[b + 1]).hit);
@@ -229,15 +240,17 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
     if (h.hit) {
       uint32_t k = (single ? off_b : 0u) + __popc(m & lt);
       for (int w = 0; w < warp; ++w) k += s_c[b][w];
-      st.r0[k] = a0; st.r1[k] = a1; st.r2[k] = a2;
-      st.key[k] = key;
-      st.rect[k] = make_uint2(rc.x, (uint32_t)h.lo | ((uint32_t)h.hi << 16));
-      st.sup[k] = (uint32_t)((tu1 / kSuperX - tu0 / kSuperX + 1) * (h.hi / kSuperY - h.lo / kSuperY + 1));
+      if (REC) { st.r0[k] = a0; st.r1[k] = a1; st.r2[k] = a2; }
+      if (META) {
+        st.key[k] = key;
+        st.rect[k] = make_uint2(rc.x, (uint32_t)h.lo | ((uint32_t)h.hi << 16));
+        st.sup[k] = (uint32_t)((tu1 / kSuperX - tu0 / kSuperX + 1) * (h.hi / kSuperY - h.lo / kSuperY + 1));
+      }
     }
     if (single) continue;
     __syncthreads();                       // band by band: cnt <= kRouteThreads <= kRouteStage
     const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_blocks + blockIdx.x];
-    for (uint32_t k = tid; k < cnt; k += kRouteThreads) route_copy_out(st, rp, b, pos + k, 0u, k);
+    for (uint32_t k = tid; k < cnt; k += kRouteThreads) route_copy_out<META, REC>(st, rp, b, pos + k, 0u, k);
     __syncthreads();
   }
   if (!single) return;
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(kRouteThreads) route_write_kernel(uint32_t n, 
     int b = 0;
     while (s_off[b + 1] <= k) ++b;
     const size_t pos = (size_t)rp.rank * rp.seg_cap + base[(size_t)b * n_blocks + blockIdx.x] + (k - s_off[b]);
-    route_copy_out(st, rp, b, pos, 0u, k);
+    route_copy_out<META, REC>(st, rp, b, pos, 0u, k);
   }
 }
 
@@ -265,9 +278,26 @@ static RouteParams make_route_params(const b200gs_route* r, const FrameLayout& B
 }
 
 // slice_ws: the slice's frame workspace after launch_preprocess_fwd (layout SL, n entries); BL: layout of the band
-// workspaces; scratch: route_scratch_bytes(n, world) bytes of the slice workspace
+// workspaces; scratch: route_scratch_bytes(n, world) bytes of the slice workspace.
+// what: kRouteAll = count + scan + everything written; kRouteMeta = count + scan + keys / rects / supertile counts only
+// (the records follow with kRouteRecords, which reuses the scanned offsets in `scratch` - typically on another stream,
+// beside the destination's depth sort).
+template <bool META, bool REC>
+static cudaError_t launch_route_write(uint32_t un, const void* slice_ws, const FrameLayout& SL, const RouteParams& p,
+                                      uint32_t n_blocks, const uint32_t* counts, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(route_write_kernel<META, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteStageBytes);
+    attr_set = true;
+  }
+  route_write_kernel<META, REC><<<(int)n_blocks, kRouteThreads, kRouteStageBytes, s>>>(
+      un, ws_ptr<uint32_t>(slice_ws, SL.depth_key), ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
+      ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2), p, n_blocks, counts);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& SL, const b200gs_route* route,
-                               const FrameLayout& BL, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+                               const FrameLayout& BL, void* scratch, size_t scratch_bytes, int what, cudaStream_t s) {
   if (scratch_bytes < route_scratch_bytes(n, route->world)) return cudaErrorInvalidValue;
   const RouteParams p = make_route_params(route, BL);
   const uint32_t n_blocks = route_blocks(n);
@@ -275,9 +305,11 @@ cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& S
   uint32_t* tiles = counts + (size_t)route->world * n_blocks;
   const uint32_t un = (uint32_t)(n > 0 ? n : 0);
   const int grid = (int)n_blocks;
+  if (what == kRouteRecords) return launch_route_write<false, true>(un, slice_ws, SL, p, n_blocks, counts, s);
   route_count_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
                                                     ws_ptr<uint2>(slice_ws, SL.rect), p, n_blocks, counts, tiles);
   route_scan_kernel<<<route->world, kRouteScanThreads, 0, s>>>(n_blocks, counts, tiles, p);
+  if (what == kRouteMeta) return launch_route_write<true, false>(un, slice_ws, SL, p, n_blocks, counts, s);
   const char* variant = getenv("B200GS_ROUTE_WRITE");
   if (variant && !strcmp(variant, "warp")) {
     route_write_warp_kernel<<<grid, kRouteThreads, 0, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
@@ -286,16 +318,7 @@ cudaError_t launch_route_slice(int n, const void* slice_ws, const FrameLayout& S
                                                            p, n_blocks, counts);
     return cudaGetLastError();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(route_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteStageBytes);
-    attr_set = true;
-  }
-  route_write_kernel<<<grid, kRouteThreads, kRouteStageBytes, s>>>(un, ws_ptr<uint32_t>(slice_ws, SL.depth_key),
-                                                    ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
-                                                    ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2), p,
-                                                    n_blocks, counts);
-  return cudaGetLastError();
+  return launch_route_write<true, true>(un, slice_ws, SL, p, n_blocks, counts, s);
 }
 
 // ---- destination side -------------------------------------------------------------------------------------------

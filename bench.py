@@ -393,28 +393,37 @@ def measure_tile_rows(env, steps, warm):
         k = lib.b200gs_profile_collect(ms_buf, call_buf, 32)
         lib.b200gs_profile_enable(0)
         regions = {lib.b200gs_profile_region_name(r).decode(): round(1e3 * ms_buf[r] / 5, 1) for r in range(k) if call_buf[r]}
+        if env.world > 1:                      # every rank's table: the slowest rank sets the frame time
+            every = [None] * env.world
+            env.dist.all_gather_object(every, regions)
+            regions = {"rank%d" % q: t for q, t in enumerate(every)}
         env.barrier()
         # measured alternatives (one knob changed at a time; every rank reads the same environment)
         variants = {}
         if os.environ.get("B200GS_TILE_ROWS_SWEEP") and env.world > 1:
-            for name, knob, val in (("route_write_per_warp_runs", "B200GS_ROUTE_WRITE", "warp"),
+            was_split = tr.split_records
+            for name, knob, val in (("records_and_keys_in_one_pass", "split", False),
+                                    ("one_pass_with_per_warp_runs", "B200GS_ROUTE_WRITE", "warp"),
                                     ("blend_strided_pixel_stores", "B200GS_ROW_STORES", "0"),
-                                    ("host_waits_for_counters_every_frame", None, None)):
-                if knob:
-                    os.environ[knob] = val
+                                    ("host_waits_for_counters_every_frame", "defer", False)):
+                if knob == "split":
+                    tr.split_records = val
+                elif knob == "defer":
+                    defer = val
                 else:
-                    defer = False
+                    os.environ[knob] = val
+                    tr.split_records = tr.split_records and knob != "B200GS_ROUTE_WRITE"
                 vms, _ = env.timed(frame, 20, 3)
                 tr.finish()
                 variants[name] = round(vms / 20, 4)
-                if knob:
+                tr.split_records = was_split
+                defer = os.environ.get("B200GS_TILE_ROWS_DEFER", "1") != "0"
+                if knob.startswith("B200GS_"):
                     del os.environ[knob]
-                else:
-                    defer = os.environ.get("B200GS_TILE_ROWS_DEFER", "1") != "0"
     del sc, sigma
     torch.cuda.empty_cache()
     return {"ms_per_frame": ms / steps, "frames_per_s": steps / (ms * 1e-3), "launches": int(launches), "bands": tr.bands,
-            "balanced": weights is not None, "checksum_root": checksum, "routed": bool(tr.routed), "deferred_check": defer,
+            "balanced": weights is not None, "checksum_root": checksum, "routed": bool(tr.routed), "records_on_side_stream": bool(tr.split_records), "deferred_check": defer,
             "frames_redone": int(redone), "regions_us_per_frame": regions, "variants_ms_per_frame": variants, **stats}
 
 
@@ -468,8 +477,9 @@ def run_mode_tile_rows(env, args):
                          "frames/s", r["ms_per_frame"] * env.K, env.K, "strong",
                          {"workload": TILE_ROWS_WORKLOAD["name"], "bands": r["bands"], "balanced_by_row_weights": r["balanced"],
                           "V": r["V"], "I_band_rank0": r["I_band"], "checksum_root": r["checksum_root"],
-                          "routed": r["routed"], "deferred_check": r["deferred_check"], "frames_redone": r["frames_redone"],
-                          "kernel_groups_us_per_frame_rank0": r["regions_us_per_frame"],
+                          "routed": r["routed"], "records_on_side_stream": r["records_on_side_stream"],
+                          "deferred_check": r["deferred_check"], "frames_redone": r["frames_redone"],
+                          "kernel_groups_us_per_frame": r["regions_us_per_frame"],
                           "variants_ms_per_frame": r["variants_ms_per_frame"],
                           "parallelism": (f"one band of tile rows per rank ({env.world}); every rank projects 1/{env.world} of "
                                           "the Gaussians and routes the splat records to the bands over NVLink peer memory "

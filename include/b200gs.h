@@ -327,11 +327,23 @@ typedef struct b200gs_route {
   int32_t band_row[B200GS_MAX_PEERS + 1];   /* band q = tile rows [band_row[q], band_row[q+1]) */
   void* band_ws[B200GS_MAX_PEERS];          /* band q's frame workspace as mapped into THIS process */
   size_t band_ws_bytes;
+  uint32_t flags, reserved;                 /* B200GS_ROUTE_* */
 } b200gs_route;
+/* b200gs_route_project_slice writes only what the destinations need BEFORE their blend (depth key, tile rect,
+ * supertile count: 16 of the 64 bytes per entry); the splat records follow with b200gs_route_records, which the caller
+ * puts on a second stream so that they cross NVLink beside the destinations' depth sort.  Two barriers then: one after
+ * b200gs_route_project_slice (before b200gs_render_project_routed), one after b200gs_route_records (before
+ * b200gs_render_rasterize*). */
+#define B200GS_ROUTE_RECORDS_LATER 1
 /* Source role: project `g_slice` (this rank's slice; cam = the FULL frame, no tile-row range) into the private
  * `slice_ws` (b200gs_workspace_sizes(g_slice->n, H, W, ...) bytes) and route the survivors. */
 int b200gs_route_project_slice(const b200gs_gaussians* g_slice, const b200gs_camera* cam, void* slice_ws,
                                size_t slice_bytes, const b200gs_route* route, void* stream);
+/* Second half of the source role when route->flags has B200GS_ROUTE_RECORDS_LATER: writes the splat records of the
+ * slice projected by the last b200gs_route_project_slice on `slice_ws` (n_slice entries, same camera, same route) to the
+ * positions that call assigned.  Any stream ordered after that call. */
+int b200gs_route_records(int32_t n_slice, const b200gs_camera* cam, void* slice_ws, size_t slice_bytes,
+                         const b200gs_route* route, void* stream);
 /* Destination role, after the barrier: gathers the routed entries of this band (cam = the band's camera: tile-row
  * range + B200GS_CAM_ROUTED) and depth-sorts them; the frame then continues with b200gs_render_rasterize* called with
  * n = world * seg_capacity and the same camera.  Statistics: V = entries routed here, I = their intersections. */

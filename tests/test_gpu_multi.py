@@ -81,6 +81,16 @@ def _worker(rank, world, port, out):
                     torch.cuda.synchronize()
                     if rank == 0:
                         out[f"{name}{rep}"] = img.cpu()
+            # records and keys in one pass (no side stream), and a frame whose counter check is deferred
+            assert tr.split_records
+            tr.split_records = False
+            img = tr.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, cams[1]["fx"], cams[1]["fy"],
+                            cams[1]["cx"], cams[1]["cy"], defer_check=True)
+            assert not tr.finish()
+            torch.cuda.synchronize()
+            if rank == 0:
+                out["tr_onepass"] = img.cpu()
+            tr.split_records = True
             # precomputed sigma / colour tensors (no tags): the routed slices are views of them
             from b200gs import api
             img = tr.render(leaves["pos"], api._real(col).clone(), leaves["opacity_raw"], api._real(sigma).clone(), c2w,
@@ -141,7 +151,7 @@ def test_dp_gradients_and_tile_row_bands_match_single_gpu():
                              cams[1]["cx"], cams[1]["cy"]).cpu()
     assert torch.equal(out["img0"], full) and torch.equal(out["img1"], full)
     assert torch.equal(out["tr0"], full) and torch.equal(out["tr2"], full) and torch.equal(out["tr_weighted"], full)
-    assert torch.equal(out["trrep0"], full) and torch.equal(out["trrep2"], full)
+    assert torch.equal(out["trrep0"], full) and torch.equal(out["trrep2"], full) and torch.equal(out["tr_onepass"], full)
     with torch.no_grad():
         from b200gs import api
         unfused = b200gs.render(leaves["pos"], api._real(col).clone(), leaves["opacity_raw"], api._real(sigma).clone(), c2w,

@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _routed_frame(b200gs, args, H, W, bands, dev):
+def _routed_frame(b200gs, args, H, W, bands, dev, split=False):
     """Emulates len(bands) ranks in this process; returns (image, per band (V, I))."""
     from b200gs import _lib, ops
     lib = _lib.load()
@@ -30,7 +30,8 @@ def _routed_frame(b200gs, args, H, W, bands, dev):
     full.tile_row_begin = full.tile_row_end = 0
     routes = []
     for r in range(world):
-        route = _lib.Route(world=world, rank=r, seg_capacity=per, band_ws_bytes=ws_bytes)
+        route = _lib.Route(world=world, rank=r, seg_capacity=per, band_ws_bytes=ws_bytes,
+                           flags=_lib.ROUTE_RECORDS_LATER if split else 0)
         for q in range(world):
             route.band_ws[q] = band_ws[q].data_ptr()
             route.band_row[q] = min(bands[q][0], n_rows)
@@ -40,6 +41,8 @@ def _routed_frame(b200gs, args, H, W, bands, dev):
     for r in range(world):                                   # source role of every rank
         lo, hi = min(n, r * per), min(n, (r + 1) * per)
         keep.append(ops.route_project_slice(*args[:8], c2w, full, routes[r], lo, hi, slice_ws))
+        if split:                                            # ... records in a second pass (a side stream in real life)
+            ops.route_records(hi - lo, c2w, full, routes[r], slice_ws)
     counts = []
     for r in range(world):                                   # destination role of every rank
         band = copy.copy(cfg)
@@ -81,6 +84,8 @@ def test_routed_bands_equal_the_one_gpu_frame(n, H, W, log_scale):
                 assert (args[2] is not None) == fused
                 img, counts = _routed_frame(b200gs, args, H, W, bands, dev)
                 assert torch.equal(img, full), (fused, bands, float((img - full).abs().max()))
+                img2, counts2 = _routed_frame(b200gs, args, H, W, bands, dev, split=True)
+                assert torch.equal(img2, full) and counts2 == counts, (fused, bands)
                 # every intersection belongs to exactly one band
                 frame = ops.Frame(*ops._gaussians(*args[:8]), args[-1], c2w, dev)
                 with torch.cuda.device(dev):
