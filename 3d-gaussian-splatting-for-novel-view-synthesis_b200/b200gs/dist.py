@@ -214,9 +214,11 @@ class TileRowRenderer:
             routed = _lib.env("B200GS_TILE_ROWS_ROUTED", "1") != "0"
         self.routed = bool(routed) and self.world > 1
         self._route = None                # (b200gs_route, N it was sized for, workspace area, band workspace view)
-        # the 48-byte splat records cross NVLink on a second stream, beside the destinations' depth sort; only the 16
-        # bytes per entry the binning needs are on the critical path (B200GS_ROUTE_SPLIT=0: everything in one go)
-        self.split_records = self.routed and _lib.env("B200GS_ROUTE_SPLIT", "1") != "0"
+        # opt-in (B200GS_ROUTE_SPLIT=1): the 48-byte splat records cross NVLink on a second stream, beside the
+        # destinations' depth sort, and only the 16 bytes per entry the binning needs stay on the critical path.
+        # Measured at 8 ranks: 0.555 against 0.540 ms per frame - a radix-pass CTA holds a whole SM's registers, so
+        # the two do not share SMs, and the scheme pays a fourth barrier; off by default.
+        self.split_records = self.routed and _lib.env("B200GS_ROUTE_SPLIT", "0") == "1"
         self._side = None
         self._slice_ws = [None]
         self._pending = None              # frame whose counters have not been looked at yet (defer_check)

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_routed_kernel(int world
 
 cudaError_t launch_gather_routed(int world, uint32_t seg_cap, void* band_ws, const FrameLayout& BL, uint32_t* out_keys,
                                  uint32_t* out_ids, uint32_t* depth_hist, const DepthKeyPlan& kp, cudaStream_t s) {
-  dim3 grid((seg_cap + kGatherTile - 1) / kGatherTile, world);
+  dim3 grid((seg_cap + kGatherTile - 1) / kGatherTile, world);      // blocks behind a segment's entries leave at once
   gather_routed_kernel<<<grid, kGatherThreads, 0, s>>>(world, seg_cap,
                                                        ws_ptr<uint2>(band_ws, BL.header + kRouteInOffset),
                                                        ws_ptr<uint32_t>(band_ws, BL.depth_key), out_keys, out_ids,

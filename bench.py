@@ -402,7 +402,7 @@ def measure_tile_rows(env, steps, warm):
         variants = {}
         if os.environ.get("B200GS_TILE_ROWS_SWEEP") and env.world > 1:
             was_split = tr.split_records
-            for name, knob, val in (("records_and_keys_in_one_pass", "split", False),
+            for name, knob, val in (("records_on_a_side_stream", "split", True),
                                     ("one_pass_with_per_warp_runs", "B200GS_ROUTE_WRITE", "warp"),
                                     ("blend_strided_pixel_stores", "B200GS_ROW_STORES", "0"),
                                     ("host_waits_for_counters_every_frame", "defer", False)):

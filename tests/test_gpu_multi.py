@@ -81,16 +81,16 @@ def _worker(rank, world, port, out):
                     torch.cuda.synchronize()
                     if rank == 0:
                         out[f"{name}{rep}"] = img.cpu()
-            # records and keys in one pass (no side stream), and a frame whose counter check is deferred
-            assert tr.split_records
-            tr.split_records = False
+            # records on a side stream behind the keys (opt-in), and a frame whose counter check is deferred
+            assert not tr.split_records
+            tr.split_records = True
             img = tr.render(leaves["pos"], col, leaves["opacity_raw"], sigma, c2w, cams[1]["fx"], cams[1]["fy"],
                             cams[1]["cx"], cams[1]["cy"], defer_check=True)
             assert not tr.finish()
             torch.cuda.synchronize()
             if rank == 0:
                 out["tr_onepass"] = img.cpu()
-            tr.split_records = True
+            tr.split_records = False
             # precomputed sigma / colour tensors (no tags): the routed slices are views of them
             from b200gs import api
             img = tr.render(leaves["pos"], api._real(col).clone(), leaves["opacity_raw"], api._real(sigma).clone(), c2w,
