@@ -379,8 +379,8 @@ def measure_tile_rows(env, steps, warm):
         img = frame(0)
         tr.finish()
         torch.cuda.synchronize()
-        env.barrier()
         checksum = float(img.double().sum()) if env.rank == tr.root else 0.0
+        env.barrier()      # (the root's checksum must not delay its first barrier of the profiled frames below)
         stats = dict(V=tr.last_frame.n_visible, I_band=tr.last_frame.n_isect)
         # per kernel group, this rank (CUDA events inside the library around every group; a separate, untimed pass)
         lib = env.lib
