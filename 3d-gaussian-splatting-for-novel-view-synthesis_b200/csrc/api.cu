@@ -522,6 +522,8 @@ int b200gs_render_project(const b200gs_gaussians* g, const b200gs_camera* cam, v
   return B200GS_OK;
 }
 
+static_assert(sizeof(b200gs_route) == 12 + 17 * 4 + 16 * 8 + 8 + 8, "b200gs_route layout (b200gs/_lib.py::Route mirrors it)");
+
 static int check_route(const b200gs_route* r, const char* who) {
   if (!r || r->world < 1 || r->world > B200GS_MAX_PEERS || r->rank < 0 || r->rank >= r->world || r->seg_capacity == 0)
     return fail(B200GS_ERR_ARG, std::string(who) + ": bad route (world, rank or seg_capacity)");

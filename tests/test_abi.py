@@ -42,6 +42,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.PeerLayout) == 3 * 8 * 8 + 16
     assert ctypes.sizeof(_lib.PeerGroup) == 8 + 16 * 8 + 8
     assert ctypes.sizeof(_lib.PeerTensor) == 32
+    assert ctypes.sizeof(_lib.Route) == 12 + 17 * 4 + 16 * 8 + 8 + 8       # static_assert of the same figure in api.cu
 
 
 def test_no_cpu_fallback():
