@@ -60,6 +60,25 @@ def shard_tile_rows(n_rows: int, world: int, weights: Sequence[float] | None = N
     return [(cuts[i], max(cuts[i], cuts[i + 1])) for i in range(world)]
 
 
+def route_plan(n: int, world: int, bands: Sequence[Tuple[int, int]], n_rows: int):
+    """Host arithmetic of a routed tile-row frame (csrc/route.cu): returns (per, slices, band_row).
+
+    `per` = slice length = capacity of one (source rank, band) segment: ceil(n / world) rounded up to 32 entries, so
+    that every slice starts 16-byte aligned in all six parameter arrays; slices[r] = [begin, end) of the Gaussians rank
+    r projects (trailing ranks may get empty slices); band_row[q] = first tile row of band q, band_row[world] = n_rows
+    (the bands of `shard_tile_rows` are contiguous, an empty band is [r, r))."""
+    if world <= 0 or n < 0:
+        raise ValueError("world must be positive and n non-negative")
+    if len(bands) != world:
+        raise ValueError("need one band per rank")
+    per = max(32, -(-((n + world - 1) // world) // 32) * 32)
+    slices = [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+    band_row = [min(int(b), n_rows) for b, _e in bands] + [n_rows]
+    if any(band_row[q + 1] < band_row[q] for q in range(world)) or band_row[0] != 0:
+        raise ValueError("bands must be contiguous, in rank order and start at row 0")
+    return per, slices, band_row
+
+
 def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: bool = False) -> None:
     """SUM all-reduce of `.grad` of every parameter (in place).  Ranks that have no gradient for a
     parameter contribute zeros, so densify/prune decisions taken from the reduced gradients stay
@@ -273,7 +292,7 @@ class TileRowRenderer:
         if self._route is not None and self._route[1] >= n:
             return self._route
         self._route = None
-        per = max(32, -(-((n + self.world - 1) // self.world) // 32) * 32)     # slice length: a multiple of 32 entries
+        per, _, _ = route_plan(n, self.world, self.bands, self.n_rows)         # slice length: a multiple of 32 entries
         lib = _lib.load()
         ws_bytes, _ = ops._sizes(lib, self.world * per, self.H, self.W, 0)
         area = peer.PeerArea([(ws_bytes + 3) // 4], self.device, group=self.group, multicast=False)
@@ -296,15 +315,15 @@ class TileRowRenderer:
         pos, cfg, c2w = args[0], args[-1], args[-2]
         n = int(pos.shape[0])
         route, _, area, ws, per = self._ensure_route(n)
-        for q, (b, _e) in enumerate(self.bands):          # shard_tile_rows: contiguous, band q = [cut q, cut q+1)
-            route.band_row[q] = min(b, self.n_rows)
-        route.band_row[self.world] = self.n_rows
+        _, slices, band_row = route_plan(n, self.world, self.bands, self.n_rows)
+        for q, row in enumerate(band_row):                # shard_tile_rows: contiguous, band q = [cut q, cut q+1)
+            route.band_row[q] = row
         full = copy.copy(cfg)
         full.tile_row_begin = full.tile_row_end = 0
         full.out, full.out_ptr, full.keep_outside_band = None, 0, False
         cfg.keep_outside_band = True
         cfg.out_ptr = self.root_ptr
-        lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        lo, hi = slices[self.rank]
         # root has consumed the previous frame and every rank has finished its previous band: frame buffer and band
         # workspaces may be overwritten
         self.area.barrier()

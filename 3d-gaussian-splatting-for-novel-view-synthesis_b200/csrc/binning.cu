@@ -20,7 +20,8 @@
 namespace gs {
 
 constexpr int kEmitBlock = 256;
-constexpr int kSplitParts = 4;     // CTAs per supertile: each takes a contiguous quarter of the supertile's list
+constexpr int kSplitParts = 4;     // CTAs per supertile of a whole frame: each takes a contiguous part of the supertile's list
+constexpr int kSplitPartsMax = 16; // a band has few supertiles with the same long lists: more parts (launch_split_super)
 constexpr int kSuperTiles = kSuperX * kSuperY;   // 32: one bit per tile in a 32-bit mask
 
 // One thread per depth rank r.  Gaussian id = order[r]; its supertile pairs go to [offsets[r], +count).
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
                                                                     uint32_t capacity,
                                                                     const b200gs_frame_stats* __restrict__ stats,
                                                                     int super_x, int super_y0, int tiles_x, int tiles_y,
-                                                                    uint32_t* __restrict__ tile_count,
+                                                                    int parts, uint32_t* __restrict__ tile_count,
                                                                     uint32_t* __restrict__ part_total,
                                                                     uint2* __restrict__ ranges,
                                                                     uint32_t* __restrict__ lists) {
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
   __shared__ uint32_t s_red[kSplitWarps];
   __shared__ uint32_t s_seg[2];
   // s = band-local supertile id (the sort key); (sx, sy) = its position in the frame
-  const int s = blockIdx.x / kSplitParts, part = blockIdx.x % kSplitParts, sx = s % super_x, sy = super_y0 + s / super_x;
+  const int s = blockIdx.x / parts, part = blockIdx.x % parts, sx = s % super_x, sy = super_y0 + s / super_x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t count = stats->n_super;
   if (count > capacity || stats->overflow) count = 0;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
     // totals the counting pass left behind (one word per CTA: summing the per-tile counts here instead made every
     // CTA read up to 128 words per earlier supertile - 67 M loads per headline frame)
     uint32_t acc = 0;
-    for (int i = tid; i < s * kSplitParts; i += kSplitThreads) acc += part_total[i];
+    for (int i = tid; i < s * parts; i += kSplitThreads) acc += part_total[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s_red[warp] = acc;
@@ -149,9 +150,9 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
 #pragma unroll
       for (int w = 0; w < kSplitWarps; ++w) base += s_red[w];
       uint32_t c = 0, before = 0;     // whole-supertile count of tile `lane`, and the part of it in earlier parts
-#pragma unroll
-      for (int q = 0; q < kSplitParts; ++q) {
-        const uint32_t v = tile_count[(s * kSplitParts + q) * kSuperTiles + lane];
+#pragma unroll 4
+      for (int q = 0; q < parts; ++q) {
+        const uint32_t v = tile_count[(s * parts + q) * kSuperTiles + lane];
         c += v;
         if (q < part) before += v;
       }
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
   __syncthreads();
   // this CTA's quarter of the supertile's list (boundaries are multiples of 32 so warp-chunks stay whole)
   const uint32_t seg_lo = s_seg[0], seg_hi = s_seg[1];
-  const uint32_t per = ((seg_hi - seg_lo + kSplitParts - 1) / kSplitParts + 31u) & ~31u;
+  const uint32_t per = ((seg_hi - seg_lo + (uint32_t)parts - 1) / (uint32_t)parts + 31u) & ~31u;
   const uint32_t lo = min(seg_lo + part * per, seg_hi), hi = min(lo + per, seg_hi);
   const uint32_t lane_lt = (1u << lane) - 1u;
   uint32_t my_total = 0;   // WRITE == false: lane t of every warp accumulates the count of tile t
@@ -229,9 +230,9 @@ __global__ void __launch_bounds__(kSplitThreads) split_super_kernel(const uint32
     __syncthreads();
     if (tid < kSuperTiles) {
       const uint32_t c = s_run[tid];
-      tile_count[(s * kSplitParts + part) * kSuperTiles + tid] = c;
+      tile_count[(s * parts + part) * kSuperTiles + tid] = c;
       const uint32_t tot = __reduce_add_sync(0xffffffffu, c);      // warp 0 = the 32 tiles
-      if (tid == 0) part_total[s * kSplitParts + part] = tot;
+      if (tid == 0) part_total[s * parts + part] = tot;
     }
   }
 }
@@ -240,12 +241,25 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
                                uint32_t capacity, const b200gs_frame_stats* stats, int super_x, int super_y0, int super_y,
                                int tiles_x, int tiles_y, uint32_t* tile_count, uint2* ranges, uint32_t* lists,
                                cudaStream_t s) {
-  const int grid = super_x * super_y * kSplitParts;
-  if (grid <= 0) return cudaSuccess;
+  // CTAs per supertile: 4 for a whole frame (2 040 CTAs at 1080p).  A band of tile rows has few supertiles whose lists
+  // are as long as ever - an eighth of a 4K frame: 150 supertiles x ~7 000 pairs, 600 CTAs walking two to three 1024-entry
+  // chunks each, 72 us for count + write - so it gets more parts, up to what the workspace section (sized for the whole
+  // frame's supertiles x 4) holds: ~2 000 CTAs of one chunk each.
+  const int n_super = super_x * super_y;
+  if (n_super <= 0) return cudaSuccess;
+  const int full = ceil_div(tiles_x, kSuperX) * ceil_div(tiles_y, kSuperY);
+  int parts = kSplitParts;
+  static const int parts_env = getenv("B200GS_SPLIT_PARTS") ? atoi(getenv("B200GS_SPLIT_PARTS")) : 0;
+  const int room = kSplitParts * full / n_super;
+  int want = parts_env > 0 ? parts_env : 2048 / n_super;
+  if (want > kSplitPartsMax) want = kSplitPartsMax;
+  if (want > room) want = room;
+  if (want > parts) parts = want;
+  const int grid = n_super * parts;
   uint32_t* part_total = tile_count + (size_t)grid * kSuperTiles;     // one word per CTA, behind the per-tile counts
   // measured on the headline frame (count + write): 256 threads 64.9 us, 128 threads 81.7 us
   static const int threads = getenv("B200GS_SPLIT_THREADS") ? atoi(getenv("B200GS_SPLIT_THREADS")) : 256;
-#define GS_SPLIT_ARGS keys, vals, rect, capacity, stats, super_x, super_y0, tiles_x, tiles_y, tile_count, part_total, ranges, lists
+#define GS_SPLIT_ARGS keys, vals, rect, capacity, stats, super_x, super_y0, tiles_x, tiles_y, parts, tile_count, part_total, ranges, lists
   if (threads == 256) {
     if (write) split_super_kernel<true, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);
     else split_super_kernel<false, 256><<<grid, 256, 0, s>>>(GS_SPLIT_ARGS);

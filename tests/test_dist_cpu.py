@@ -87,6 +87,33 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("n,world", [(6_000_000, 8), (1000, 3), (50, 8), (0, 2), (33, 1)])
+def test_route_plan_slices_cover_the_gaussians_once(n, world):
+    """Routed tile-row frames: slices are aligned, disjoint, cover [0, n) in rank order (the segment order the stable
+    depth sort relies on) and fit their segments; band rows are the contiguous cuts of shard_tile_rows."""
+    from b200gs.dist import route_plan, shard_tile_rows
+    n_rows = 135
+    for weights in (None, [1.0] + [0.0] * (n_rows - 1), [float(i % 7) for i in range(n_rows)]):
+        bands = shard_tile_rows(n_rows, world, weights)
+        per, slices, band_row = route_plan(n, world, bands, n_rows)
+        assert per % 32 == 0 and per * world >= n
+        assert slices[0][0] == 0 and slices[-1][1] == n
+        for r in range(world):
+            lo, hi = slices[r]
+            assert lo % 32 == 0 or lo == n
+            assert 0 <= hi - lo <= per
+            if r:
+                assert lo == slices[r - 1][1]
+        assert band_row[0] == 0 and band_row[-1] == n_rows and len(band_row) == world + 1
+        assert all(band_row[q] <= band_row[q + 1] for q in range(world))
+        for q, (b, e) in enumerate(bands):
+            assert (band_row[q], band_row[q + 1]) == (b, e) or e <= b
+    with pytest.raises(ValueError):
+        route_plan(10, 2, [(0, 5)], 10)
+    with pytest.raises(ValueError):
+        route_plan(10, 2, [(5, 10), (0, 5)], 10)
+
+
 def test_two_rank_gloo_allreduce_and_bands():
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
