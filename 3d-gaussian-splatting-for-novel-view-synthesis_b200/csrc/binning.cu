@@ -244,14 +244,15 @@ cudaError_t launch_split_super(bool write, const uint32_t* keys, const uint32_t*
   // CTAs per supertile: 4 for a whole frame (2 040 CTAs at 1080p).  A band of tile rows has few supertiles whose lists
   // are as long as ever - an eighth of a 4K frame: 150 supertiles x ~7 000 pairs, 600 CTAs walking two to three 1024-entry
   // chunks each, 72 us for count + write - so it gets more parts, up to what the workspace section (sized for the whole
-  // frame's supertiles x 4) holds: ~2 000 CTAs of one chunk each.
+  // frame's supertiles x 4) holds.  Measured on that band (tools/routed_probe.py): 4 parts 73 us, 8 parts 56 us, 13 parts
+  // 62 us (every CTA of the write pass sums the totals of all CTAs before it) - hence one wave of resident CTAs.
   const int n_super = super_x * super_y;
   if (n_super <= 0) return cudaSuccess;
   const int full = ceil_div(tiles_x, kSuperX) * ceil_div(tiles_y, kSuperY);
   int parts = kSplitParts;
   static const int parts_env = getenv("B200GS_SPLIT_PARTS") ? atoi(getenv("B200GS_SPLIT_PARTS")) : 0;
   const int room = kSplitParts * full / n_super;
-  int want = parts_env > 0 ? parts_env : 2048 / n_super;
+  int want = parts_env > 0 ? parts_env : 1200 / n_super;
   if (want > kSplitPartsMax) want = kSplitPartsMax;
   if (want > room) want = room;
   if (want > parts) parts = want;
