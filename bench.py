@@ -103,6 +103,43 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class Deadline:
+    """A rank-local deadline around optional work: `start()` arms it; if `cancel()` does not come first, `on_expire()`
+    runs on a timer thread and the process ends with exit code 0 (`exit_fn`).  Exactly one side wins: `cancel()`
+    returns False once the timer thread has taken over, and the caller must then leave the printing to it."""
+
+    def __init__(self, seconds: float, on_expire, exit_fn=os._exit):
+        self._lock = threading.Lock()
+        self._taken = False
+        self._on_expire, self._exit = on_expire, exit_fn
+        self._timer = threading.Timer(max(0.0, seconds), self._fire)
+        self._timer.daemon = True
+        self._started = False
+
+    def start(self):
+        self._started = True
+        self._timer.start()
+
+    def _fire(self):
+        with self._lock:
+            if self._taken:
+                return
+            self._taken = True
+        try:
+            self._on_expire()
+        finally:
+            self._exit(0)
+
+    def cancel(self) -> bool:
+        with self._lock:
+            if self._taken:
+                return False
+            self._taken = True
+        if self._started:
+            self._timer.cancel()
+        return True
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------------
@@ -741,111 +778,126 @@ def run_mode_render(env, args):
         del ex, proj, bins, img_cpu
     del fr, img_view0
 
-    # ---- the other two north-star modes on a few steps (reported inside `config`; `--mode` runs them at full length) --
+    # ---- the other two north-star modes on a few steps (reported inside `config`; `--mode` runs them at full length).
+    #      Everything the headline line needs is measured by now: the two legs run under a deadline, so that a leg that
+    #      hangs (one rank failing inside a peer-memory exchange leaves the others at a barrier) costs its own numbers, not
+    #      the line - on expiry rank 0 prints the line with the leg marked, and every rank leaves with exit code 0 ----------
     extra_steps = max(4, min(K, 10))
-    tile_rows = None
+    extras = {"tile_rows": None, "train": {"peer": None, "nccl": None, "peer_error": None, "peer_transport": None}}
+
+    def build_line(tile_rows, train):
+        hbm, peak_src, sm_max = peaks()
+        counts = ncu_counts()
+        bytes_model = algorithmic_bytes(N, V, I, P, tiles, S)
+        table = {}
+        for name, (ms, calls) in {**opt_regions, **train_regions, **fwd_regions}.items():
+            b = bytes_model.get(name)
+            row = {"ms": round(ms, 5), "calls": calls, "alg_bytes": b,
+                   "gbs": None if b is None else round(b / (ms * 1e-3) / 1e9, 1),
+                   "frac_hbm": None if b is None else round(b / (ms * 1e-3) / 1e9 / hbm, 4)}
+            c = counts.get(name) or {}
+            if isinstance(c, dict) and c.get("inst_executed"):
+                # warp instructions issued per second against the issue peak: SMs x 4 schedulers x SM clock
+                row["frac_issue"] = round(c["inst_executed"] / (148 * 4 * sm_max * 1e6 * ms * 1e-3), 4)
+            table[name] = row
+        step_kernels_ms = sum(v[0] for v in fwd_regions.values())
+        dom = max(fwd_regions, key=lambda k: fwd_regions[k][0])
+        dom_ms = fwd_regions[dom][0]
+        dom_counts = counts.get(dom) if isinstance(counts.get(dom), dict) else {}
+        issue_peak = 148 * 4 * sm_max * 1e6            # warp instructions per second the four schedulers of every SM can issue
+        hbm_obj = {"achieved": bytes_model[dom] / (dom_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                   "frac": bytes_model[dom] / (dom_ms * 1e-3) / 1e9 / hbm, "alg_bytes_per_launch": bytes_model[dom],
+                   "peak_source": peak_src}
+        if dom_counts.get("inst_executed"):
+            ach = dom_counts["inst_executed"] / (dom_ms * 1e-3)
+            roofline = {"kernel": dom, "bound": "fp32_issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9,
+                        "unit": "G warp-instructions/s", "frac": ach / issue_peak,
+                        "traffic": dom_counts.get("dram_bytes"), "ms_per_launch": dom_ms,
+                        "share_of_step_kernel_time": dom_ms / step_kernels_ms,
+                        "inst_executed_per_launch": dom_counts["inst_executed"],
+                        "inst_source": "ncu --set full capture of the same workload/view (profiles/ncu_traffic.json); time measured live",
+                        "peak_source": f"148 SMs x 4 issue slots x {sm_max:.0f} MHz (max SM clock, MEASURED_PEAKS.json)",
+                        "hbm": hbm_obj,
+                        "note": "the blend is FP32-issue / MUFU bound (SURVEY.md 8d): the HBM object is kept for reference only"}
+        else:
+            roofline = {"kernel": dom, "bound": "hbm", **hbm_obj, "traffic": dom_counts.get("dram_bytes") if dom_counts else None,
+                        "ms_per_launch": dom_ms, "share_of_step_kernel_time": dom_ms / step_kernels_ms}
+        fps = world * K / (ms_render * 1e-3)
+        best_train = min([x for x in (train["peer"], train["nccl"]) if x is not None], default=None)
+        config = {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I,
+                  "super_pairs_view0": S,
+                  "parallelism": f"frames/views sharded round-robin over {world} rank(s); per rank frames are software-"
+                                 "pipelined by b200gs.RenderPipeline (project + binning of frame i+1 on a high-priority "
+                                 "stream while frame i is blended on a second stream); Gaussians replicated",
+                  "capacity_mode": os.environ.get("B200GS_CAPACITY_MODE"),
+                  "l2_policy": "inputs larger than L2: every step streams 236 MB of parameters (L2 = 126 MB) and a different view",
+                  # the other ways of counting frames, in keys a driver keeps
+                  "single_stream_fps": world * K / (ms_render_1s * 1e-3),
+                  "sync_per_frame_fps": world * K / s_sync_per_frame,
+                  "sync_per_frame_note": "the reference's own timed region (render_trained.py:337-349): synchronize before and "
+                                         "after every evaluate_sh + render, host clock",
+                  "e2e_f32_frames_fps": world * K / s_e2e_f32,
+                  "train_full_iteration": None if best_train is None else {
+                      "views_per_s": world * extra_steps / (best_train * 1e-3), "ms_per_iteration": best_train / extra_steps,
+                      "ms_peer_adam": None if train["peer"] is None else train["peer"] / extra_steps,
+                      "ms_nccl_bucket": None if train["nccl"] is None else train["nccl"] / extra_steps,
+                      "transport": train["peer_transport"], "peer_error": train["peer_error"], "steps": extra_steps,
+                      "what": "scripts/train.py:463-538 on the fused path, views data-parallel (bench.py --mode train)"},
+                  "tile_rows_4k": None if tile_rows is None else (tile_rows if "error" in tile_rows else {
+                      "frames_per_s": tile_rows["frames_per_s"], "ms_per_frame": tile_rows["ms_per_frame"],
+                      "bands": tile_rows["bands"], "steps": extra_steps,
+                      "what": "6M Gaussians, 3840x2160, one band of tile rows per rank (bench.py --mode tile_rows)"}),
+                  "parity": parity}
+        line = base_line(env, METRIC, fps, "frames/s", ms_render, K, "weak", config)
+        line.update({
+            "single_stream": {"value": world * K / (ms_render_1s * 1e-3), "unit": "frames/s", "ms_per_step": ms_render_1s / K,
+                              "note": "one frame at a time on one stream (frame latency)"},
+            "train": {"with_l1_ssim_loss": {"value": K / (ms_train_loss * 1e-3), "unit": "it/s", "ms_per_step": ms_train_loss / K,
+                                            "step": "build_sigma + evaluate_sh + render + b200gs.compute_loss (fused L1 + SSIM, "
+                                                    "losses.py:158) + backward, one GPU's share"}},
+            "e2e": {"value": world * K / s_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 3,
+                    "api": "b200gs.evaluate_sh + b200gs.RenderPipeline (pose from pinned host memory in; finished frame "
+                           "delivered to pinned host memory as uint8 through b200gs.to_uint8 - the conversion the reference "
+                           "scripts apply to every frame they keep, render_trained.py:357, bit-identical - 3 B/pixel over PCIe)"},
+            "e2e_f32_frames": {"value": world * K / s_e2e_f32, "unit": "frames/s", "h2d_bytes_per_step": 64,
+                               "d2h_bytes_per_step": H * W * 12,
+                               "api": "the same loop delivering the raw fp32 image (12 B/pixel): PCIe-bound on one GPU and "
+                                      "host-fabric-bound beyond two (profiles/r02_d2h_ceiling.json)"},
+            "e2e_host_buffers": {"value": host_fps, "unit": "frames/s", "h2d_bytes_per_step": 236 * N + 64,
+                                 "d2h_bytes_per_step": H * W * 12,
+                                 "api": "b200gs_render_host (C ABI, every parameter array uploaded from host memory each call)"},
+            "gpu_launches": int(launches_render),
+            "gpu_launches_train": int(launches_train),
+            "roofline": roofline,
+            "kernels": table,
+            "clocks": clocks,
+            "cpu_baseline": cpu_base,
+            "parity": parity,
+        })
+        return line
+
+    def on_deadline():
+        if rank != 0:
+            return
+        tr_leg, tn_leg = extras["tile_rows"], dict(extras["train"])
+        if tr_leg is None:
+            tr_leg = {"error": "deadline: the tile-row leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"}
+        if tn_leg["peer"] is None and tn_leg["nccl"] is None:
+            tn_leg["peer_error"] = "deadline: the training leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"
+        emit(build_line(tr_leg, tn_leg))
+
+    deadline = Deadline(float(os.environ.get("B200GS_BENCH_EXTRAS_DEADLINE_S", "300")), on_deadline)
     if not args.no_extras:
+        deadline.start()
         try:
-            tile_rows = measure_tile_rows(env, extra_steps, 3)
+            extras["tile_rows"] = measure_tile_rows(env, extra_steps, 3)
         except Exception as e:                    # noqa: BLE001 - reported, must not take the line with it
-            tile_rows = {"error": f"{type(e).__name__}: {e}"[:300]}
-    train = {"peer": None, "nccl": None, "peer_error": None, "peer_transport": None}
-    if not args.no_extras:
-        train = measure_train_iteration(env, sc, cams, extra_steps, 4, want_nccl=True)
-
-    if rank != 0:
-        env.finish()
-        return 0
-
-    hbm, peak_src, sm_max = peaks()
-    counts = ncu_counts()
-    bytes_model = algorithmic_bytes(N, V, I, P, tiles, S)
-    table = {}
-    for name, (ms, calls) in {**opt_regions, **train_regions, **fwd_regions}.items():
-        b = bytes_model.get(name)
-        row = {"ms": round(ms, 5), "calls": calls, "alg_bytes": b,
-               "gbs": None if b is None else round(b / (ms * 1e-3) / 1e9, 1),
-               "frac_hbm": None if b is None else round(b / (ms * 1e-3) / 1e9 / hbm, 4)}
-        c = counts.get(name) or {}
-        if isinstance(c, dict) and c.get("inst_executed"):
-            # warp instructions issued per second against the issue peak: SMs x 4 schedulers x SM clock
-            row["frac_issue"] = round(c["inst_executed"] / (148 * 4 * sm_max * 1e6 * ms * 1e-3), 4)
-        table[name] = row
-    step_kernels_ms = sum(v[0] for v in fwd_regions.values())
-    dom = max(fwd_regions, key=lambda k: fwd_regions[k][0])
-    dom_ms = fwd_regions[dom][0]
-    dom_counts = counts.get(dom) if isinstance(counts.get(dom), dict) else {}
-    issue_peak = 148 * 4 * sm_max * 1e6            # warp instructions per second the four schedulers of every SM can issue
-    hbm_obj = {"achieved": bytes_model[dom] / (dom_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-               "frac": bytes_model[dom] / (dom_ms * 1e-3) / 1e9 / hbm, "alg_bytes_per_launch": bytes_model[dom],
-               "peak_source": peak_src}
-    if dom_counts.get("inst_executed"):
-        ach = dom_counts["inst_executed"] / (dom_ms * 1e-3)
-        roofline = {"kernel": dom, "bound": "fp32_issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9,
-                    "unit": "G warp-instructions/s", "frac": ach / issue_peak,
-                    "traffic": dom_counts.get("dram_bytes"), "ms_per_launch": dom_ms,
-                    "share_of_step_kernel_time": dom_ms / step_kernels_ms,
-                    "inst_executed_per_launch": dom_counts["inst_executed"],
-                    "inst_source": "ncu --set full capture of the same workload/view (profiles/ncu_traffic.json); time measured live",
-                    "peak_source": f"148 SMs x 4 issue slots x {sm_max:.0f} MHz (max SM clock, MEASURED_PEAKS.json)",
-                    "hbm": hbm_obj,
-                    "note": "the blend is FP32-issue / MUFU bound (SURVEY.md 8d): the HBM object is kept for reference only"}
-    else:
-        roofline = {"kernel": dom, "bound": "hbm", **hbm_obj, "traffic": dom_counts.get("dram_bytes") if dom_counts else None,
-                    "ms_per_launch": dom_ms, "share_of_step_kernel_time": dom_ms / step_kernels_ms}
-    fps = world * K / (ms_render * 1e-3)
-    best_train = min([x for x in (train["peer"], train["nccl"]) if x is not None], default=None)
-    config = {"workload": wl["name"], "N": N, "H": H, "W": W, "views": wl["n_views"], "V_view0": V, "I_view0": I,
-              "super_pairs_view0": S,
-              "parallelism": f"frames/views sharded round-robin over {world} rank(s); per rank frames are software-"
-                             "pipelined by b200gs.RenderPipeline (project + binning of frame i+1 on a high-priority "
-                             "stream while frame i is blended on a second stream); Gaussians replicated",
-              "capacity_mode": os.environ.get("B200GS_CAPACITY_MODE"),
-              "l2_policy": "inputs larger than L2: every step streams 236 MB of parameters (L2 = 126 MB) and a different view",
-              # the other ways of counting frames, in keys a driver keeps
-              "single_stream_fps": world * K / (ms_render_1s * 1e-3),
-              "sync_per_frame_fps": world * K / s_sync_per_frame,
-              "sync_per_frame_note": "the reference's own timed region (render_trained.py:337-349): synchronize before and "
-                                     "after every evaluate_sh + render, host clock",
-              "e2e_f32_frames_fps": world * K / s_e2e_f32,
-              "train_full_iteration": None if best_train is None else {
-                  "views_per_s": world * extra_steps / (best_train * 1e-3), "ms_per_iteration": best_train / extra_steps,
-                  "ms_peer_adam": None if train["peer"] is None else train["peer"] / extra_steps,
-                  "ms_nccl_bucket": None if train["nccl"] is None else train["nccl"] / extra_steps,
-                  "transport": train["peer_transport"], "peer_error": train["peer_error"], "steps": extra_steps,
-                  "what": "scripts/train.py:463-538 on the fused path, views data-parallel (bench.py --mode train)"},
-              "tile_rows_4k": None if tile_rows is None else (tile_rows if "error" in tile_rows else {
-                  "frames_per_s": tile_rows["frames_per_s"], "ms_per_frame": tile_rows["ms_per_frame"],
-                  "bands": tile_rows["bands"], "steps": extra_steps,
-                  "what": "6M Gaussians, 3840x2160, one band of tile rows per rank (bench.py --mode tile_rows)"}),
-              "parity": parity}
-    line = base_line(env, METRIC, fps, "frames/s", ms_render, K, "weak", config)
-    line.update({
-        "single_stream": {"value": world * K / (ms_render_1s * 1e-3), "unit": "frames/s", "ms_per_step": ms_render_1s / K,
-                          "note": "one frame at a time on one stream (frame latency)"},
-        "train": {"with_l1_ssim_loss": {"value": K / (ms_train_loss * 1e-3), "unit": "it/s", "ms_per_step": ms_train_loss / K,
-                                        "step": "build_sigma + evaluate_sh + render + b200gs.compute_loss (fused L1 + SSIM, "
-                                                "losses.py:158) + backward, one GPU's share"}},
-        "e2e": {"value": world * K / s_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 3,
-                "api": "b200gs.evaluate_sh + b200gs.RenderPipeline (pose from pinned host memory in; finished frame "
-                       "delivered to pinned host memory as uint8 through b200gs.to_uint8 - the conversion the reference "
-                       "scripts apply to every frame they keep, render_trained.py:357, bit-identical - 3 B/pixel over PCIe)"},
-        "e2e_f32_frames": {"value": world * K / s_e2e_f32, "unit": "frames/s", "h2d_bytes_per_step": 64,
-                           "d2h_bytes_per_step": H * W * 12,
-                           "api": "the same loop delivering the raw fp32 image (12 B/pixel): PCIe-bound on one GPU and "
-                                  "host-fabric-bound beyond two (profiles/r02_d2h_ceiling.json)"},
-        "e2e_host_buffers": {"value": host_fps, "unit": "frames/s", "h2d_bytes_per_step": 236 * N + 64,
-                             "d2h_bytes_per_step": H * W * 12,
-                             "api": "b200gs_render_host (C ABI, every parameter array uploaded from host memory each call)"},
-        "gpu_launches": int(launches_render),
-        "gpu_launches_train": int(launches_train),
-        "roofline": roofline,
-        "kernels": table,
-        "clocks": clocks,
-        "cpu_baseline": cpu_base,
-        "parity": parity,
-    })
-    emit(line)
+            extras["tile_rows"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        extras["train"] = measure_train_iteration(env, sc, cams, extra_steps, 4, want_nccl=True)
+    if not deadline.cancel():
+        time.sleep(3600)                          # the deadline thread is printing the line and ends the process
+    if rank == 0:
+        emit(build_line(extras["tile_rows"], extras["train"]))
     env.finish()
     return 0
 

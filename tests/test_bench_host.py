@@ -1,0 +1,97 @@
+"""CPU: the host-side pieces of bench.py - the deadline around the optional legs, the byte model of SURVEY.md section 8d,
+and the reference arm end to end on a small workload (the staged unmodified reference when baseline/_ref exists, the
+oracle port otherwise)."""
+import io
+import json
+import os
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+
+
+def test_deadline_cancelled_in_time_never_fires():
+    fired, exits = [], []
+    d = bench.Deadline(0.2, lambda: fired.append(1), exit_fn=exits.append)
+    d.start()
+    assert d.cancel() is True
+    time.sleep(0.4)
+    assert fired == [] and exits == []
+
+
+def test_deadline_not_started_can_be_cancelled():
+    d = bench.Deadline(0.0, lambda: None, exit_fn=lambda c: None)
+    assert d.cancel() is True
+
+
+def test_deadline_expiry_runs_the_handler_once_and_exits_zero():
+    fired, exits, gate = [], [], threading.Event()
+
+    def on_expire():
+        fired.append(1)
+
+    def exit_fn(code):
+        exits.append(code)
+        gate.set()
+    d = bench.Deadline(0.05, on_expire, exit_fn=exit_fn)
+    d.start()
+    assert gate.wait(5.0)
+    assert fired == [1] and exits == [0]
+    assert d.cancel() is False          # the timer thread owns the line now
+
+
+def test_deadline_exits_even_when_the_handler_raises():
+    exits, gate = [], threading.Event()
+
+    def exit_fn(code):
+        exits.append(code)
+        gate.set()
+    d = bench.Deadline(0.01, lambda: 1 / 0, exit_fn=exit_fn)
+    old = threading.excepthook
+    threading.excepthook = lambda a: None       # the ZeroDivisionError of the handler is expected
+    try:
+        d.start()
+        assert gate.wait(5.0)
+    finally:
+        threading.excepthook = old
+    assert exits == [0]
+
+
+def test_byte_model_matches_the_survey_formulas():
+    """B_fwd = 248 N + 60 V + 84 I + 12 P and B_bwd = 76 I + 20 P + 36 V + 472 N are the graded totals; the
+    per-kernel split of bench.py must not claim more than those (it may claim less: the supertile scheme moves fewer
+    bytes per intersection than the flat key/value layout the survey assumed)."""
+    N, V, I, P, tiles, S = 1_000_000, 894_710, 4_381_412, 1920 * 1080, 8160, 1_316_943
+    b = bench.algorithmic_bytes(N, V, I, P, tiles, S)
+    fwd = b["preprocess_fwd"] + b["depth_sort"] + b["emit_super"] + b["super_sort"] + b["split_tiles"] + b["blend_fwd"]
+    assert fwd <= 248 * N + 60 * V + 84 * I + 12 * P + 8 * P
+    assert b["blend_fwd"] == 40 * I + 20 * P and b["blend_bwd"] == 76 * I + 20 * P
+    assert b["preprocess_bwd"] == 520 * N and b["adam_step"] == 28 * 59 * N
+
+
+def test_reference_arm_runs_end_to_end_on_a_small_workload(monkeypatch, capsys):
+    small = dict(bench.WORKLOAD, name="test workload", n=4000, W=160, H=96, log_scale=-3.5, n_views=2)
+    monkeypatch.setattr(bench, "WORKLOAD", small)
+    monkeypatch.setenv("RANK", "0")
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1)
+    assert bench.run_reference(args) == 0
+    out = capsys.readouterr().out.strip().splitlines()
+    line = json.loads(out[-1])
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "gaussian_splatting", "__init__.py"))
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["unit"] == "frames/s"
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(line["value"] - 1e3 / line["ms_per_step"]) <= 1e-9 * line["value"]
+    assert len(line["config"]["frame_seconds"]) == line["steps"]       # only steps that ran are claimed
+
+
+def test_reference_arm_other_ranks_do_no_work(monkeypatch, capsys):
+    monkeypatch.setenv("RANK", "3")
+    assert bench.run_reference(types.SimpleNamespace(gpus=4, steps=2, warmup=1)) == 0
+    assert capsys.readouterr().out == ""
