@@ -884,7 +884,10 @@ def run_mode_render(env, args):
             tr_leg = {"error": "deadline: the tile-row leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"}
         if tn_leg["peer"] is None and tn_leg["nccl"] is None:
             tn_leg["peer_error"] = "deadline: the training leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"
-        emit(build_line(tr_leg, tn_leg))
+        line = build_line(tr_leg, tn_leg)
+        line["config"]["extras_deadline"] = {"tile_rows_finished": extras["tile_rows"] is not None,
+                                             "train": tn_leg["peer_error"]}
+        emit(line)
 
     deadline = Deadline(float(os.environ.get("B200GS_BENCH_EXTRAS_DEADLINE_S", "300")), on_deadline)
     if not args.no_extras:
