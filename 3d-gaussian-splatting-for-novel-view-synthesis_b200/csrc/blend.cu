@@ -216,11 +216,8 @@ cudaError_t launch_blend_fwd(const RenderParams& rp, const void* ws, const Frame
     // and the (high-priority) binning CTAs of the next frame - 46 KB for a radix pass - have to wait until blend
     // CTAs retire.  65 % leaves them room at the price of some L1: 2 175 -> 2 230 pipelined frames/s on the headline
     // workload (50 %: 2 142, 80 %: 2 147, 100 %: 1 832; one frame at a time it costs 0.8 %, hence the second instance).
-    static bool once = false;
-    if (!once) {
-      once = true;
-      cudaFuncSetAttribute(blend_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 65);
-    }
+    static std::atomic<uint64_t> once{0};
+    once_per_device(once, [] { cudaFuncSetAttribute(blend_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 65); });
     blend_fwd_kernel<true><<<grid, kBlendThreads, 0, s>>>(
         rp, ws_ptr<uint2>(ws, L.ranges), vals, ws_ptr<float4>(ws, L.rec0), ws_ptr<float4>(ws, L.rec1),
         ws_ptr<float4>(ws, L.rec2), image, const_cast<float*>(ws_ptr<float>(ws, L.final_T)),

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <atomic>
+
 #include "gs_math.cuh"
 #include "../../include/b200gs.h"
 
@@ -15,6 +17,20 @@ constexpr uint32_t kCulledKey = 0xFFFFFFFFu;
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory, the shared-memory carve-out) belong to the
+// (kernel, device) pair, not to the process: a process that renders on cuda:0 and then on cuda:1 has to set them on both.
+// `mask` is a per-call-site bit set of device ordinals; f() runs before the bit is published, so a second host thread
+// can at worst repeat the (idempotent) attribute call, never launch ahead of it.
+template <class F>
+inline void once_per_device(std::atomic<uint64_t>& mask, F&& f) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return;
+  f();
+  mask.fetch_or(bit, std::memory_order_release);
+}
 
 // ---- streaming loads / stores (read-once data must not pollute L1) ---------------------------------
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {

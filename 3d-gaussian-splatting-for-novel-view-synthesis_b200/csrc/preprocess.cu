@@ -964,12 +964,13 @@ cudaError_t launch_preprocess_fwd(const GaussIn& g, const float* c2w, const Rend
   if (rc && rs && !no_tma && aligned16(g.pos) && aligned16(g.scale_raw) && aligned16(g.q_raw) && aligned16(g.f_dc) &&
       aligned16(g.f_rest) && aligned16(g.opacity_raw)) {
     static int sm_count = 0;
-    if (!sm_count) {
+    static std::atomic<uint64_t> attr_set{0};
+    once_per_device(attr_set, [] {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       cudaFuncSetAttribute(preprocess_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStage));
-    }
+    });
     const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;     // 3 resident CTAs per SM (2 x 30 KB stages each)
     preprocess_fwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStage), s>>>(g, c2w, rp, f, grid, depth_hist, depth_key_plan(rp));
     if (hist_done) *hist_done = depth_hist != nullptr;
@@ -1050,12 +1051,13 @@ cudaError_t launch_preprocess_bwd(const GaussIn& g, const GaussGrad& gg, const f
       aligned16(g.f_rest) && aligned16(g.opacity_raw) && aligned16(gg.pos) && aligned16(gg.scale_raw) &&
       aligned16(gg.q_raw) && aligned16(gg.f_dc) && aligned16(gg.f_rest) && aligned16(gg.opacity_raw)) {
     static int sm_count = 0;
-    if (!sm_count) {
+    static std::atomic<uint64_t> attr_set{0};
+    once_per_device(attr_set, [] {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       cudaFuncSetAttribute(preprocess_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(PreStageBwd));
-    }
+    });
     const int pgrid = grid < 3 * sm_count ? grid : 3 * sm_count;
     preprocess_bwd_tma_kernel<<<pgrid, kPreBlock, 2 * sizeof(PreStageBwd), s>>>(g, gg, c2w, rp, f, grid);
     return cudaGetLastError();

@@ -285,11 +285,10 @@ static RouteParams make_route_params(const b200gs_route* r, const FrameLayout& B
 template <bool META, bool REC>
 static cudaError_t launch_route_write(uint32_t un, const void* slice_ws, const FrameLayout& SL, const RouteParams& p,
                                       uint32_t n_blocks, const uint32_t* counts, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  once_per_device(attr_set, [] {
     cudaFuncSetAttribute(route_write_kernel<META, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteStageBytes);
-    attr_set = true;
-  }
+  });
   route_write_kernel<META, REC><<<(int)n_blocks, kRouteThreads, kRouteStageBytes, s>>>(
       un, ws_ptr<uint32_t>(slice_ws, SL.depth_key), ws_ptr<uint2>(slice_ws, SL.rect), ws_ptr<float4>(slice_ws, SL.rec0),
       ws_ptr<float4>(slice_ws, SL.rec1), ws_ptr<float4>(slice_ws, SL.rec2), p, n_blocks, counts);

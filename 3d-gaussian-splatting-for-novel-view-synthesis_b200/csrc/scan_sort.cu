@@ -777,12 +777,11 @@ cudaError_t launch_radix_sort(const uint32_t* keys_src, const uint32_t* vals_src
     const uint32_t ks = p == 0 ? key_sub : 0u, km = p == 0 ? key_max : 0xFFFFFFFFu;   // later passes read transformed keys
 #define GS_PASS2(B, T, I)                                                                                              \
   do {                                                                                                                 \
-    static bool attr_done = false;                                                                                     \
-    if (!attr_done) {                                                                                                  \
-      attr_done = true;                                                                                                \
+    static std::atomic<uint64_t> attr_done{0};                                                                         \
+    once_per_device(attr_done, [] {                                                                                    \
       cudaFuncSetAttribute(onesweep_pass2_kernel<B, T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
                            (int)pass2_smem_bytes<B, T, I>());                                                          \
-    }                                                                                                                  \
+    });                                                                                                                \
     onesweep_pass2_kernel<B, T, I><<<(int)grid, T, pass2_smem_bytes<B, T, I>(), s>>>(                                  \
         ki, vi, ko, vo, n, n_dev, sp.shift[p], sp.bits[p], ghist + p * kMaxRadix, status, tickets + p, ks, km);        \
   } while (0)
