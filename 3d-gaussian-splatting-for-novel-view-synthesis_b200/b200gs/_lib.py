@@ -52,6 +52,7 @@ class AdamTensor(Structure):
 
 MAX_PEERS = 16
 PEER_MAX_TENSORS = 8
+CLIP_MAX_TENSORS = 16          # B200GS_CLIP_MAX_TENSORS
 PEER_CTRL_BYTES = 4096
 
 
@@ -107,6 +108,8 @@ SYMBOLS = {
     "b200gs_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_double, c_double, c_double, c_void_p]),
     "b200gs_clip_workspace_bytes": (c_size_t, [ctypes.c_int64]),
     "b200gs_clip_grad_norm": (c_int, [c_void_p, ctypes.c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b200gs_clip_workspace_bytes_multi": (c_size_t, [c_void_p, c_int32]),
+    "b200gs_clip_grad_norm_multi": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200gs_densify_workspace_bytes": (c_size_t, [c_int32]),
     "b200gs_densify_plan": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p, c_size_t,
                                     c_void_p, c_void_p]),

@@ -76,7 +76,7 @@ _clip_ws = {}
 def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=False, foreach=None):
     """torch.nn.utils.clip_grad_norm_ for CUDA fp32 gradients (L2 norm), no host sync.  Returns the total norm
     as a 0-dim device tensor.  One tensor (the reference clips `model.pos` only) is a norm kernel + an in-place
-    scale; several tensors are clipped by their joint norm like torch does."""
+    scale; several tensors are clipped by their joint norm like torch does, by the same two kernels."""
     if float(norm_type) != 2.0 or error_if_nonfinite:
         raise NotImplementedError("b200gs.clip_grad_norm_ implements the L2 norm without error_if_nonfinite")
     if isinstance(parameters, torch.Tensor):
@@ -88,16 +88,17 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=Fals
     for g in grads:
         if not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous():
             raise _lib.B200GSError("b200gs.clip_grad_norm_: gradients must be contiguous CUDA fp32 tensors")
-    if len(grads) > 1:       # joint norm over several tensors: flatten views are not contiguous in general -> torch ops
-        norms = torch.stack([torch.linalg.vector_norm(g) for g in grads])
-        total = torch.linalg.vector_norm(norms)
-        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
-        for g in grads:
-            g.mul_(coef)
-        return total
-    g = grads[0]
-    dev = g.device
-    nbytes = int(lib.b200gs_clip_workspace_bytes(g.numel()))
+    dev = grads[0].device
+    if any(g.device != dev for g in grads):
+        raise _lib.B200GSError("b200gs.clip_grad_norm_: all gradients must live on one device")
+    if len(grads) > _lib.CLIP_MAX_TENSORS:
+        raise NotImplementedError(f"b200gs.clip_grad_norm_ clips at most {_lib.CLIP_MAX_TENSORS} tensors per call "
+                                  f"(got {len(grads)})")
+    # one tensor (the reference: model.pos) or several: the same two kernels (sum of squares over all tensors with the
+    # coefficient computed by the last block, then one in-place scale), the tensors given as a table of pointers
+    ptrs = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    numels = (ctypes.c_int64 * len(grads))(*[g.numel() for g in grads])
+    nbytes = int(lib.b200gs_clip_workspace_bytes_multi(numels, len(grads)))
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _clip_ws.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -105,6 +106,6 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=Fals
         _clip_ws[key] = ws
     total = torch.empty((), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.b200gs_clip_grad_norm(ops._ptr(g), g.numel(), float(max_norm), ops._ptr(ws), ws.numel(),
-                                             ops._ptr(total), ops._stream(dev)), "clip_grad_norm")
+        _lib.check(lib.b200gs_clip_grad_norm_multi(ptrs, numels, len(grads), float(max_norm), ops._ptr(ws), ws.numel(),
+                                                   ops._ptr(total), ops._stream(dev)), "clip_grad_norm")
     return total

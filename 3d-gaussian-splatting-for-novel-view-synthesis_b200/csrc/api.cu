@@ -355,6 +355,27 @@ int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* wor
   return B200GS_OK;
 }
 
+size_t b200gs_clip_workspace_bytes_multi(const int64_t* numel, int32_t n_tensors) {
+  if (!numel || n_tensors <= 0) return gs::clip_workspace_bytes(0);
+  return gs::clip_workspace_bytes_multi(numel, n_tensors);
+}
+
+int b200gs_clip_grad_norm_multi(float* const* grads, const int64_t* numel, int32_t n_tensors, double max_norm,
+                                void* workspace, size_t workspace_bytes, float* total_norm_out, void* stream) {
+  if (n_tensors < 0 || (n_tensors > 0 && (!grads || !numel))) return fail(B200GS_ERR_ARG, "clip_grad_norm_multi: null table");
+  int live = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (numel[i] < 0 || (numel[i] > 0 && !grads[i])) return fail(B200GS_ERR_ARG, "clip_grad_norm_multi: numel < 0 or null tensor");
+    live += numel[i] > 0;
+  }
+  if (live > B200GS_CLIP_MAX_TENSORS) return fail(B200GS_ERR_ARG, "clip_grad_norm_multi: more than B200GS_CLIP_MAX_TENSORS tensors");
+  if (live > 0 && (!workspace || workspace_bytes < gs::clip_workspace_bytes_multi(numel, n_tensors)))
+    return fail(B200GS_ERR_WORKSPACE, "clip_grad_norm_multi: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  PCU(R_CLIP, 2, gs::launch_clip_grad_norm_multi(grads, numel, n_tensors, max_norm, workspace, total_norm_out, s));
+  return B200GS_OK;
+}
+
 size_t b200gs_densify_workspace_bytes(int32_t n) { return gs::densify_workspace_bytes(n); }
 
 int b200gs_densify_plan(int32_t n, const float* opacity_raw, const float* scale_raw, const float* pos_grad,

@@ -267,6 +267,9 @@ cudaError_t launch_fill_list_tiles(const uint2* ranges, int n_tiles, uint32_t co
 cudaError_t launch_adam_step(const b200gs_adam_tensor* tensors, int n_tensors, double beta1, double beta2, double eps,
                              cudaStream_t s);
 size_t clip_workspace_bytes(long long numel);
+size_t clip_workspace_bytes_multi(const int64_t* numel, int n_tensors);
+cudaError_t launch_clip_grad_norm_multi(float* const* grads, const int64_t* numel, int n_tensors, double max_norm, void* ws,
+                                        float* total_norm_out, cudaStream_t s);
 cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
                                   cudaStream_t s);
 

@@ -109,23 +109,52 @@ cudaError_t launch_adam_step(const b200gs_adam_tensor* tensors, int n_tensors, d
   return cudaSuccess;
 }
 
-// ---- clip_grad_norm_ (torch/nn/utils/clip_grad.py): total_norm = ||g||_2, g *= min(1, max_norm / (total_norm + 1e-6)) ----
+// ---- clip_grad_norm_ (torch/nn/utils/clip_grad.py): total_norm = ||(g_1, ..., g_k)||_2 over ALL the tensors of the call,
+//      every g_i *= min(1, max_norm / (total_norm + 1e-6)).  The reference clips one tensor (scripts/train.py:536:
+//      model.pos); several tensors go through the same two kernels with a table of pointers, like adam_step. ----
 constexpr int kClipThreads = 256;
 constexpr int kClipChunk = kClipThreads * 16;
+constexpr int kClipMaxTensors = B200GS_CLIP_MAX_TENSORS;
 
-size_t clip_workspace_bytes(long long numel) {
-  const size_t blocks = (size_t)((numel + kClipChunk - 1) / kClipChunk) + 1;
-  return 256 + align_up(blocks * sizeof(float), 256);
+struct ClipTensor {
+  float* g;
+  long long n;
+  int block_begin;                 // first block of this tensor
+};
+struct ClipTable {
+  ClipTensor t[kClipMaxTensors];
+  int n_tensors;
+};
+
+static size_t clip_blocks(long long numel) { return (size_t)((numel + kClipChunk - 1) / kClipChunk); }
+
+size_t clip_workspace_bytes(long long numel) { return 256 + align_up((clip_blocks(numel) + 1) * sizeof(float), 256); }
+
+size_t clip_workspace_bytes_multi(const int64_t* numel, int n_tensors) {
+  size_t blocks = 0;
+  for (int i = 0; i < n_tensors; ++i) blocks += clip_blocks(numel[i] > 0 ? numel[i] : 0);
+  return 256 + align_up((blocks + 1) * sizeof(float), 256);
 }
 
-__global__ void __launch_bounds__(kClipThreads) grad_sqnorm_kernel(const float* __restrict__ g, long long n,
+__device__ __forceinline__ const ClipTensor& clip_tensor_of_block(const ClipTable& tb) {
+  int ti = 0;
+#pragma unroll
+  for (int k = 1; k < kClipMaxTensors; ++k)
+    if (k < tb.n_tensors && (int)blockIdx.x >= tb.t[k].block_begin) ti = k;
+  return tb.t[ti];
+}
+
+__global__ void __launch_bounds__(kClipThreads) grad_sqnorm_kernel(const __grid_constant__ ClipTable tb,
                                                                    float* __restrict__ partials, uint32_t* ticket,
                                                                    float* __restrict__ coef, float* __restrict__ total_norm,
                                                                    float max_norm) {
   __shared__ float s_w[kClipThreads / 32];
   __shared__ double s_d[kClipThreads / 32];
   __shared__ bool s_last;
-  const long long base = (long long)blockIdx.x * kClipChunk;
+  const ClipTensor& t = clip_tensor_of_block(tb);
+  const float* __restrict__ g = t.g;
+  const long long n = t.n;
+  const long long base = (long long)((int)blockIdx.x - t.block_begin) * kClipChunk;
   float acc = 0.f;
 #pragma unroll 4
   for (int k = 0; k < 16; ++k) {
@@ -165,11 +194,14 @@ __global__ void __launch_bounds__(kClipThreads) grad_sqnorm_kernel(const float* 
   }
 }
 
-__global__ void __launch_bounds__(kClipThreads) grad_scale_kernel(float* __restrict__ g, long long n,
+__global__ void __launch_bounds__(kClipThreads) grad_scale_kernel(const __grid_constant__ ClipTable tb,
                                                                   const float* __restrict__ coef) {
   const float c = *coef;
-  if (c == 1.f) return;                                // nothing to clip: leave the gradient bit-for-bit alone
-  const long long base = (long long)blockIdx.x * kClipChunk;
+  if (c == 1.f) return;                                // nothing to clip: leave the gradients bit-for-bit alone
+  const ClipTensor& t = clip_tensor_of_block(tb);
+  float* __restrict__ g = t.g;
+  const long long n = t.n;
+  const long long base = (long long)((int)blockIdx.x - t.block_begin) * kClipChunk;
 #pragma unroll 4
   for (int k = 0; k < 16; ++k) {
     const long long i = base + k * kClipThreads + threadIdx.x;
@@ -177,9 +209,22 @@ __global__ void __launch_bounds__(kClipThreads) grad_scale_kernel(float* __restr
   }
 }
 
-cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
-                                  cudaStream_t s) {
-  if (numel <= 0) {
+cudaError_t launch_clip_grad_norm_multi(float* const* grads, const int64_t* numel, int n_tensors, double max_norm, void* ws,
+                                        float* total_norm_out, cudaStream_t s) {
+  ClipTable tb;
+  tb.n_tensors = 0;
+  size_t blocks = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (numel[i] <= 0) continue;                       // an empty tensor adds nothing to the norm
+    if (tb.n_tensors == kClipMaxTensors) return cudaErrorInvalidValue;
+    ClipTensor& t = tb.t[tb.n_tensors++];
+    t.g = grads[i];
+    t.n = numel[i];
+    t.block_begin = (int)blocks;
+    blocks += clip_blocks(numel[i]);
+  }
+  for (int k = tb.n_tensors; k < kClipMaxTensors; ++k) tb.t[k] = ClipTensor{nullptr, 0, 0x7fffffff};
+  if (blocks == 0) {
     if (total_norm_out) return cudaMemsetAsync(total_norm_out, 0, sizeof(float), s);
     return cudaSuccess;
   }
@@ -188,10 +233,15 @@ cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm,
   float* partials = ws_ptr<float>(ws, 256);
   cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
   if (e != cudaSuccess) return e;
-  const unsigned blocks = (unsigned)((numel + kClipChunk - 1) / kClipChunk);
-  grad_sqnorm_kernel<<<blocks, kClipThreads, 0, s>>>(grad, numel, partials, ticket, coef, total_norm_out, (float)max_norm);
-  grad_scale_kernel<<<blocks, kClipThreads, 0, s>>>(grad, numel, coef);
+  grad_sqnorm_kernel<<<(unsigned)blocks, kClipThreads, 0, s>>>(tb, partials, ticket, coef, total_norm_out, (float)max_norm);
+  grad_scale_kernel<<<(unsigned)blocks, kClipThreads, 0, s>>>(tb, coef);
   return cudaGetLastError();
+}
+
+cudaError_t launch_clip_grad_norm(float* grad, long long numel, double max_norm, void* ws, float* total_norm_out,
+                                  cudaStream_t s) {
+  const int64_t n = numel;
+  return launch_clip_grad_norm_multi(&grad, &n, 1, max_norm, ws, total_norm_out, s);
 }
 
 }  // namespace gs

@@ -241,6 +241,14 @@ int b200gs_adam_step(const b200gs_adam_tensor* tensors, int32_t n_tensors, doubl
 size_t b200gs_clip_workspace_bytes(int64_t numel);
 int b200gs_clip_grad_norm(float* grad, int64_t numel, double max_norm, void* workspace, size_t workspace_bytes,
                           float* total_norm_out, void* stream);
+/* The same for SEVERAL gradient tensors, as torch.nn.utils.clip_grad_norm_(parameters, max_norm) takes them: the norm
+ * is the joint L2 norm of all tensors (torch/nn/utils/clip_grad.py: the norm of the per-tensor norms), one coefficient
+ * scales every tensor.  At most B200GS_CLIP_MAX_TENSORS non-empty tensors per call.  workspace:
+ * b200gs_clip_workspace_bytes_multi(numel, n_tensors) bytes, caller-owned. */
+#define B200GS_CLIP_MAX_TENSORS 16
+size_t b200gs_clip_workspace_bytes_multi(const int64_t* numel, int32_t n_tensors);
+int b200gs_clip_grad_norm_multi(float* const* grads, const int64_t* numel, int32_t n_tensors, double max_norm,
+                                void* workspace, size_t workspace_bytes, float* total_norm_out, void* stream);
 
 /* scripts/train.py:89-195  GaussianModel.densify_and_prune (+ _prune_points / _split_points / _clone_points), called
  * every 100 iterations (train.py:544-557): prune rows with sigmoid(opacity_raw) < opacity_threshold; of the kept rows

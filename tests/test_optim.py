@@ -112,6 +112,40 @@ def test_clip_grad_norm_matches_torch(n, scale):
     assert abs(float(t1) - float(t2)) <= 1e-5 * float(t2) and float((c.grad - d.grad).abs().max()) <= 1e-6
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_norm", [0.25, 1e6])
+def test_clip_grad_norm_of_the_six_parameter_tensors_matches_torch(max_norm):
+    """torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm): one joint norm, one coefficient, every tensor
+    scaled - through the table-driven kernels (no torch ops on the way), incl. an empty tensor and odd sizes."""
+    import b200gs
+    g = torch.Generator().manual_seed(11)
+    n = 70_001
+    shapes = [(n, 3), (n,), (n, 3), (n, 45), (n, 3), (n, 4), (0, 3), (5,)]
+    mine = [torch.zeros(s, device="cuda", requires_grad=True) for s in shapes]
+    ref = [torch.zeros(s, device="cuda", requires_grad=True) for s in shapes]
+    for a, b in zip(mine, ref):
+        gr = (torch.randn(a.shape, generator=g) * 1e-3).cuda()
+        a.grad, b.grad = gr.clone(), gr.clone()
+    before = [a.grad.clone() for a in mine]
+    t_mine = b200gs.clip_grad_norm_(mine, max_norm)
+    t_ref = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+    assert t_mine.is_cuda and abs(float(t_mine) - float(t_ref)) <= 2e-6 * float(t_ref)
+    for a, b, g0 in zip(mine, ref, before):
+        if a.numel() == 0:
+            continue
+        if max_norm > float(t_ref):
+            assert torch.equal(a.grad, g0)                               # below the threshold: bit-for-bit untouched
+        assert float((a.grad - b.grad).abs().max()) <= 2e-6 * float(b.grad.abs().max())
+    with pytest.raises(NotImplementedError):
+        b200gs.clip_grad_norm_([_with_grad(3) for _ in range(17)], 1.0)
+
+
+def _with_grad(n):
+    p = torch.zeros(n, device="cuda", requires_grad=True)
+    p.grad = torch.ones(n, device="cuda")
+    return p
+
+
 def test_install_can_swap_the_optimizer(monkeypatch):
     import sys
     import types
