@@ -116,7 +116,7 @@ def test_route_plan_slices_cover_the_gaussians_once(n, world):
 
 def test_two_rank_gloo_allreduce_and_bands():
     world, port = 2, _free_port()
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:        # no fork() of this multi-threaded process
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         out = dict(out)
@@ -185,7 +185,7 @@ def _dp_worker(rank, world, port, out):
 
 def test_dp_launcher_reduces_once_per_iteration_and_keeps_replicas_identical():
     world, port = 2, _free_port()
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:        # no fork() of this multi-threaded process
         out = mgr.dict()
         mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
         out = dict(out)
