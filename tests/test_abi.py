@@ -32,6 +32,35 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200gs_workspace_sizes(-1, 128, 128, 0, sz) != 0
 
 
+def test_argument_checks_answer_before_any_cuda_call():
+    """Error behaviour of the C ABI that does not need a device: bad arguments come back as B200GS_ERR_* codes (no
+    exception crosses the boundary, include/b200gs.h), with a message in b200gs_last_error()."""
+    import ctypes
+    from b200gs import _lib
+    lib = _lib.load()
+    ERR_ARG, ERR_WS = -1, -2
+    # clip_grad_norm_ with several tensors: null table, negative length, a null tensor, too many tensors, small workspace
+    one = (ctypes.c_int64 * 1)(4096)
+    ptr = (ctypes.c_void_p * 1)(0x1000)
+    assert lib.b200gs_clip_grad_norm_multi(None, None, 1, 1.0, None, 0, None, None) == ERR_ARG
+    assert lib.b200gs_clip_grad_norm_multi(ptr, (ctypes.c_int64 * 1)(-1), 1, 1.0, None, 0, None, None) == ERR_ARG
+    assert lib.b200gs_clip_grad_norm_multi((ctypes.c_void_p * 1)(None), one, 1, 1.0, None, 0, None, None) == ERR_ARG
+    many = _lib.CLIP_MAX_TENSORS + 1
+    assert lib.b200gs_clip_grad_norm_multi((ctypes.c_void_p * many)(*[0x1000] * many), (ctypes.c_int64 * many)(*[8] * many),
+                                           many, 1.0, ptr, 1 << 20, None, None) == ERR_ARG
+    assert b"B200GS_CLIP_MAX_TENSORS" in lib.b200gs_last_error()
+    assert lib.b200gs_clip_grad_norm_multi(ptr, one, 1, 1.0, ptr, 16, None, None) == ERR_WS
+    # the workspace grows with the number of blocks and covers the single-tensor size
+    two = (ctypes.c_int64 * 2)(4096, 1)
+    w1, w2 = lib.b200gs_clip_workspace_bytes_multi(one, 1), lib.b200gs_clip_workspace_bytes_multi(two, 2)
+    assert w1 == lib.b200gs_clip_workspace_bytes(4096) and w2 >= w1
+    big = (ctypes.c_int64 * 2)(10_000_000, 10_000_000)
+    assert lib.b200gs_clip_workspace_bytes_multi(big, 2) >= 256 + 4 * (2 * (10_000_000 // 4096) + 1)
+    # the single-tensor entry point and the optimizer step check their arguments the same way
+    assert lib.b200gs_clip_grad_norm(None, 5, 1.0, None, 0, None, None) == ERR_ARG
+    assert lib.b200gs_adam_step(None, 2, 0.9, 0.999, 1e-15, None) == ERR_ARG
+
+
 def test_struct_layouts_match_header():
     import ctypes
     from b200gs import _lib
