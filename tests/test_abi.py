@@ -61,6 +61,49 @@ def test_argument_checks_answer_before_any_cuda_call():
     assert lib.b200gs_adam_step(None, 2, 0.9, 0.999, 1e-15, None) == ERR_ARG
 
 
+def test_render_entry_point_rejects_bad_calls_with_error_codes():
+    """b200gs_render_project (include/b200gs.h; the C side of gaussian_splatting.render.render, render.py:62-64): the
+    argument checks run before the first CUDA call, in the order camera -> Gaussians -> workspace."""
+    import ctypes
+    from b200gs import _lib
+    lib = _lib.load()
+    ERR_ARG, ERR_WS, ERR_TILE = -1, -2, -4
+    P = 0x1000                                   # any non-null, 16-byte aligned address: nothing is dereferenced
+
+    def cam(**kw):
+        c = _lib.Camera(c2w=P, H=64, W=64, fx=50., fy=50., cx=32., cy=32., near_plane=0.01, far_plane=100., pix_guard=32.,
+                        min_conis=1e-6, chi_square_clip=6.25, alpha_max=0.99, alpha_cutoff=1 / 128., tile=16,
+                        tile_row_begin=0, tile_row_end=0, flags=0)
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def gauss(**kw):
+        g = _lib.Gaussians(n=10, pos=P, opacity_raw=P, scale_raw=P, q_raw=P, sigma=None, f_dc=P, f_rest=P, color=None)
+        for k, v in kw.items():
+            setattr(g, k, v)
+        return g
+
+    def call(g, c, ws=P, nbytes=1 << 40):
+        return lib.b200gs_render_project(ctypes.byref(g) if g is not None else None,
+                                         ctypes.byref(c) if c is not None else None, ws, nbytes, None, None)
+    assert call(gauss(), None) == ERR_ARG
+    assert call(gauss(), cam(c2w=None)) == ERR_ARG
+    assert call(gauss(), cam(tile=8)) == ERR_TILE and b"T=16" in lib.b200gs_last_error()     # render(..., T=8)
+    assert call(gauss(), cam(H=0)) == ERR_ARG
+    assert call(None, cam()) == ERR_ARG
+    assert call(gauss(n=-1), cam()) == ERR_ARG
+    assert call(gauss(pos=None), cam()) == ERR_ARG
+    assert call(gauss(scale_raw=None), cam()) == ERR_ARG          # neither (scale_raw, q_raw) nor sigma
+    assert call(gauss(f_dc=None), cam()) == ERR_ARG               # neither (f_dc, f_rest) nor color
+    assert call(gauss(q_raw=P + 4), cam()) == ERR_ARG and b"16-byte" in lib.b200gs_last_error()
+    assert call(gauss(), cam(), ws=None) == ERR_ARG
+    assert call(gauss(), cam(), nbytes=64) == ERR_WS
+    sz = _lib.Sizes()
+    assert lib.b200gs_workspace_sizes(10, 64, 64, 100, sz) == 0
+    assert call(gauss(), cam(), nbytes=sz.frame_bytes - 1) == ERR_WS
+
+
 def test_struct_layouts_match_header():
     import ctypes
     from b200gs import _lib
