@@ -464,6 +464,18 @@ def measure_tile_rows(env, steps, warm):
             "frames_redone": int(redone), "regions_us_per_frame": regions, "variants_ms_per_frame": variants, **stats}
 
 
+def legs_at_deadline(extras: dict):
+    """What the default line reports for the two optional legs when their deadline expires: a finished leg keeps its
+    numbers, an unfinished one is marked (`extras` = {"tile_rows": result or None, "train": measure_train_iteration's
+    dict, all None until it returns})."""
+    tr_leg, tn_leg = extras["tile_rows"], dict(extras["train"])
+    if tr_leg is None:
+        tr_leg = {"error": "deadline: the tile-row leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"}
+    if tn_leg.get("peer") is None and tn_leg.get("nccl") is None:
+        tn_leg["peer_error"] = "deadline: the training leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"
+    return tr_leg, tn_leg
+
+
 def run_b200gs(args):
     env = Env(args)
     if args.mode == "train":
@@ -879,11 +891,7 @@ def run_mode_render(env, args):
     def on_deadline():
         if rank != 0:
             return
-        tr_leg, tn_leg = extras["tile_rows"], dict(extras["train"])
-        if tr_leg is None:
-            tr_leg = {"error": "deadline: the tile-row leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"}
-        if tn_leg["peer"] is None and tn_leg["nccl"] is None:
-            tn_leg["peer_error"] = "deadline: the training leg did not finish (B200GS_BENCH_EXTRAS_DEADLINE_S)"
+        tr_leg, tn_leg = legs_at_deadline(extras)
         line = build_line(tr_leg, tn_leg)
         line["config"]["extras_deadline"] = {"tile_rows_finished": extras["tile_rows"] is not None,
                                              "train": tn_leg["peer_error"]}

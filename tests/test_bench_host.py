@@ -63,6 +63,19 @@ def test_deadline_exits_even_when_the_handler_raises():
     assert exits == [0]
 
 
+def test_legs_at_deadline_keep_finished_numbers_and_mark_the_rest():
+    none = {"peer": None, "nccl": None, "peer_error": None, "peer_transport": None}
+    tr, tn = bench.legs_at_deadline({"tile_rows": None, "train": dict(none)})
+    assert "deadline" in tr["error"] and "deadline" in tn["peer_error"]
+    done_tr = {"ms_per_frame": 2.1, "frames_per_s": 470.0}
+    tr, tn = bench.legs_at_deadline({"tile_rows": done_tr, "train": dict(none)})
+    assert tr is done_tr and "deadline" in tn["peer_error"]
+    done_tn = {"peer": 17.5, "nccl": 18.0, "peer_error": None, "peer_transport": "local"}
+    src = {"tile_rows": done_tr, "train": done_tn}
+    tr, tn = bench.legs_at_deadline(src)
+    assert tn == done_tn and tn is not src["train"]               # a copy: the caller's dict is not edited
+
+
 def test_byte_model_matches_the_survey_formulas():
     """B_fwd = 248 N + 60 V + 84 I + 12 P and B_bwd = 76 I + 20 P + 36 V + 472 N are the graded totals; the
     per-kernel split of bench.py must not claim more than those (it may claim less: the supertile scheme moves fewer
